@@ -1,0 +1,247 @@
+"""Circuit builders written against the *public building API* only.
+
+Every builder takes the package object `hv` -- either the real reference (`heavi`, through
+`oracle/ref_shim.py`, container only) or the product front-end (`heavi_b200`) -- and returns
+`(model, f)` (plus a Monte-Carlo driver where one exists).  Because the same code drives both,
+a golden vector generated from the reference pins node/source indexing, stamp order and S for
+the product.
+
+BASELINE.json configs:  c1 README demo, c2 demo2 Cauer filter set, c3 synthetic 8-port
+Touchstone block, c4 Monte-Carlo Cauer band-pass, c5 ladder/TL network.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SYNTH8 = os.path.join(HERE, "golden", "synth8.snp")
+
+
+def _model(hv):
+    return hv.Model(suppress_loadbar=True)
+
+
+# ---------------------------------------------------------------- config 1 (README.md:34-52)
+def build_c1(hv, nF: int = 2001):
+    smd = hv.lib.smd
+    m = _model(hv)
+    n1 = m.node()
+    m.new_port(50, n1)
+    n2 = m.node()
+    n3 = m.node()
+    m.new_port(50, n3)
+    smd.SMDResistor(5, smd.SMDResistorSize.R0402).connect(n2, n3)
+    m.filters.cauer_filter(m.gnd, n1, n2, 2e9, 70e6, 5, 0.03, hv.FilterType.CHEBYCHEV,
+                           type=hv.BandType.BANDPASS)
+    return m, hv.frange(1.8e9, 2.2e9, nF)
+
+
+# ---------------------------------------------------------------- config 2 (examples/demo2:13-24)
+def build_c2(hv, band: str = "bandpass", nF: int = 100_001):
+    m = _model(hv)
+    n1 = m.quick_port(50)
+    n2 = m.quick_port(50)
+    bt = {"bandpass": hv.BandType.BANDPASS, "lowpass": hv.BandType.LOWPASS,
+          "highpass": hv.BandType.HIGHPASS, "bandstop": hv.BandType.BANDSTOP}[band]
+    m.filters.cauer_filter(m.gnd, n1, n2, 2.5e9, 0.2e9, 5, 0.05, hv.FilterType.CHEBYCHEV, bt, 50)
+    return m, hv.frange(2e9, 3e9, nF)
+
+
+# ---------------------------------------------------------------- config 3
+def synth8_data(nfs: int = 201):
+    """Reciprocal passive synthetic 8-port: S(f) = (Q diag(g e^{-j 2 pi f tau})) Q^T."""
+    rng = np.random.default_rng(1234)
+    fs = np.linspace(0.5e9, 6.5e9, nfs)
+    Q, _ = np.linalg.qr(rng.normal(size=(8, 8)) + 1j * rng.normal(size=(8, 8)))
+    tau = rng.uniform(0.05e-9, 0.4e-9, 8)
+    g = rng.uniform(0.2, 0.7, 8)
+    S = np.empty((nfs, 8, 8), dtype=complex)
+    for k, fk in enumerate(fs):
+        S[k] = (Q * (g * np.exp(-2j * np.pi * fk * tau))) @ Q.T
+    return fs, S
+
+
+def write_synth8(path: str = SYNTH8) -> str:
+    """Touchstone v1, `# hz s ri r 50`, one line per frequency, single-space separated
+    (the reference's parser splits on single spaces only, touchstone.py:204)."""
+    fs, S = synth8_data()
+    with open(path, "w") as fh:
+        fh.write("! synthetic reciprocal passive 8-port, default_rng(1234) (tests/circuits.py)\n")
+        fh.write("# hz s ri r 50\n")
+        for k, fk in enumerate(fs):
+            nums = ["%.17g" % fk]
+            for v in S[k].reshape(-1):
+                nums.append("%.17g" % v.real)
+                nums.append("%.17g" % v.imag)
+            fh.write(" ".join(nums) + "\n")
+    return path
+
+
+def build_c3(hv, nF: int = 1_000_000, path: str = SYNTH8):
+    m = _model(hv)
+    blk = hv.FileBasedNPort(path)
+    inner = [m.node() for _ in range(8)]
+    for k, n in enumerate(inner):
+        sig = m.quick_port(50)
+        mid = m.node()
+        m.inductor(sig, mid, (1.0 + 0.25 * k) * 1e-9)
+        m.capacitor(mid, m.gnd, (0.5 + 0.1 * k) * 1e-12)
+        m.capacitor(mid, n, (2.0 + 0.3 * k) * 1e-12)
+    blk.connect(*inner)
+    return m, np.linspace(1e9, 6e9, nF)
+
+
+# ---------------------------------------------------------------- config 4
+def build_c4(hv, nF: int = 2001):
+    """c1's Cauer band-pass (no SMD part) with every L and C ~ N(v, (0.02 v / 3)^2)."""
+    nominal = _model(hv)
+    a = nominal.quick_port(50)
+    b = nominal.quick_port(50)
+    caps, inds, _ = nominal.filters.cauer_filter(nominal.gnd, a, b, 2e9, 70e6, 5, 0.03,
+                                                 hv.FilterType.CHEBYCHEV, type=hv.BandType.BANDPASS)
+    values = {id(c): c.value for c in caps + inds}
+
+    mc = hv.MonteCarlo()
+    m = _model(hv)
+    p1 = m.quick_port(50)
+    p2 = m.quick_port(50)
+    # same topology, rebuilt component by component in the nominal model's creation order
+    node_map = {id(nominal.gnd): m.gnd, id(a): p1, id(b): p2}
+
+    def mapped(node):
+        key = id(node)
+        if key not in node_map:
+            node_map[key] = m.node()
+        return node_map[key]
+
+    for comp in nominal.components:
+        if id(comp) not in values:
+            continue
+        v = values[id(comp)]
+        rv = mc.gaussian(v, 0.02 * v / 3)
+        n1, n2 = mapped(comp.nodes[0]), mapped(comp.nodes[1])
+        if comp.component_name == "Capacitor":
+            m.capacitor(n1, n2, rv)
+        else:
+            m.inductor(n1, n2, rv)
+    return m, hv.frange(1.8e9, 2.2e9, nF), mc
+
+
+# ---------------------------------------------------------------- config 5
+def build_c5(hv, nF: int = 1_000_000, K: int = 190):
+    rng = np.random.default_rng(2024)
+    m = _model(hv)
+    chain = [m.node() for _ in range(K + 1)]
+    taps = [round(i * K / 7) for i in range(8)]
+    for t in taps:
+        m.new_port(50, chain[t])
+    for k in range(K):
+        if k % 2 == 0:
+            m.inductor(chain[k], chain[k + 1], 10 ** rng.uniform(np.log10(0.5e-9), np.log10(5e-9)))
+        else:
+            m.transmissionline(chain[k], chain[k + 1], rng.uniform(30, 90), rng.uniform(2, 4),
+                               rng.uniform(1e-3, 10e-3))
+        if k % 5 == 0:
+            m.resistor(chain[k], chain[k + 1], rng.uniform(200, 2000))
+    for k in range(K + 1):
+        m.capacitor(chain[k], m.gnd, 10 ** rng.uniform(np.log10(0.1e-12), np.log10(2e-12)))
+        if k % 3 == 0:
+            m.resistor(chain[k], m.gnd, rng.uniform(500, 5000))
+    return m, np.linspace(0.5e9, 6e9, nF)
+
+
+# ---------------------------------------------------------------- analytic known answers
+def build_divider(hv):
+    """10 ohm series resistor between a 50 ohm and a 75 ohm port."""
+    m = _model(hv)
+    a = m.quick_port(50)
+    b = m.quick_port(75)
+    m.resistor(a, b, 10.0)
+    return m, np.array([1e6, 1e9, 3e9])
+
+
+def build_matched_line(hv, Z0=50.0, er=2.2, length=0.0123):
+    m = _model(hv)
+    a = m.quick_port(Z0)
+    b = m.quick_port(Z0)
+    m.transmissionline(a, b, Z0, er, length)
+    return m, np.linspace(0.2e9, 9e9, 64)
+
+
+# ---------------------------------------------------------------- seeded random family
+_KINDS = ("resistor", "capacitor", "inductor", "impedance", "admittance", "tline", "tline_lossy",
+          "nport2", "impedance_fn", "self_loop")
+
+
+def build_random(hv, seed: int):
+    """Small random connected circuit exercising every stamp class and the quirks of App. A/B:
+    callable parameters, lossy lines (complex er), an N-port S block with analytic callables,
+    a port referenced to a non-ground node, a merged node and a same-node ("self loop") part."""
+    rng = np.random.default_rng(10_000 + seed)
+    m = _model(hv)
+    n_nodes = int(rng.integers(2, 8))
+    n_ports = int(rng.integers(1, 4))
+    nodes = [m.node() for _ in range(n_nodes)]
+    if seed % 5 == 3 and n_nodes > 3:
+        extra = m.node()
+        extra > nodes[1]              # merge: `extra` becomes an alias of nodes[1] (node.py:101-106)
+        nodes.append(extra)
+    port_nodes = list(rng.choice(n_nodes, size=min(n_ports, n_nodes), replace=False))
+    for q, pn in enumerate(port_nodes):
+        z0 = float(rng.choice([25.0, 50.0, 75.0, 100.0]))
+        if seed % 7 == 2 and q == 0 and n_nodes > 2:
+            ref = nodes[(pn + 1) % n_nodes]           # port against a non-ground reference node
+            m.new_port(z0, nodes[pn], ref)
+            m.resistor(ref, m.gnd, float(rng.uniform(5, 50)))
+        else:
+            m.new_port(z0, nodes[pn])
+
+    def pick2():
+        i, j = rng.choice(len(nodes) + 1, size=2, replace=False)
+        pool = nodes + [m.gnd]
+        return pool[i], pool[j]
+
+    # spanning chain keeps every node attached to something
+    for k in range(len(nodes) - 1):
+        m.inductor(nodes[k], nodes[k + 1], float(10 ** rng.uniform(-9.5, -8)))
+    for k in range(len(nodes)):
+        m.capacitor(nodes[k], m.gnd, float(10 ** rng.uniform(-12.5, -11.5)))
+    for _ in range(int(rng.integers(2, 9))):
+        kind = _KINDS[int(rng.integers(0, len(_KINDS)))]
+        a, b = pick2()
+        if kind == "resistor":
+            m.resistor(a, b, float(rng.uniform(5, 500)))
+        elif kind == "capacitor":
+            m.capacitor(a, b, float(10 ** rng.uniform(-13, -11)))
+        elif kind == "inductor":
+            m.inductor(a, b, float(10 ** rng.uniform(-10, -8)))
+        elif kind == "impedance":
+            m.impedance(a, b, complex(rng.uniform(5, 200), rng.uniform(-100, 100)))
+        elif kind == "admittance":
+            m.admittance(a, b, complex(rng.uniform(1e-3, 5e-2), rng.uniform(-2e-2, 2e-2)))
+        elif kind == "tline":
+            m.transmissionline(a, b, float(rng.uniform(30, 90)), float(rng.uniform(1, 5)),
+                               float(rng.uniform(2e-3, 30e-3)))
+        elif kind == "tline_lossy":
+            m.transmissionline(a, b, float(rng.uniform(30, 90)),
+                               complex(rng.uniform(2, 4), -rng.uniform(0.01, 0.1)),
+                               float(rng.uniform(2e-3, 30e-3)))
+        elif kind == "nport2":
+            tau = float(rng.uniform(0.05e-9, 0.3e-9))
+            r = float(rng.uniform(0.05, 0.4))
+            t = float(rng.uniform(0.3, 0.8))
+            s11 = lambda f, r=r, tau=tau: r * np.exp(-2j * np.pi * f * tau * 0.5)
+            s21 = lambda f, t=t, tau=tau: t * np.exp(-2j * np.pi * f * tau)
+            s12 = lambda f, t=t, tau=tau: 0.5 * t * np.exp(-2j * np.pi * f * tau)   # non-reciprocal
+            s22 = lambda f, r=r: r * np.ones_like(f) + 0j
+            m.n_port_S(m.gnd, [a, b], [[s11, s12], [s21, s22]], float(rng.choice([50.0, 75.0])))
+        elif kind == "impedance_fn":
+            R, L, C = float(rng.uniform(1, 100)), float(10 ** rng.uniform(-10, -9)), float(10 ** rng.uniform(-13, -12))
+            m.impedance(a, b, lambda f, R=R, L=L, C=C: R + 2j * np.pi * f * L + 1 / (2j * np.pi * f * C))
+        elif kind == "self_loop":
+            # both terminals on one node: numpy `+=` keeps the last write only (App. A)
+            m.resistor(a, a, float(rng.uniform(20, 200)))
+    f = np.sort(rng.uniform(0.3e9, 8e9, size=int(rng.integers(3, 9))))
+    return m, f
