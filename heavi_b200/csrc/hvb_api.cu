@@ -1,0 +1,455 @@
+// hvb_api.cu -- the C-ABI of libheavi_b200.so (include/heavi_b200.h): plan lifetime, kernel
+// selection, the device-buffer entry (hvb_run_device) and the host-buffer pipeline (hvb_run_host).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/heavi_b200.h"
+#include "hvb_device.cuh"
+#include "hvb_kernels.h"
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(HVB_ERR_CUDA, "%s -> %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" const char* hvb_last_error(void) { return g_err.c_str(); }
+extern "C" const char* hvb_version(void) { return "heavi_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need ? need : 16);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+struct hvb_plan {
+    int device = 0;
+    hvb_plan_desc d{};
+    // device copies of the static plan arrays
+    DevBuf const_vals, ops, coops, cell_ptr, cell_ent, port_rows, port_zpref, spl_t, spl_c, spl_trace, spl_fill, spl_range;
+    // per-run parameter buffers (device) + pinned staging
+    DevBuf consts, prefs;
+    void* h_stage = nullptr; size_t h_stage_bytes = 0;
+    // host pipeline buffers
+    DevBuf f, samples, tables, S[2], status, work, dump;
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t upload_done = nullptr;
+    // kernel choice
+    int kclass = 0, G = 0, PMAX = 0, NB = 0, threads = 0, ctas_per_sm = 0, sm_count = 0, regs = 0;
+    size_t smem = 0;
+    int region_a = 0, region_b = 0;
+    const void* kernel = nullptr;
+    int max_grid = 0;
+    int64_t launches = 0;
+};
+
+static cudaError_t upload(DevBuf& b, const void* src, size_t bytes) {
+    cudaError_t e = b.ensure(bytes);
+    if (e != cudaSuccess) return e;
+    if (bytes) e = cudaMemcpy(b.p, src, bytes, cudaMemcpyHostToDevice);
+    return e;
+}
+
+static int pick_pmax(int P) {
+    const int opts[4] = {2, 4, 8, 16};
+    for (int o : opts) if (P <= o) return o;
+    return 0;
+}
+
+static int select_kernel(hvb_plan* pl) {
+    const hvb_plan_desc& d = pl->d;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, pl->device));
+    pl->sm_count = prop.multiProcessorCount;
+    int max_nport = 0;
+    {
+        // cooperative ops need one lane per N-port row
+        std::vector<int32_t> co((size_t)d.n_coops * HVB_COOP_WORDS);
+        if (d.n_coops) CU(cudaMemcpy(co.data(), pl->coops.p, co.size() * 4, cudaMemcpyDeviceToHost));
+        for (int o = 0; o < d.n_coops; ++o) max_nport = std::max(max_nport, (int)co[(size_t)o * HVB_COOP_WORDS + 2]);
+    }
+    if (max_nport > HVB_MAX_NPORT) return fail(HVB_ERR_UNSUPPORTED, "N-port block with %d ports (max %d)", max_nport, HVB_MAX_NPORT);
+    const int P = d.P;
+    const int need = std::max(d.n, max_nport);
+    const char* force = getenv("HVB_FORCE_BLOCK");
+    const int pmax = pick_pmax(P);
+    pl->region_a = std::max(std::max(d.n_dyn, d.n * P), 1);
+    if (need <= 32 && pmax > 0 && !(force && force[0] == '1')) {
+        int G = 4;
+        while (G < need) G *= 2;
+        pl->kclass = 0; pl->G = G; pl->PMAX = pmax;
+        switch (G) {
+            case 4: pl->kernel = hvb_warp_kernel_ptr_g4(pmax); break;
+            case 8: pl->kernel = hvb_warp_kernel_ptr_g8(pmax); break;
+            case 16: pl->kernel = hvb_warp_kernel_ptr_g16(pmax); break;
+            default: pl->kernel = hvb_warp_kernel_ptr_g32(pmax); break;
+        }
+        pl->threads = hvb_warp_threads();
+        pl->region_b = std::max(d.coop_scratch, 2 * (G + pmax));
+        const int sys_per_block = (pl->threads / 32) * (32 / G);
+        pl->smem = (size_t)sys_per_block * (pl->region_a + pl->region_b) * sizeof(cplx);
+    } else {
+        pl->kclass = 1;
+        const char* nbs = getenv("HVB_BLOCK_NB");
+        pl->NB = (nbs && atoi(nbs) == 8) ? 8 : 16;
+        pl->region_b = std::max(d.coop_scratch, 1);
+        pl->threads = hvb_block_threads();
+        pl->smem = hvb_block_smem_bytes(pl->NB, d.n, d.ncols, pl->region_a, pl->region_b);
+        if (pl->smem > (size_t)prop.sharedMemPerBlockOptin && pl->NB == 16) {
+            pl->NB = 8;
+            pl->smem = hvb_block_smem_bytes(pl->NB, d.n, d.ncols, pl->region_a, pl->region_b);
+        }
+        pl->kernel = hvb_block_kernel_ptr(pl->NB);
+    }
+    if (!pl->kernel) return fail(HVB_ERR_UNSUPPORTED, "no kernel for n=%d P=%d", d.n, P);
+    if (pl->smem > (size_t)prop.sharedMemPerBlockOptin)
+        return fail(HVB_ERR_UNSUPPORTED, "system too large: needs %zu bytes of shared memory per CTA (max %zu)", pl->smem,
+                    (size_t)prop.sharedMemPerBlockOptin);
+    CU(cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, pl->kernel));
+    pl->regs = fa.numRegs;
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pl->kernel, pl->threads, pl->smem));
+    if (occ < 1) return fail(HVB_ERR_UNSUPPORTED, "kernel does not fit on an SM (smem %zu, regs %d)", pl->smem, pl->regs);
+    pl->ctas_per_sm = occ;
+    pl->max_grid = occ * pl->sm_count;
+    if (pl->kclass == 1) {
+        const char* cps = getenv("HVB_BLOCK_CTAS_PER_SM");
+        if (cps && atoi(cps) > 0) pl->max_grid = std::min(pl->max_grid, atoi(cps) * pl->sm_count);
+        CU(pl->work.ensure((size_t)pl->max_grid * d.n * d.ncols * sizeof(cplx)));
+    }
+    return HVB_OK;
+}
+
+extern "C" int hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan** out) {
+    if (!desc || !out) return fail(HVB_ERR_ARG, "null argument");
+    if (desc->n < 1 || desc->ncols < desc->n || desc->P < 0) return fail(HVB_ERR_ARG, "bad sizes n=%d ncols=%d P=%d", desc->n, desc->ncols, desc->P);
+    CU(cudaSetDevice(device));
+    hvb_plan* pl = new hvb_plan();
+    pl->device = device;
+    pl->d = *desc;
+    const hvb_plan_desc& d = *desc;
+    const int ncell = d.n * d.ncols;
+    const int nnz = d.cell_ptr[ncell];
+    cudaError_t e = cudaSuccess;
+    auto up = [&](DevBuf& b, const void* src, size_t bytes) { if (e == cudaSuccess) e = upload(b, src, bytes); };
+    up(pl->const_vals, d.const_vals, (size_t)d.n_const_vals * 16);
+    up(pl->ops, d.ops, (size_t)d.n_ops * HVB_OP_WORDS * 4);
+    up(pl->coops, d.coops, (size_t)d.n_coops * HVB_COOP_WORDS * 4);
+    up(pl->cell_ptr, d.cell_ptr, (size_t)(ncell + 1) * 4);
+    up(pl->cell_ent, d.cell_ent, (size_t)nnz * 4);
+    up(pl->port_rows, d.port_rows, (size_t)d.P * 3 * 4);
+    up(pl->port_zpref, d.port_zpref, (size_t)d.P * 4);
+    up(pl->spl_t, d.spl_t, (size_t)d.n_knots * 8);
+    up(pl->spl_c, d.spl_c, (size_t)d.n_coefs * 16);
+    up(pl->spl_trace, d.spl_trace, (size_t)d.n_traces * 16);
+    up(pl->spl_fill, d.spl_fill, (size_t)d.n_traces * 32);
+    up(pl->spl_range, d.spl_range, (size_t)d.n_traces * 16);
+    if (e == cudaSuccess) e = pl->consts.ensure((size_t)std::max(d.n_consts, 1) * 16);
+    if (e == cudaSuccess) e = pl->prefs.ensure((size_t)std::max(d.n_prefs, 1) * 8);
+    if (e == cudaSuccess) e = pl->status.ensure(16);
+    pl->h_stage_bytes = (size_t)std::max(d.n_consts, 1) * 16 + (size_t)std::max(d.n_prefs, 1) * 8;
+    if (e == cudaSuccess) e = cudaMallocHost(&pl->h_stage, pl->h_stage_bytes);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->streams[0], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->streams[1], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->upload_done, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        hvb_plan_destroy(pl);
+        return fail(HVB_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(e));
+    }
+    // the descriptor's host pointers are not kept
+    pl->d.const_vals = nullptr; pl->d.ops = nullptr; pl->d.coops = nullptr; pl->d.cell_ptr = nullptr; pl->d.cell_ent = nullptr;
+    pl->d.port_rows = nullptr; pl->d.port_zpref = nullptr; pl->d.spl_t = nullptr; pl->d.spl_c = nullptr; pl->d.spl_trace = nullptr;
+    pl->d.spl_fill = nullptr; pl->d.spl_range = nullptr;
+    if (d.ncols == d.n + d.P) {                 // dump-only plans (no right-hand sides) never solve
+        int rc = select_kernel(pl);
+        if (rc != HVB_OK) { hvb_plan_destroy(pl); return rc; }
+    }
+    *out = pl;
+    return HVB_OK;
+}
+
+extern "C" void hvb_plan_destroy(hvb_plan* pl) {
+    if (!pl) return;
+    cudaSetDevice(pl->device);
+    DevBuf* all[] = {&pl->const_vals, &pl->ops, &pl->coops, &pl->cell_ptr, &pl->cell_ent, &pl->port_rows, &pl->port_zpref,
+                     &pl->spl_t, &pl->spl_c, &pl->spl_trace, &pl->spl_fill, &pl->spl_range, &pl->consts, &pl->prefs,
+                     &pl->f, &pl->samples, &pl->tables, &pl->S[0], &pl->S[1], &pl->status, &pl->work, &pl->dump};
+    for (DevBuf* b : all) b->release();
+    if (pl->h_stage) cudaFreeHost(pl->h_stage);
+    for (int i = 0; i < 2; ++i) if (pl->streams[i]) cudaStreamDestroy(pl->streams[i]);
+    if (pl->upload_done) cudaEventDestroy(pl->upload_done);
+    delete pl;
+}
+
+static HvbDev make_dev(const hvb_plan* pl) {
+    HvbDev D{};
+    const hvb_plan_desc& d = pl->d;
+    D.n = d.n; D.ncols = d.ncols; D.P = d.P;
+    D.nvc = d.n_const_vals; D.ndyn = d.n_dyn; D.nops = d.n_ops; D.ncoops = d.n_coops; D.nR = d.n_samples_cols;
+    D.coop_scratch = d.coop_scratch;
+    D.region_a = pl->region_a; D.region_b = pl->region_b;
+    D.consts = (const cplx*)pl->consts.p;
+    D.prefs = (const int2*)pl->prefs.p;
+    D.const_vals = (const cplx*)pl->const_vals.p;
+    D.ops = (const int*)pl->ops.p;
+    D.coops = (const int*)pl->coops.p;
+    D.cell_ptr = (const int*)pl->cell_ptr.p;
+    D.cell_ent = (const int*)pl->cell_ent.p;
+    D.port_rows = (const int*)pl->port_rows.p;
+    D.port_zpref = (const int*)pl->port_zpref.p;
+    D.spl_t = (const double*)pl->spl_t.p;
+    D.spl_c = (const cplx*)pl->spl_c.p;
+    D.spl_trace = (const int4*)pl->spl_trace.p;
+    D.spl_fill = (const cplx*)pl->spl_fill.p;
+    D.spl_range = (const double2*)pl->spl_range.p;
+    D.W = (cplx*)pl->work.p;
+    return D;
+}
+
+// stage consts + prefs through pinned memory so the copy is stream-ordered
+static int push_params(hvb_plan* pl, const hvb_run_args* a, cudaStream_t st) {
+    const hvb_plan_desc& d = pl->d;
+    const size_t cb = (size_t)d.n_consts * 16, pb = (size_t)d.n_prefs * 8;
+    if ((cb && !a->consts) || (pb && !a->prefs)) return fail(HVB_ERR_ARG, "consts/prefs missing");
+    // the previous run's copy out of the staging buffer must have finished
+    CU(cudaEventSynchronize(pl->upload_done));
+    char* hs = (char*)pl->h_stage;
+    if (cb) memcpy(hs, a->consts, cb);
+    if (pb) memcpy(hs + (size_t)std::max(d.n_consts, 1) * 16, a->prefs, pb);
+    if (cb) CU(cudaMemcpyAsync(pl->consts.p, hs, cb, cudaMemcpyHostToDevice, st));
+    if (pb) CU(cudaMemcpyAsync(pl->prefs.p, hs + (size_t)std::max(d.n_consts, 1) * 16, pb, cudaMemcpyHostToDevice, st));
+    CU(cudaEventRecord(pl->upload_done, st));
+    return HVB_OK;
+}
+
+static int launch(hvb_plan* pl, HvbDev& D, cudaStream_t st) {
+    const long long total = D.nS * D.nF;
+    if (total <= 0) return HVB_OK;
+    long long blocks;
+    if (pl->kclass == 0) {
+        const int spb = (pl->threads / 32) * (32 / pl->G);
+        blocks = (total + spb - 1) / spb;
+    } else {
+        blocks = total;
+    }
+    const int grid = (int)std::min<long long>(blocks, pl->max_grid);
+    void* args[] = {&D};
+    CU(cudaLaunchKernel(pl->kernel, dim3(grid), dim3(pl->threads), args, pl->smem, st));
+    pl->launches++;
+    return HVB_OK;
+}
+
+static int check_args(const hvb_plan* pl, const hvb_run_args* a) {
+    if (!pl || !a) return fail(HVB_ERR_ARG, "null argument");
+    if (a->nF < 0 || a->nS < 1) return fail(HVB_ERR_ARG, "bad nF=%lld nS=%lld", (long long)a->nF, (long long)a->nS);
+    if (pl->d.n_samples_cols > 0 && !a->samples) return fail(HVB_ERR_ARG, "plan has %d sample columns but samples is NULL", pl->d.n_samples_cols);
+    if (a->n_tables > 0 && !a->tables) return fail(HVB_ERR_ARG, "tables missing");
+    return HVB_OK;
+}
+
+extern "C" int hvb_run_device(hvb_plan* pl, const hvb_run_args* a, double* d_S, int64_t ldS, int32_t* d_status, void* stream) {
+    int rc = check_args(pl, a);
+    if (rc) return rc;
+    if (pl->d.ncols != pl->d.n + pl->d.P) return fail(HVB_ERR_ARG, "plan has no right-hand sides (dump plan)");
+    CU(cudaSetDevice(pl->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = push_params(pl, a, st);
+    if (rc) return rc;
+    HvbDev D = make_dev(pl);
+    D.nF = a->nF; D.nS = a->nS; D.ldS = ldS; D.table_ld = a->nF;
+    D.f = a->f; D.samples = a->samples; D.tables = (const cplx*)a->tables;
+    D.S = (cplx*)d_S; D.status = d_status;
+    return launch(pl, D, st);
+}
+
+extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, int32_t* status_out) {
+    int rc = check_args(pl, a);
+    if (rc) return rc;
+    if (!S_out) return fail(HVB_ERR_ARG, "S_out is NULL");
+    const hvb_plan_desc& d = pl->d;
+    if (d.ncols != d.n + d.P) return fail(HVB_ERR_ARG, "plan has no right-hand sides (dump plan)");
+    CU(cudaSetDevice(pl->device));
+    const int64_t nF = a->nF, nS = a->nS;
+    const int64_t PP = (int64_t)d.P * d.P;
+    if (nF == 0 || PP == 0) { if (status_out) *status_out = 0; return HVB_OK; }
+    cudaStream_t s0 = pl->streams[0], s1 = pl->streams[1];
+
+    // inputs: uploaded once, on stream 0; stream 1 waits for them
+    CU(pl->f.ensure((size_t)nF * 8));
+    CU(cudaMemcpyAsync(pl->f.p, a->f, (size_t)nF * 8, cudaMemcpyHostToDevice, s0));
+    if (d.n_samples_cols) {
+        CU(pl->samples.ensure((size_t)nS * d.n_samples_cols * 8));
+        CU(cudaMemcpyAsync(pl->samples.p, a->samples, (size_t)nS * d.n_samples_cols * 8, cudaMemcpyHostToDevice, s0));
+    }
+    if (a->n_tables) {
+        CU(pl->tables.ensure((size_t)a->n_tables * nF * 16));
+        CU(cudaMemcpyAsync(pl->tables.p, a->tables, (size_t)a->n_tables * nF * 16, cudaMemcpyHostToDevice, s0));
+    }
+    CU(cudaMemsetAsync(pl->status.p, 0, 4, s0));
+    rc = push_params(pl, a, s0);
+    if (rc) return rc;
+    cudaEvent_t ready;
+    CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+    CU(cudaEventRecord(ready, s0));
+    CU(cudaStreamWaitEvent(s1, ready, 0));
+
+    // tiles: whole samples when several fit in a chunk, else frequency slabs of one sample
+    const char* env = getenv("HVB_CHUNK_MB");
+    const int64_t chunk_bytes = (int64_t)(env && atoi(env) > 0 ? atoi(env) : 128) << 20;
+    const int64_t max_pts = std::max<int64_t>(chunk_bytes / (PP * 16), 1);
+    int64_t Sc = 1, Fc = nF;
+    if (nF <= max_pts) Sc = std::min<int64_t>(nS, std::max<int64_t>(max_pts / nF, 1));
+    else Fc = max_pts;
+    // small jobs still get two tiles so that the copy-out of the first overlaps the second kernel
+    if (Sc >= nS && Fc >= nF && nS * nF >= 65536) {
+        if (nS >= 2) Sc = (nS + 1) / 2; else Fc = (nF + 1) / 2;
+    }
+    for (int b = 0; b < 2; ++b) CU(pl->S[b].ensure((size_t)Sc * PP * Fc * 16));
+
+    int tile = 0;
+    for (int64_t sb = 0; sb < nS; sb += Sc) {
+        const int64_t ns = std::min(Sc, nS - sb);
+        for (int64_t fb = 0; fb < nF; fb += Fc, ++tile) {
+            const int64_t nf = std::min(Fc, nF - fb);
+            cudaStream_t st = pl->streams[tile & 1];
+            HvbDev D = make_dev(pl);
+            D.nF = nf; D.nS = ns; D.ldS = nf; D.table_ld = nF;
+            D.f = (const double*)pl->f.p + fb;
+            D.samples = d.n_samples_cols ? (const double*)pl->samples.p + sb * d.n_samples_cols : nullptr;
+            D.tables = a->n_tables ? (const cplx*)pl->tables.p + fb : nullptr;
+            D.S = (cplx*)pl->S[tile & 1].p;
+            D.status = (int*)pl->status.p;
+            rc = launch(pl, D, st);
+            if (rc) { cudaEventDestroy(ready); return rc; }
+            // rows of nf elements, one per (sample, j, i); destination pitch is the full nF
+            char* dst = (char*)S_out + ((size_t)sb * PP * nF + (size_t)fb) * 16;
+            CU(cudaMemcpy2DAsync(dst, (size_t)nF * 16, D.S, (size_t)nf * 16, (size_t)nf * 16, (size_t)(ns * PP),
+                                 cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CU(cudaStreamSynchronize(s0));
+    CU(cudaStreamSynchronize(s1));
+    cudaEventDestroy(ready);
+    int32_t stw = 0;
+    CU(cudaMemcpy(&stw, pl->status.p, 4, cudaMemcpyDeviceToHost));
+    if (status_out) *status_out = stw;
+    return HVB_OK;
+}
+
+extern "C" int hvb_assemble_host(hvb_plan* pl, const hvb_run_args* a, double* W_out) {
+    int rc = check_args(pl, a);
+    if (rc) return rc;
+    if (!W_out) return fail(HVB_ERR_ARG, "W_out is NULL");
+    const hvb_plan_desc& d = pl->d;
+    CU(cudaSetDevice(pl->device));
+    const int64_t nF = a->nF, nS = a->nS, pts = nF * nS;
+    if (pts == 0) return HVB_OK;
+    cudaStream_t st = pl->streams[0];
+    CU(pl->f.ensure((size_t)nF * 8));
+    CU(cudaMemcpyAsync(pl->f.p, a->f, (size_t)nF * 8, cudaMemcpyHostToDevice, st));
+    if (d.n_samples_cols) {
+        CU(pl->samples.ensure((size_t)nS * d.n_samples_cols * 8));
+        CU(cudaMemcpyAsync(pl->samples.p, a->samples, (size_t)nS * d.n_samples_cols * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (a->n_tables) {
+        CU(pl->tables.ensure((size_t)a->n_tables * nF * 16));
+        CU(cudaMemcpyAsync(pl->tables.p, a->tables, (size_t)a->n_tables * nF * 16, cudaMemcpyHostToDevice, st));
+    }
+    rc = push_params(pl, a, st);
+    if (rc) return rc;
+    const size_t bytes = (size_t)pts * d.n * d.ncols * 16;
+    CU(pl->dump.ensure(bytes));
+    HvbDev D = make_dev(pl);
+    D.nF = nF; D.nS = nS; D.ldS = nF; D.table_ld = nF;
+    D.f = (const double*)pl->f.p;
+    D.samples = (const double*)pl->samples.p;
+    D.tables = (const cplx*)pl->tables.p;
+    D.W = (cplx*)pl->dump.p;
+    D.region_a = std::max(d.n_dyn, 1);
+    D.region_b = std::max(d.coop_scratch, 1);
+    const size_t smem = (size_t)(D.region_a + D.region_b) * 16;
+    const void* k = hvb_dump_kernel_ptr();
+    CU(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void* args[] = {&D};
+    const int grid = (int)std::min<int64_t>(pts, 148 * 16);
+    CU(cudaLaunchKernel(k, dim3(grid), dim3(32), args, smem, st));
+    pl->launches++;
+    CU(cudaMemcpyAsync(W_out, pl->dump.p, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return HVB_OK;
+}
+
+extern "C" int hvb_plan_kernel_info(hvb_plan* pl, hvb_kernel_info* out) {
+    if (!pl || !out) return fail(HVB_ERR_ARG, "null argument");
+    out->kernel_class = pl->kclass;
+    out->group = pl->kclass == 0 ? pl->G : pl->NB;
+    out->pmax = pl->PMAX;
+    out->threads = pl->threads;
+    out->smem_bytes = (int32_t)pl->smem;
+    out->regs = pl->regs;
+    out->ctas_per_sm = pl->ctas_per_sm;
+    out->sm_count = pl->sm_count;
+    out->launches = pl->launches;
+    return HVB_OK;
+}
+
+extern "C" int hvb_measure_dfma_peak(int device, double* tflops_out) {
+    if (!tflops_out) return fail(HVB_ERR_ARG, "null argument");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double* d_out = nullptr;
+    CU(cudaMalloc(&d_out, (size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const void* k = hvb_dfma_probe_ptr();
+    int it = iters;
+    void* args[] = {&d_out, &it};
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CU(cudaEventRecord(e0, 0));
+        CU(cudaLaunchKernel(k, dim3(blocks), dim3(threads), args, 0, 0));
+        CU(cudaEventRecord(e1, 0));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * (double)iters * blocks * threads;     // 8 chains x 8 unroll FMAs
+        if (rep >= 1) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *tflops_out = best;
+    return HVB_OK;
+}

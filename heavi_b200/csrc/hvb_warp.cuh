@@ -1,0 +1,266 @@
+// hvb_warp.cuh -- kernel A: systems with n <= 32 unknowns, G lanes per system, rows in registers.
+//
+// One system (one (sample, frequency) point) is owned by a group of G in {4,8,16,32} lanes, so a
+// warp works on 32/G points at once.  Lane r of the group holds row r of the augmented matrix
+// [A | B] in registers: G complex matrix columns + PMAX complex right-hand sides.  Per point:
+//
+//   1. value program  -> per-point stamp values in shared memory (group-cooperative N-port ops,
+//                        then the simple ops distributed over the lanes)
+//   2. gather         -> each lane sums its row's cells from the cell program (component order)
+//   3. Gauss-Jordan   -> n pivot steps with implicit partial pivoting: rows never move; the pivot
+//                        lane is found with a 32-bit key butterfly (|re|+|im| like LAPACK izamax,
+//                        ties to the lowest row), publishes its row through a double-buffered
+//                        shared-memory line, and every other row eliminates column k.  Because
+//                        rows above and below are eliminated there is no back substitution: after
+//                        n steps row r holds x[col(r)] = b_r / pivot_r for all P excitations.
+//   4. epilogue       -> S[j,i] from port voltages (solvers/spfn.py:159-176), stored with
+//                        frequency fastest so neighbouring groups/warps write neighbouring words.
+//
+// No __syncthreads anywhere: a group only ever synchronises with its own warp.
+#pragma once
+#include "hvb_device.cuh"
+
+#include <type_traits>
+
+#define HVB_WARP_THREADS 128
+
+// compile-time loop: indices are template constants, so register arrays are always statically indexed
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& fn) {
+    if constexpr (I < N) {
+        fn(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(fn);
+    }
+}
+
+// registers per thread are capped so that small systems keep many warps resident
+template <int G, int PMAX>
+struct WarpCfg {
+    static constexpr int kRegsWanted = 4 * (G + PMAX) + 44;
+    static constexpr int kMinBlocks = kRegsWanted <= 64 ? 8 : kRegsWanted <= 80 ? 6 : kRegsWanted <= 96 ? 5
+                                    : kRegsWanted <= 128 ? 4 : kRegsWanted <= 168 ? 3 : kRegsWanted <= 255 ? 2 : 1;
+};
+
+template <int G>
+__device__ __forceinline__ unsigned group_max_u32(unsigned key) {
+#pragma unroll
+    for (int off = G / 2; off >= 1; off >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, off));
+    return key;
+}
+
+// pivot key: high word of |re|+|im| with the low 5 bits replaced by (31 - lane) so that one
+// integer max yields both the largest magnitude (to 15 mantissa bits) and its lowest-index owner.
+__device__ __forceinline__ unsigned pivot_key(cplx v, bool excluded, int gl) {
+    const double mag = fabs(v.x) + fabs(v.y);
+    const unsigned hi = (unsigned)__double2hiint(mag);
+    return excluded ? 0u : (((hi & ~31u) | (unsigned)(31 - gl)) + 32u);
+}
+__device__ __forceinline__ unsigned pivot_status(unsigned key) {
+    const unsigned top = (key - 32u) & ~31u;
+    unsigned bad = 0;
+    if (key < 32u || top == 0u) bad |= HVB_STATUS_ZERO_PIVOT_BIT;
+    if (top >= 0x7FF00000u) bad |= HVB_STATUS_NONFINITE_BIT;
+    return bad;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cooperative N-port value op, executed by all G lanes of a group (base/nport.py:28-39):
+//   S_ij(f) -> Y = (1/Z0) (I - S) (I + S)^-1 -> (P+1)x(P+1) indefinite block with the reference
+//   node's row / column.  The inverse is applied as a solve of (I+S)^T X^T = (I-S)^T with the
+//   same implicit-pivot Gauss-Jordan, rows in the group's shared-memory scratch.
+// ------------------------------------------------------------------------------------------------
+template <int G>
+__device__ __forceinline__ unsigned coop_nport(const HvbDev& D, const int* __restrict__ op, double f, long long fi,
+                                               const double* __restrict__ srow, cplx* __restrict__ dyn,
+                                               cplx* __restrict__ scratch, int gl) {
+    const int code = op[0], out = op[1] - D.nvc, Pn = op[2], first = op[3];
+    const int ldo = Pn + 1;
+    unsigned bad = 0;
+    if (code == COOP_NPORT_Y) {
+        for (int e = gl; e < Pn * Pn; e += G)
+            dyn[out + (e / Pn) * ldo + (e % Pn)] = eval_param(D, first + e, f, fi, srow);
+        __syncwarp();
+    } else {
+        const int ld = 2 * Pn;
+        for (int e = gl; e < Pn * Pn; e += G) {
+            const int i = e / Pn, j = e % Pn;
+            const cplx s = eval_param(D, first + e, f, fi, srow);
+            const double d = (i == j) ? 1.0 : 0.0;
+            scratch[j * ld + i] = cmk(d + s.x, s.y);              // (I+S)^T
+            scratch[j * ld + Pn + i] = cmk(d - s.x, -s.y);        // (I-S)^T
+        }
+        __syncwarp();
+        bool done = gl >= Pn;
+        int mycol = 0;
+        for (int k = 0; k < Pn; ++k) {
+            const cplx mine = (gl < Pn) ? scratch[gl * ld + k] : cmk(0.0, 0.0);
+            const unsigned key = group_max_u32<G>(pivot_key(mine, done, gl));
+            bad |= pivot_status(key);
+            const int p = 31 - (int)(key & 31u);
+            if (gl == p) { done = true; mycol = k; }
+            const cplx inv = crecip_fast(scratch[p * ld + k]);
+            if (gl < Pn && gl != p) {
+                const cplx m = cmul(mine, inv);
+                for (int c = k + 1; c < ld; ++c) {
+                    cplx v = scratch[gl * ld + c];
+                    cfnma(v, m, scratch[p * ld + c]);
+                    scratch[gl * ld + c] = v;
+                }
+            }
+            __syncwarp();
+        }
+        if (gl < Pn) {
+            const cplx inv = crecip_fast(scratch[gl * ld + mycol]);
+            const cplx z0 = D.consts[op[4]];
+            const cplx iz = crecip_np(z0);                          // (1/Z0), nport.py:32
+            for (int c = 0; c < Pn; ++c) {
+                const cplx x = cmul(scratch[gl * ld + Pn + c], inv);   // X^T[mycol][c] = X[c][mycol]
+                dyn[out + c * ldo + mycol] = (iz.y == 0.0) ? cscale(x, iz.x) : cmul(iz, x);
+            }
+        }
+        __syncwarp();
+    }
+    // reference-node row / column: -row sums, -column sums, +total (nport.py:35-38)
+    for (int i = gl; i < Pn; i += G) {
+        cplx rs = cmk(0.0, 0.0), cs = cmk(0.0, 0.0);
+        for (int j = 0; j < Pn; ++j) {
+            rs = cadd(rs, dyn[out + i * ldo + j]);
+            cs = cadd(cs, dyn[out + j * ldo + i]);
+        }
+        dyn[out + i * ldo + Pn] = cneg(rs);
+        dyn[out + Pn * ldo + i] = cneg(cs);
+        scratch[i] = rs;
+    }
+    __syncwarp();
+    if (gl == 0) {
+        cplx tot = cmk(0.0, 0.0);
+        for (int i = 0; i < Pn; ++i) tot = cadd(tot, scratch[i]);
+        dyn[out + Pn * ldo + Pn] = tot;
+    }
+    __syncwarp();
+    return bad;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel A
+// ------------------------------------------------------------------------------------------------
+template <int G, int PMAX>
+__global__ void __launch_bounds__(HVB_WARP_THREADS, WarpCfg<G, PMAX>::kMinBlocks) hvb_warp_kernel(const HvbDev D) {
+    extern __shared__ __align__(16) unsigned char hvb_smem[];
+    constexpr int SPW = 32 / G;
+    constexpr int BROW = G + PMAX;                       // one broadcast line (complex words)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gl = lane % G, grp = lane / G;
+    const int sys_in_block = warp * SPW + grp;
+    const int sys_per_block = (HVB_WARP_THREADS / 32) * SPW;
+    cplx* regA = reinterpret_cast<cplx*>(hvb_smem) + (size_t)sys_in_block * (D.region_a + D.region_b);
+    cplx* regB = regA + D.region_a;
+    const int n = D.n, P = D.P, ncols = D.ncols;
+    const long long total = D.nS * D.nF;
+    const int r = gl;
+
+    for (long long q0 = (long long)blockIdx.x * sys_per_block; q0 < total;
+         q0 += (long long)gridDim.x * sys_per_block) {
+        const long long q = q0 + sys_in_block;
+        const bool active = q < total;
+        const long long qq = active ? q : total - 1;     // idle groups shadow the last point
+        const long long s = qq / D.nF, fi = qq - s * D.nF;
+        const double f = __ldg(D.f + fi);
+        const double* __restrict__ srow = D.samples + s * D.nR;
+        unsigned bad = 0;
+
+        // ---- 1. value program ----------------------------------------------------------------
+        for (int o = 0; o < D.ncoops; ++o)
+            bad |= coop_nport<G>(D, D.coops + o * HVB_COOP_WORDS, f, fi, srow, regA, regB, gl);
+        for (int o = gl; o < D.nops; o += G) eval_simple_op(D, D.ops + o * HVB_OP_WORDS, f, fi, srow, regA);
+        __syncwarp();
+
+        // ---- 2. gather this lane's row ---------------------------------------------------------
+        cplx a[G], b[PMAX];
+        {
+            const bool live = r < n;
+            int lo = live ? __ldg(D.cell_ptr + r * ncols) : 0;
+            auto gather = [&](bool on, int cell_end) -> cplx {
+                cplx acc = cmk(0.0, 0.0);
+                if (on) {
+                    const int hi = __ldg(D.cell_ptr + cell_end);
+                    for (int e = lo; e < hi; ++e) {
+                        const int ent = __ldg(D.cell_ent + e);
+                        const cplx v = load_value(D, ent >> 1, regA);
+                        if (ent & 1) { acc.x -= v.x; acc.y -= v.y; } else { acc.x += v.x; acc.y += v.y; }
+                    }
+                    lo = hi;
+                }
+                return acc;
+            };
+            static_for<0, G>([&](auto cc) {
+                constexpr int c = decltype(cc)::value;
+                a[c] = gather(live && c < n, r * ncols + c + 1);
+            });
+            static_for<0, PMAX>([&](auto ii) {
+                constexpr int i = decltype(ii)::value;
+                b[i] = gather(live && i < P, r * ncols + n + i + 1);
+            });
+        }
+        __syncwarp();
+
+        // ---- 3. Gauss-Jordan with implicit partial pivoting ------------------------------------
+        bool done = r >= n;
+        int mycol = 0;
+        cplx myinv = cmk(0.0, 0.0);
+        static_for<0, G>([&](auto kk) {
+            constexpr int k = decltype(kk)::value;
+            if (k < n) {
+                const unsigned key = group_max_u32<G>(pivot_key(a[k], done, gl));
+                bad |= pivot_status(key);
+                const int p = 31 - (int)(key & 31u);
+                const bool is_p = (gl == p);
+                cplx* __restrict__ brow = regB + (k & 1) * BROW;
+                if (is_p) {
+                    static_for<k, G>([&](auto cc) {
+                        constexpr int c = decltype(cc)::value;
+                        if (c < n) brow[c] = a[c];
+                    });
+                    static_for<0, PMAX>([&](auto ii) {
+                        constexpr int i = decltype(ii)::value;
+                        if (i < P) brow[G + i] = b[i];
+                    });
+                    done = true;
+                    mycol = k;
+                }
+                __syncwarp();
+                const cplx inv = crecip_fast(brow[k]);
+                cplx m = cmul(a[k], inv);
+                if (is_p) { myinv = inv; m = cmk(0.0, 0.0); }
+                static_for<k + 1, G>([&](auto cc) {
+                    constexpr int c = decltype(cc)::value;
+                    if (c < n) cfnma(a[c], m, brow[c]);
+                });
+                static_for<0, PMAX>([&](auto ii) {
+                    constexpr int i = decltype(ii)::value;
+                    if (i < P) cfnma(b[i], m, brow[G + i]);
+                });
+            }
+        });
+
+        // ---- 4. solution rows -> shared, then S ------------------------------------------------
+        __syncwarp();
+        if (r < n) {
+            static_for<0, PMAX>([&](auto ii) {
+                constexpr int i = decltype(ii)::value;
+                if (i < P) regA[mycol * P + i] = cmul(b[i], myinv);
+            });
+        }
+        __syncwarp();
+        for (int e = gl; e < P * P; e += G) {
+            const int j = e / P, i = e - j * P;
+            const cplx Zi = eval_param(D, __ldg(D.port_zpref + i), f, fi, srow);
+            const cplx Zj = eval_param(D, __ldg(D.port_zpref + j), f, fi, srow);
+            const cplx sv = s_entry(D, regA, j, i, Zi, Zj);
+            if (!(isfinite(sv.x) && isfinite(sv.y))) bad |= HVB_STATUS_NONFINITE_BIT;
+            if (active) D.S[((s * P + j) * P + i) * D.ldS + fi] = sv;
+        }
+        if (bad && active && D.status) atomicOr(D.status, (int)bad);
+        __syncwarp();
+    }
+}

@@ -1,0 +1,265 @@
+"""ctypes binding of `libheavi_b200.so` (C-ABI: include/heavi_b200.h) and the compiled-netlist object
+`Network.run_sp` drives.
+
+There is deliberately no CPU path here: if the CUDA library is missing or no CUDA device is
+present, every entry raises.  PyTorch is used only for pinned host buffers and (in the
+device-resident entry used by the benchmark) for device buffers and streams; no tensor crosses the
+C-ABI, only `data_ptr()` integers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import warnings
+
+import numpy as np
+
+from . import plan as pl
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libheavi_b200.so")
+
+HVB_STATUS_NONFINITE = 1
+HVB_STATUS_ZERO_PIVOT = 2
+
+_i32p = C.POINTER(C.c_int32)
+_f64p = C.POINTER(C.c_double)
+
+
+class PlanDesc(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in (
+        "n", "ncols", "P", "n_consts", "n_prefs", "n_const_vals", "n_dyn", "n_ops", "n_coops",
+        "n_samples_cols", "coop_scratch", "n_traces", "n_knots", "n_coefs")] + [
+        ("const_vals", _f64p), ("ops", _i32p), ("coops", _i32p), ("cell_ptr", _i32p), ("cell_ent", _i32p),
+        ("port_rows", _i32p), ("port_zpref", _i32p), ("spl_t", _f64p), ("spl_c", _f64p),
+        ("spl_trace", _i32p), ("spl_fill", _f64p), ("spl_range", _f64p)]
+
+
+class RunArgs(C.Structure):
+    _fields_ = [("consts", C.c_void_p), ("prefs", C.c_void_p), ("f", C.c_void_p), ("nF", C.c_int64),
+                ("samples", C.c_void_p), ("nS", C.c_int64), ("tables", C.c_void_p), ("n_tables", C.c_int32)]
+
+
+class KernelInfo(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("kernel_class", "group", "pmax", "threads", "smem_bytes", "regs",
+                                         "ctas_per_sm", "sm_count")] + [("launches", C.c_int64)]
+
+
+EXPORTS = ("hvb_plan_create", "hvb_plan_destroy", "hvb_run_host", "hvb_run_device", "hvb_assemble_host",
+           "hvb_plan_kernel_info", "hvb_measure_dfma_peak", "hvb_last_error", "hvb_version")
+
+_lib = None
+
+
+def load_library():
+    """dlopen the CUDA library; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C heavi_b200/csrc`.  heavi_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    lib.hvb_plan_create.argtypes = [C.POINTER(PlanDesc), C.c_int, C.POINTER(C.c_void_p)]
+    lib.hvb_plan_create.restype = C.c_int
+    lib.hvb_plan_destroy.argtypes = [C.c_void_p]
+    lib.hvb_plan_destroy.restype = None
+    lib.hvb_run_host.argtypes = [C.c_void_p, C.POINTER(RunArgs), C.c_void_p, _i32p]
+    lib.hvb_run_host.restype = C.c_int
+    lib.hvb_run_device.argtypes = [C.c_void_p, C.POINTER(RunArgs), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.hvb_run_device.restype = C.c_int
+    lib.hvb_assemble_host.argtypes = [C.c_void_p, C.POINTER(RunArgs), C.c_void_p]
+    lib.hvb_assemble_host.restype = C.c_int
+    lib.hvb_plan_kernel_info.argtypes = [C.c_void_p, C.POINTER(KernelInfo)]
+    lib.hvb_plan_kernel_info.restype = C.c_int
+    lib.hvb_measure_dfma_peak.argtypes = [C.c_int, _f64p]
+    lib.hvb_measure_dfma_peak.restype = C.c_int
+    lib.hvb_last_error.restype = C.c_char_p
+    lib.hvb_version.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        msg = load_library().hvb_last_error().decode()
+        if rc == -1:
+            raise ValueError(f"heavi_b200: {msg}")
+        if rc == -3:
+            raise NotImplementedError(f"heavi_b200: {msg}")
+        raise RuntimeError(f"heavi_b200 (code {rc}): {msg}")
+
+
+def current_device() -> int:
+    env = os.environ.get("HVB_DEVICE")
+    if env is not None:
+        return int(env)
+    try:
+        import torch
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:
+        pass
+    if "LOCAL_RANK" in os.environ:
+        return int(os.environ["LOCAL_RANK"])
+    return 0
+
+
+def pinned_empty(shape, dtype=np.complex128) -> np.ndarray:
+    """numpy array on page-locked memory (torch's caching host allocator), so that the D2H of S runs
+    at full PCIe rate and asynchronously."""
+    import torch
+    tdt = {np.dtype(np.complex128): torch.complex128, np.dtype(np.float64): torch.float64}[np.dtype(dtype)]
+    return torch.empty(tuple(int(x) for x in shape), dtype=tdt, pin_memory=True).numpy()
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+class DevicePlanHandle:
+    """Owns one `hvb_plan*`."""
+
+    def __init__(self, plan: pl.DevicePlan, device: int | None = None):
+        self.lib = load_library()
+        self.plan = plan
+        self.device = current_device() if device is None else device
+        keep = self._keep = {}
+
+        def arr(name, a, dt):
+            a = np.ascontiguousarray(a, dtype=dt)
+            if a.size == 0:
+                a = np.zeros(1, dtype=dt)
+            keep[name] = a
+            return a
+
+        d = PlanDesc()
+        d.n, d.ncols, d.P = plan.n, plan.ncols, plan.P
+        d.n_consts, d.n_prefs = len(plan.consts), len(plan.prefs)
+        d.n_const_vals, d.n_dyn = len(plan.const_vals), plan.n_dyn
+        d.n_ops, d.n_coops = len(plan.ops), len(plan.coops)
+        d.n_samples_cols, d.coop_scratch = plan.n_samples_cols, plan.coop_scratch
+        d.n_traces, d.n_knots, d.n_coefs = len(plan.spl_trace), len(plan.spl_t), len(plan.spl_c)
+        d.const_vals = arr("cv", plan.const_vals, np.complex128).ctypes.data_as(_f64p)
+        d.ops = arr("ops", plan.ops, np.int32).ctypes.data_as(_i32p)
+        d.coops = arr("coops", plan.coops, np.int32).ctypes.data_as(_i32p)
+        d.cell_ptr = arr("cp", plan.cell_ptr, np.int32).ctypes.data_as(_i32p)
+        d.cell_ent = arr("ce", plan.cell_ent, np.int32).ctypes.data_as(_i32p)
+        d.port_rows = arr("pr", plan.port_rows, np.int32).ctypes.data_as(_i32p)
+        d.port_zpref = arr("pz", plan.port_zpref, np.int32).ctypes.data_as(_i32p)
+        d.spl_t = arr("st", plan.spl_t, np.float64).ctypes.data_as(_f64p)
+        d.spl_c = arr("sc", plan.spl_c, np.complex128).ctypes.data_as(_f64p)
+        d.spl_trace = arr("str", plan.spl_trace, np.int32).ctypes.data_as(_i32p)
+        d.spl_fill = arr("sf", plan.spl_fill, np.complex128).ctypes.data_as(_f64p)
+        d.spl_range = arr("sr", plan.spl_range, np.float64).ctypes.data_as(_f64p)
+        handle = C.c_void_p()
+        _check(self.lib.hvb_plan_create(C.byref(d), self.device, C.byref(handle)))
+        self.handle = handle
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.hvb_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def _args(self, consts, prefs, f_ptr, nF, samples_ptr, nS, tables_ptr, nT):
+        self._run_keep = (np.ascontiguousarray(consts, dtype=np.complex128), np.ascontiguousarray(prefs, dtype=np.int32))
+        a = RunArgs()
+        a.consts = _ptr(self._run_keep[0])
+        a.prefs = _ptr(self._run_keep[1])
+        a.f, a.nF = f_ptr, nF
+        a.samples, a.nS = samples_ptr, nS
+        a.tables, a.n_tables = tables_ptr, nT
+        return a
+
+    def kernel_info(self) -> dict:
+        ki = KernelInfo()
+        _check(self.lib.hvb_plan_kernel_info(self.handle, C.byref(ki)))
+        return {k: getattr(ki, k) for k, _ in KernelInfo._fields_}
+
+    # ---- host buffers in, host buffer out ------------------------------------------------------
+    def run_host(self, f, consts, prefs, tables, samples, out: np.ndarray | None = None):
+        p = self.plan
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        nF, nS = f.shape[0], samples.shape[0]
+        if out is None:
+            out = pinned_empty((nS, p.P, p.P, nF))
+        tables = np.ascontiguousarray(tables, dtype=np.complex128)
+        samples = np.ascontiguousarray(samples, dtype=np.float64)
+        a = self._args(consts, prefs, _ptr(f), nF, _ptr(samples), nS, _ptr(tables), tables.shape[0])
+        status = C.c_int32(0)
+        _check(self.lib.hvb_run_host(self.handle, C.byref(a), out.ctypes.data_as(C.c_void_p), C.byref(status)))
+        return out, status.value
+
+    def assemble_host(self, f, consts, prefs, tables, samples) -> np.ndarray:
+        p = self.plan
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        nF, nS = f.shape[0], samples.shape[0]
+        out = np.empty((nS, nF, p.n, p.ncols), dtype=np.complex128)
+        tables = np.ascontiguousarray(tables, dtype=np.complex128)
+        samples = np.ascontiguousarray(samples, dtype=np.float64)
+        a = self._args(consts, prefs, _ptr(f), nF, _ptr(samples), nS, _ptr(tables), tables.shape[0])
+        _check(self.lib.hvb_assemble_host(self.handle, C.byref(a), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    # ---- device buffers (torch tensors) ----------------------------------------------------------
+    def run_device(self, d_f, consts, prefs, d_tables, d_samples, d_out, d_status=None, stream=None):
+        """All `d_*` are torch CUDA tensors; enqueues on `stream` (torch stream) without syncing."""
+        import torch
+        nF = d_f.shape[0]
+        nS = d_samples.shape[0] if d_samples is not None else 1
+        nT = d_tables.shape[0] if d_tables is not None else 0
+        st = stream if stream is not None else torch.cuda.current_stream()
+        a = self._args(consts, prefs, d_f.data_ptr(), nF,
+                       d_samples.data_ptr() if d_samples is not None and d_samples.numel() else None, nS,
+                       d_tables.data_ptr() if nT else None, nT)
+        _check(self.lib.hvb_run_device(self.handle, C.byref(a), d_out.data_ptr(), d_out.shape[-1],
+                                       d_status.data_ptr() if d_status is not None else None,
+                                       C.c_void_p(st.cuda_stream)))
+
+
+def measure_dfma_peak(device: int | None = None) -> float:
+    lib = load_library()
+    out = C.c_double(0.0)
+    _check(lib.hvb_measure_dfma_peak(current_device() if device is None else device, C.byref(out)))
+    return out.value
+
+
+class CompiledNetwork:
+    """A frozen `Network`: stamp table + device plan + the library handle."""
+
+    def __init__(self, net, mode: str | None = None, device: int | None = None):
+        self.table = net.stamp_table()
+        mode = mode or os.environ.get("HVB_MODE", "auto")
+        self.plan = pl.compile_plan(self.table, mode)
+        self.handle = DevicePlanHandle(self.plan, device)
+        self._dump = None
+
+    def resolve(self, f, drivers=None, values=None):
+        return pl.resolve_run(self.plan, f, drivers, values)
+
+    def run(self, f: np.ndarray, drivers=None, values=None, out=None) -> np.ndarray:
+        """S[nS,P,P,nF] complex128 on pinned host memory."""
+        consts, prefs, tables, samples = self.resolve(f, drivers, values)
+        S, status = self.handle.run_host(f, consts, prefs, tables, samples, out)
+        if status & HVB_STATUS_NONFINITE:
+            # the reference's numba lstsq raises for NaN/Inf input
+            raise np.linalg.LinAlgError("MNA matrix or S-parameters contain NaN/Inf (e.g. f = 0 with an inductor)")
+        if status & HVB_STATUS_ZERO_PIVOT:
+            warnings.warn("singular MNA system at one or more points: the reference returns the SVD "
+                          "minimum-norm solution there, the LU solver cannot", RuntimeWarning)
+        return S
+
+    def assemble(self, f: np.ndarray, drivers=None, values=None) -> np.ndarray:
+        """Dense reference-layout MNA tensor [(N+M), (N+M), nF] of the first sample (debug/parity)."""
+        if self._dump is None:
+            dplan = pl.compile_plan(self.table, "dump")
+            self._dump = DevicePlanHandle(dplan, self.handle.device)
+        dp = self._dump.plan
+        f = np.ascontiguousarray(np.asarray(f, dtype=np.float64))
+        consts, prefs, tables, samples = pl.resolve_run(dp, f, drivers, values)
+        W = self._dump.assemble_host(f, consts, prefs, tables, samples[:1])
+        return np.ascontiguousarray(np.moveaxis(W[0], 0, 2))

@@ -1,0 +1,144 @@
+/*
+ * heavi_b200.h -- C-ABI of libheavi_b200.so, the B200 (sm_100a) engine behind heavi's
+ * frequency-sweep S-parameter path.
+ *
+ * The reference (FennisRobert/heavi, pure Python) has no FFI layer; its seam for this path is
+ *     Network.run_sp(frequencies, reinitialize=False) -> Sparameters      src/heavi/network.py:354-421
+ * whose body (1) asks every component for a Python closure and lets each add a dense (k,k,nF)
+ * block into a dense (N+M,N+M,nF) complex128 tensor              network.py:385-394, base/[star].py
+ *             (2) builds `indices[P,4]` and `impedance_vector[M,nF]`       network.py:397-404
+ *             (3) calls solve_MNA_RF_nopgb(As, Zs, indices, f, N, M)       solvers/spfn.py:106-179
+ * The entry points below replace (1)+(2)+(3) in one call: the host freezes the netlist into the
+ * arrays of `hvb_plan_desc` (a stamp table compiled into a value program and a per-cell gather
+ * program, see heavi_b200/plan.py) and the library assembles, factors and converts every
+ * (Monte-Carlo sample, frequency) point on the GPU.  Nothing here takes or returns a torch type;
+ * all arguments are plain pointers and sizes.  INTEGRATION.md shows the ctypes stub a maintainer of
+ * the reference would add to network.py to bind these.
+ *
+ * Conventions: every function returns 0 on success or a negative hvb_status; the message for the
+ * last failure on the calling thread is hvb_last_error().  Complex numbers are interleaved
+ * (re, im) float64 pairs.  A plan belongs to one CUDA device and is not thread-safe; distinct
+ * plans are independent.  Caller keeps ownership of every array it passes in; the library copies
+ * what it needs during the call.
+ */
+#ifndef HEAVI_B200_H
+#define HEAVI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hvb_plan hvb_plan;
+
+enum hvb_status {
+    HVB_OK = 0,
+    HVB_ERR_ARG = -1,        /* bad argument / malformed plan                                   */
+    HVB_ERR_CUDA = -2,       /* CUDA runtime error (message has the CUDA string)                */
+    HVB_ERR_UNSUPPORTED = -3 /* valid request this build cannot serve (e.g. N-port > 32 ports)  */
+};
+
+/* Bits of the per-run status word (hvb_run_* `status_out[0]`).  The reference raises LinAlgError
+ * from numba's lstsq when the matrix holds NaN/Inf; a zero pivot is where the
+ * reference silently returns the SVD minimum-norm solution (App. B-7). */
+#define HVB_STATUS_NONFINITE 1
+#define HVB_STATUS_ZERO_PIVOT 2
+
+/* Frozen netlist.  Field meanings follow heavi_b200/plan.py:DevicePlan one to one.
+ * Replaces: the list of SP_matrix_compiler closures (network.py:385-386) plus `indices`
+ * (network.py:400-404). */
+typedef struct hvb_plan_desc {
+    int32_t n;             /* system dimension actually factored                                */
+    int32_t ncols;         /* n + number of right-hand sides (== n for a dump-only plan)        */
+    int32_t P;             /* ports                                                             */
+    int32_t n_consts;      /* length of the per-run `consts` array                              */
+    int32_t n_prefs;       /* parameter references (kind, index) pairs                          */
+    int32_t n_const_vals;  /* plan-time stamp values (id 0 is 1+0j)                             */
+    int32_t n_dyn;         /* per-point stamp values                                            */
+    int32_t n_ops;         /* simple value ops, 8 int32 words each                              */
+    int32_t n_coops;       /* cooperative value ops (N-port blocks), 8 int32 words each         */
+    int32_t n_samples_cols;/* columns of the per-sample parameter matrix                        */
+    int32_t coop_scratch;  /* complex scratch words a cooperative op needs per point            */
+    int32_t n_traces;      /* B-spline traces                                                   */
+    int32_t n_knots;       /* total knots                                                       */
+    int32_t n_coefs;       /* total spline coefficients                                         */
+    const double*  const_vals; /* [n_const_vals] complex                                        */
+    const int32_t* ops;        /* [n_ops*8]                                                     */
+    const int32_t* coops;      /* [n_coops*8]                                                   */
+    const int32_t* cell_ptr;   /* [n*ncols+1] CSR over matrix cells, row-major                  */
+    const int32_t* cell_ent;   /* [cell_ptr[n*ncols]]  (value id << 1) | negate                 */
+    const int32_t* port_rows;  /* [P*3] sig,int,gnd system rows; -1 ground, -2 int = gnd + E    */
+    const int32_t* port_zpref; /* [P] parameter reference of each port's Z0                     */
+    const double*  spl_t;      /* [n_knots]                                                     */
+    const double*  spl_c;      /* [n_coefs] complex                                             */
+    const int32_t* spl_trace;  /* [n_traces*4] t_off, nt, c_off, k                              */
+    const double*  spl_fill;   /* [n_traces*2] complex: value below / above the data range      */
+    const double*  spl_range;  /* [n_traces*2] first / last data abscissa                       */
+} hvb_plan_desc;
+
+/* Per-run parameters: what only the host can evaluate (callable parameters tabulated with the
+ * reference's own numpy arithmetic, Monte-Carlo draws made in the reference's RNG order).
+ * Replaces: SimParam.__call__(f) inside every closure (numeric.py:127-129) and
+ * MonteCarlo.iterate's per-sample mutation (numeric.py:498-503). */
+typedef struct hvb_run_args {
+    const double*  consts;     /* [n_consts] complex                                            */
+    const int32_t* prefs;      /* [n_prefs*2]                                                   */
+    const double*  f;          /* [nF] frequencies, float64                                     */
+    int64_t        nF;
+    const double*  samples;    /* [nS*n_samples_cols] row-major, may be NULL when no columns    */
+    int64_t        nS;
+    const double*  tables;     /* [n_tables*nF] complex, row-major; NULL when n_tables == 0     */
+    int32_t        n_tables;
+} hvb_run_args;
+
+/* Create / destroy.  `device` is a CUDA ordinal.  The plan copies everything in `desc`. */
+int  hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan** out);
+void hvb_plan_destroy(hvb_plan* plan);
+
+/* S-parameters with HOST buffers: uploads f / samples / tables, runs the kernels in pipelined
+ * chunks and writes S_out[nS][P][P][nF] (complex128, frequency fastest -- the layout of
+ * Sparameters._S, sparam.py:49-63, with a leading sample axis).  `S_out` may be pageable or
+ * pinned.  `status_out` (optional, 1 int32) receives the OR of HVB_STATUS_* bits.
+ * Replaces: the whole body of Network.run_sp after index allocation (network.py:380-416). */
+int hvb_run_host(hvb_plan* plan, const hvb_run_args* args, double* S_out, int32_t* status_out);
+
+/* Same computation with DEVICE buffers owned by the caller (e.g. torch tensors' data_ptr()):
+ * `args->f`, `args->samples`, `args->tables` and `d_S_out` are device pointers; consts/prefs stay
+ * host pointers.  Work is enqueued on `stream` (a cudaStream_t, NULL = legacy default stream) and
+ * the call returns without synchronising.  `d_status` (optional) is a device int32.
+ * `ldS` is the frequency pitch of the output in elements (>= nF). */
+int hvb_run_device(hvb_plan* plan, const hvb_run_args* args, double* d_S_out, int64_t ldS,
+                   int32_t* d_status, void* stream);
+
+/* Assemble only: writes the dense matrix the plan describes, W[nS][nF][n][ncols] complex128, to
+ * HOST memory.  With a "dump" plan (n = ncols = N+M, ground kept) this is the reference's
+ * `mna_matrix[:, :, f]` (network.py:392-394), used by the parity tests. */
+int hvb_assemble_host(hvb_plan* plan, const hvb_run_args* args, double* W_out);
+
+/* Introspection for the benchmark / tests. */
+typedef struct hvb_kernel_info {
+    int32_t kernel_class;   /* 0 = warp kernel (n <= 32), 1 = block kernel                       */
+    int32_t group;          /* lanes per system (warp kernel)                                    */
+    int32_t pmax;           /* RHS register columns (warp kernel)                                */
+    int32_t threads;        /* threads per CTA                                                   */
+    int32_t smem_bytes;     /* dynamic shared memory per CTA                                     */
+    int32_t regs;           /* registers per thread (cudaFuncGetAttributes)                      */
+    int32_t ctas_per_sm;    /* occupancy                                                         */
+    int32_t sm_count;
+    int64_t launches;       /* kernel launches issued by this plan so far                        */
+} hvb_kernel_info;
+int hvb_plan_kernel_info(hvb_plan* plan, hvb_kernel_info* out);
+
+/* FP64 FMA peak of the device, measured with a register-resident DFMA loop on `stream`
+ * (TFLOP/s).  bench.py uses it as the roofline denominator because MEASURED_PEAKS.json has no
+ * FP64 entry. */
+int hvb_measure_dfma_peak(int device, double* tflops_out);
+
+const char* hvb_last_error(void);
+const char* hvb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEAVI_B200_H */
