@@ -128,8 +128,10 @@ __global__ void __launch_bounds__(HVB_BLOCK_THREADS) hvb_block_kernel(const HvbD
                 for (int j = 0; j < NB; ++j) u[j] = (j < nb) ? W[(size_t)(kb + j) * ld + c0 + c] : cmk(0.0, 0.0);
 #pragma unroll
                 for (int j = 1; j < NB; ++j) {
+                    if (j < nb) {                       // rows >= nb of the panel head do not exist
 #pragma unroll
-                    for (int i = 0; i < j; ++i) cfnma(u[j], panel[j * NB + i], u[i]);
+                        for (int i = 0; i < j; ++i) cfnma(u[j], panel[j * NB + i], u[i]);
+                    }
                 }
 #pragma unroll
                 for (int j = 0; j < NB; ++j) {

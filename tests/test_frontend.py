@@ -1,0 +1,127 @@
+"""CPU: behaviour of the drop-in building API (reference: heavi/network.py, node.py, sparam.py)."""
+import numpy as np
+import pytest
+
+import heavi_b200 as hv
+from heavi_b200.results import Sparameters
+
+
+def test_port_creates_internal_node_before_signal_node():
+    m = hv.Model()
+    p = m.new_port(50)
+    m.resistor(p.sig_node, m.gnd, 50.0)
+    m._prepare()
+    assert m.gnd.index == 0 and p.int_node.index == 1 and p.sig_node.index == 2
+    assert p.sources[0].index == 3 and p.index == 1
+
+
+def test_unconnected_node_raises_value_error():
+    m = hv.Model()
+    a = m.quick_port(50)
+    m.node()                                       # dangling
+    m.resistor(a, m.gnd, 10.0)
+    with pytest.raises(ValueError, match="is not connected to any components"):
+        m.stamp_table()
+
+
+def test_merged_nodes_share_an_index():
+    m = hv.Model()
+    a = m.quick_port(50)
+    b = m.node()
+    c = m.node()
+    assert (c > b) is b
+    m.resistor(a, b, 10.0)
+    m.capacitor(c, m.gnd, 1e-12)
+    m._prepare()
+    assert c.index == b.index
+    assert max(n.index for n in m._nodes) + 1 == 4
+
+
+def test_quick_port_forwards_second_argument_as_signal_node():
+    m = hv.Model()
+    n = m.node()
+    assert m.quick_port(50, n) is n                # reference quirk, network.py:500
+
+
+def test_reinitialize_does_not_grow_sources():
+    m = hv.Model()
+    a = m.quick_port(50)
+    m.resistor(a, m.gnd, 75.0)
+    m._prepare()
+    m._initialized = False
+    m._prepare()
+    assert len(m.sources) == 1
+
+
+def test_sparameters_container():
+    S = np.arange(2 * 2 * 3, dtype=np.complex128).reshape(2, 2, 3)
+    sp = Sparameters(S, np.array([1, 2, 3], dtype=np.float32))
+    assert sp.nports == 2 and sp.nfreqs == 3 and sp.shape == (2, 2, 3)
+    assert np.array_equal(sp.S21, S[1, 0]) and np.array_equal(sp(1, 2), S[0, 1]) and np.array_equal(sp.S(2, 2), S[1, 1])
+    with pytest.raises(ValueError):
+        sp.S(3, 1)
+    with pytest.raises(ValueError):
+        sp.S110                                    # greedy regex -> (11, 0), like the reference
+    with pytest.raises(AttributeError):
+        sp.nothing
+    assert "S54" in dir(sp) and "S55" not in [x for x in dir(sp)[:20]]
+
+
+def test_scalar_param_semantics():
+    from heavi_b200.params import Scalar, enforce_simparam, Function, Random
+    s = Scalar(3.0)
+    assert np.array_equal(s(np.array([1.0, 2.0])), np.array([3.0, 3.0])) and s.value == 3.0
+    assert isinstance(enforce_simparam(lambda f: f), Function)
+    with pytest.raises(ValueError):
+        enforce_simparam("x")
+    mc = hv.MonteCarlo()
+    u = mc.uniform(0, 1)
+    with pytest.raises(ValueError, match="Uninitialized"):
+        u(np.array([1.0]))
+    assert isinstance(u, Random)
+
+
+def test_touchstone_roundtrip(tmp_path):
+    f = np.linspace(1e9, 2e9, 7)
+    S = np.zeros((7, 2, 2), dtype=complex)
+    S[:, 0, 0], S[:, 1, 0], S[:, 0, 1], S[:, 1, 1] = 0.1 + 0.2j, 0.8 - 0.1j, 0.05j, 0.3
+    path = tmp_path / "x.s2p"
+    with open(path, "w") as fh:
+        fh.write("! test\n# GHz S RI R 75\n")
+        for k in range(7):
+            # 2-port order: S11 S21 S12 S22
+            vals = [S[k, 0, 0], S[k, 1, 0], S[k, 0, 1], S[k, 1, 1]]
+            fh.write("%.9f " % (f[k] / 1e9) + " ".join("%.6f %.6f" % (v.real, v.imag) for v in vals) + "\n")
+    blk = hv.FileBasedNPort(str(path))
+    assert blk.n_ports == 2 and blk.refimp == 75.0 and blk.freq_unit == 1e9
+    assert np.allclose(blk.Sdata, S) and np.allclose(blk.Fdata, f)
+    with pytest.raises(ValueError):
+        hv.FileBasedNPort(str(tmp_path / "missing.s2p"))
+    bad = tmp_path / "x.s8p"
+    bad.write_text(path.read_text())
+    with pytest.raises(ValueError):
+        hv.FileBasedNPort(str(bad))                # suffix rejected unless ignore_extension
+    assert hv.FileBasedNPort(str(bad), ignore_extension=True).n_ports == 2
+
+
+def test_cauer_filter_values_and_counts():
+    m = hv.Model()
+    a, b = m.quick_port(50), m.quick_port(50)
+    caps, inds, load = m.filters.cauer_filter(m.gnd, a, b, 2.5e9, 0.2e9, 5, 0.05, hv.FilterType.CHEBYCHEV,
+                                              hv.BandType.BANDPASS, 50)
+    assert len(caps) == 5 and len(inds) == 5 and load == pytest.approx(1.0)
+    # series branch resonates at the centre frequency
+    assert 1 / (2 * np.pi * np.sqrt(caps[0].value * inds[0].value)) == pytest.approx(2.5e9, rel=1e-12)
+    m._prepare()
+    assert m.n_nodes == 10 and len(m.sources) == 2
+
+
+def test_run_sp_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = hv.Model()
+    a = m.quick_port(50)
+    m.resistor(a, m.gnd, 10.0)
+    with pytest.raises(RuntimeError):
+        m.run_sp(np.array([1e9]))

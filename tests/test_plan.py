@@ -1,0 +1,96 @@
+"""CPU: the plan compiler (value program + cell program + port tables) interpreted in numpy must
+reproduce the reference's dense tensor and S for every golden circuit, in every solver mode."""
+import numpy as np
+import pytest
+
+import heavi_b200 as hv
+import plan_interp as pi
+from heavi_b200 import plan as pl
+from helpers import dense_y, golden, max_ulps, parity_report, registry
+
+REG = registry(hv)
+
+
+@pytest.mark.parametrize("name", sorted(REG))
+def test_dump_plan_reproduces_reference_tensor(name):
+    g = golden(name)
+    tab = REG[name]().stamp_table()
+    W = pi.dump_plan(pl.compile_plan(tab, "dump"), g["y_f"])
+    Yg = dense_y(g)
+    assert np.array_equal(W != 0, Yg != 0) or max_ulps(W, Yg) < 200    # same stamp pattern
+    # inversion-based N-port blocks and lossy lines differ by rounding only
+    assert np.max(np.abs(W - Yg)) <= 1e-13 * max(1.0, np.max(np.abs(Yg)))
+
+
+@pytest.mark.parametrize("mode", ["full", "norton"])
+@pytest.mark.parametrize("name", sorted(REG))
+def test_plan_solves_to_reference(name, mode):
+    g = golden(name)
+    tab = REG[name]().stamp_table()
+    if mode == "norton" and not pl.norton_legal(tab):
+        pytest.skip("port internal node is shared")
+    p = pl.compile_plan(tab, mode)
+    f = g["f"] if name != "c5_ladder" else g["f"][:4]
+    S = pi.run_plan(p, f)[0]
+    nf = len(f)
+    frac, adjudicated, ext = parity_report(S, g["S"][:, :, :nf], g["S_ext"][:, :, :nf])
+    assert frac >= 0.998 and adjudicated and ext < 5e-14
+    expected_n = tab.N + tab.M - 1 if mode == "full" else tab.N - 1 - tab.P
+    assert p.n == expected_n and p.ncols == p.n + tab.P
+
+
+def test_norton_illegal_when_internal_node_is_shared():
+    m = hv.Model(suppress_loadbar=True)
+    a = m.node()
+    p1 = m.new_port(50, a)
+    b = m.quick_port(50)
+    m.resistor(a, b, 10.0)
+    m.capacitor(p1.int_node, m.gnd, 1e-12)       # something else touches the port's internal node
+    tab = m.stamp_table()
+    assert not pl.norton_legal(tab)
+    assert pl.compile_plan(tab, "auto").mode == "full"
+    with pytest.raises(ValueError):
+        pl.compile_plan(tab, "norton")
+
+
+def test_duplicate_index_last_write_wins():
+    """App. A: a part with both terminals on one node adds +y (not 0) to the diagonal."""
+    m = hv.Model(suppress_loadbar=True)
+    a = m.quick_port(50)
+    m.resistor(a, a, 25.0)
+    m.capacitor(a, m.gnd, 1e-12)
+    p = pl.compile_plan(m.stamp_table(), "dump")
+    W = pi.dump_plan(p, np.array([1e9]))
+    ia = a.index
+    assert W[ia, ia, 0].real == pytest.approx(1 / 50 + 1 / 25)
+
+
+def test_callable_scalar_and_table_parameters():
+    m = hv.Model(suppress_loadbar=True)
+    a = m.quick_port(50)
+    b = m.quick_port(50)
+    m.impedance(a, b, lambda f: 30.0)                         # callable returning a scalar
+    m.admittance(b, m.gnd, lambda f: 1e-3 + 2j * np.pi * f * 1e-12)
+    p = pl.compile_plan(m.stamp_table(), "auto")
+    f = np.array([1e9, 2e9, 3e9])
+    consts, prefs, tables, samples = pl.resolve_run(p, f)
+    assert tables.shape == (1, 3)                             # only the genuinely f-dependent one
+    kinds = [k for k, _ in prefs]
+    assert kinds.count(pl.PK_TABLE) == 1
+    S = pi.run_plan(p, f)[0]
+    from oracle import mna_oracle as orc
+    ref = orc.run_sp(m.records(), m.n_nodes, len(m.sources), f, method="lu_batched")
+    assert np.max(np.abs(S - ref)) < 1e-13
+
+
+def test_sample_parameters_and_batch_columns():
+    import circuits
+    g = golden("c4_mc")
+    m, f, mc = circuits.build_c4(hv)
+    p = pl.compile_plan(m.stamp_table(), "auto")
+    assert p.n_samples_cols == 10
+    S = pi.run_plan(p, g["f"][:64], mc._random_numbers, g["mc_draws"])
+    assert S.shape[0] == 4
+    frac, adj, ext = parity_report(S, g["mc_S"][:, :, :, :64], g["mc_S"][:, :, :, :64])
+    assert frac >= 0.95
+    assert np.max(np.abs(S - g["mc_S"][:, :, :, :64])) < 1e-10

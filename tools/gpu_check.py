@@ -38,6 +38,9 @@ def check(name, m, drivers=None, values=None, Sgold=None):
                            np.abs(S - ref).max(), np.abs(S - ext).max()))
             except Exception as e:
                 out.append("%s/blk%s: EXC %r" % (mode, force_block, e))
+                if "illegal" in repr(e) or "launch failure" in repr(e):
+                    print(" | ".join(out), flush=True)
+                    sys.exit(3)
     print(" | ".join(out), flush=True)
 
 if __name__ == "__main__":
