@@ -13,6 +13,7 @@
 #include "../../include/heavi_b200.h"
 #include "hvb_device.cuh"
 #include "hvb_kernels.h"
+#include "hvb_warp_shapes.h"
 
 static thread_local std::string g_err;
 
@@ -54,7 +55,7 @@ struct hvb_plan {
     int device = 0;
     hvb_plan_desc d{};
     // device copies of the static plan arrays
-    DevBuf const_vals, ops, coops, cell_ptr, cell_ent, port_rows, port_zpref, spl_t, spl_c, spl_trace, spl_fill, spl_range;
+    DevBuf const_vals, ops, coops, cell_ptr, cell_ent, row_ptr, row_ent, port_rows, port_zpref, spl_t, spl_c, spl_trace, spl_fill, spl_range;
     // per-run parameter buffers (device) + pinned staging
     DevBuf consts, prefs;
     void* h_stage = nullptr; size_t h_stage_bytes = 0;
@@ -78,10 +79,35 @@ static cudaError_t upload(DevBuf& b, const void* src, size_t bytes) {
     return e;
 }
 
-static int pick_pmax(int P) {
-    const int opts[4] = {2, 4, 8, 16};
-    for (int o : opts) if (P <= o) return o;
-    return 0;
+static const void* warp_kernel_ptr(int n, int p) {
+    const void* k = nullptr;
+    if (!k) k = hvb_warp_kernel_ptr_s1(n, p);
+    if (!k) k = hvb_warp_kernel_ptr_s2(n, p);
+    if (!k) k = hvb_warp_kernel_ptr_m1(n, p);
+    if (!k) k = hvb_warp_kernel_ptr_m2(n, p);
+    if (!k) k = hvb_warp_kernel_ptr_b1(n, p);
+    if (!k) k = hvb_warp_kernel_ptr_b2(n, p);
+    if (!k) k = hvb_warp_kernel_ptr_b3(n, p);
+    if (!k) k = hvb_warp_kernel_ptr_b4(n, p);
+    return k;
+}
+
+extern "C" int hvb_warp_shape(int32_t n, int32_t P, int32_t max_nport, int32_t* n_pad, int32_t* p_pad) {
+    if (!n_pad || !p_pad) return fail(HVB_ERR_ARG, "null argument");
+    *n_pad = 0; *p_pad = 0;
+    const char* force = getenv("HVB_FORCE_BLOCK");
+    if (force && force[0] == '1') return HVB_OK;
+    const int need = std::max(std::max(n, max_nport), 2), needp = std::max(P, 1);
+    double best = 0.0;
+    for (int i = 0; i < HVB_N_WARP_SHAPES; ++i) {
+        const int N = HVB_WARP_SHAPES[i][0], Pp = HVB_WARP_SHAPES[i][1];
+        if (N < need || Pp < needp) continue;
+        const int G = N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32;
+        // issue-slot cost of one point: lanes occupied x elimination work per lane
+        const double cost = (double)G * N * (0.5 * N + Pp + 6.0);
+        if (*n_pad == 0 || cost < best) { best = cost; *n_pad = N; *p_pad = Pp; }
+    }
+    return HVB_OK;
 }
 
 static int select_kernel(hvb_plan* pl) {
@@ -98,24 +124,21 @@ static int select_kernel(hvb_plan* pl) {
     }
     if (max_nport > HVB_MAX_NPORT) return fail(HVB_ERR_UNSUPPORTED, "N-port block with %d ports (max %d)", max_nport, HVB_MAX_NPORT);
     const int P = d.P;
-    const int need = std::max(d.n, max_nport);
+    const int PP = d.ncols - d.n;
+    pl->region_a = std::max(std::max(d.n_dyn, d.n * PP), 1);
+    const void* wk = warp_kernel_ptr(d.n, PP);
     const char* force = getenv("HVB_FORCE_BLOCK");
-    const int pmax = pick_pmax(P);
-    pl->region_a = std::max(std::max(d.n_dyn, d.n * P), 1);
-    if (need <= 32 && pmax > 0 && !(force && force[0] == '1')) {
-        int G = 4;
-        while (G < need) G *= 2;
-        pl->kclass = 0; pl->G = G; pl->PMAX = pmax;
-        switch (G) {
-            case 4: pl->kernel = hvb_warp_kernel_ptr_g4(pmax); break;
-            case 8: pl->kernel = hvb_warp_kernel_ptr_g8(pmax); break;
-            case 16: pl->kernel = hvb_warp_kernel_ptr_g16(pmax); break;
-            default: pl->kernel = hvb_warp_kernel_ptr_g32(pmax); break;
-        }
+    const size_t staged = (size_t)d.n_const_vals * 16 + (size_t)(d.n + 1 + d.n_row_ent) * 4 + 16;
+    if (wk && max_nport <= d.n && staged <= 24576 && !(force && force[0] == '1')) {
+        const int N = d.n;
+        const int G = N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32;
+        pl->kclass = 0; pl->G = N; pl->PMAX = PP;
+        pl->kernel = wk;
         pl->threads = hvb_warp_threads();
-        pl->region_b = std::max(d.coop_scratch, 2 * (G + pmax));
+        pl->region_b = std::max(d.coop_scratch, N * (N + PP));
         const int sys_per_block = (pl->threads / 32) * (32 / G);
-        pl->smem = (size_t)sys_per_block * (pl->region_a + pl->region_b) * sizeof(cplx);
+        const size_t shared_words = (size_t)d.n_const_vals + (((size_t)(N + 1 + d.n_row_ent) * 4 + 15) / 16);
+        pl->smem = (shared_words + (size_t)sys_per_block * (pl->region_a + pl->region_b)) * sizeof(cplx);
     } else {
         pl->kclass = 1;
         const char* nbs = getenv("HVB_BLOCK_NB");
@@ -167,6 +190,8 @@ extern "C" int hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan**
     up(pl->coops, d.coops, (size_t)d.n_coops * HVB_COOP_WORDS * 4);
     up(pl->cell_ptr, d.cell_ptr, (size_t)(ncell + 1) * 4);
     up(pl->cell_ent, d.cell_ent, (size_t)nnz * 4);
+    up(pl->row_ptr, d.row_ptr, (size_t)(d.n + 1) * 4);
+    up(pl->row_ent, d.row_ent, (size_t)d.n_row_ent * 4);
     up(pl->port_rows, d.port_rows, (size_t)d.P * 3 * 4);
     up(pl->port_zpref, d.port_zpref, (size_t)d.P * 4);
     up(pl->spl_t, d.spl_t, (size_t)d.n_knots * 8);
@@ -187,10 +212,10 @@ extern "C" int hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan**
         return fail(HVB_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(e));
     }
     // the descriptor's host pointers are not kept
-    pl->d.const_vals = nullptr; pl->d.ops = nullptr; pl->d.coops = nullptr; pl->d.cell_ptr = nullptr; pl->d.cell_ent = nullptr;
+    pl->d.const_vals = nullptr; pl->d.ops = nullptr; pl->d.coops = nullptr; pl->d.cell_ptr = nullptr; pl->d.cell_ent = nullptr; pl->d.row_ptr = nullptr; pl->d.row_ent = nullptr;
     pl->d.port_rows = nullptr; pl->d.port_zpref = nullptr; pl->d.spl_t = nullptr; pl->d.spl_c = nullptr; pl->d.spl_trace = nullptr;
     pl->d.spl_fill = nullptr; pl->d.spl_range = nullptr;
-    if (d.ncols == d.n + d.P) {                 // dump-only plans (no right-hand sides) never solve
+    if (d.ncols >= d.n + d.P && d.ncols > d.n) { // dump-only plans (no right-hand sides) never solve
         int rc = select_kernel(pl);
         if (rc != HVB_OK) { hvb_plan_destroy(pl); return rc; }
     }
@@ -201,7 +226,7 @@ extern "C" int hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan**
 extern "C" void hvb_plan_destroy(hvb_plan* pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
-    DevBuf* all[] = {&pl->const_vals, &pl->ops, &pl->coops, &pl->cell_ptr, &pl->cell_ent, &pl->port_rows, &pl->port_zpref,
+    DevBuf* all[] = {&pl->const_vals, &pl->ops, &pl->coops, &pl->cell_ptr, &pl->cell_ent, &pl->row_ptr, &pl->row_ent, &pl->port_rows, &pl->port_zpref,
                      &pl->spl_t, &pl->spl_c, &pl->spl_trace, &pl->spl_fill, &pl->spl_range, &pl->consts, &pl->prefs,
                      &pl->f, &pl->samples, &pl->tables, &pl->S[0], &pl->S[1], &pl->status, &pl->work, &pl->dump};
     for (DevBuf* b : all) b->release();
@@ -215,11 +240,14 @@ static HvbDev make_dev(const hvb_plan* pl) {
     HvbDev D{};
     const hvb_plan_desc& d = pl->d;
     D.n = d.n; D.ncols = d.ncols; D.P = d.P;
+    D.PP = d.ncols - d.n; D.nnz_rows = d.n_row_ent;
+    D.row_ptr = (const int*)pl->row_ptr.p;
+    D.row_ent = (const int*)pl->row_ent.p;
     D.nvc = d.n_const_vals; D.ndyn = d.n_dyn; D.nops = d.n_ops; D.ncoops = d.n_coops; D.nR = d.n_samples_cols;
     D.coop_scratch = d.coop_scratch;
     D.region_a = pl->region_a; D.region_b = pl->region_b;
-    D.consts = (const cplx*)pl->consts.p;
-    D.prefs = (const int2*)pl->prefs.p;
+    D.pv.consts = (const cplx*)pl->consts.p;
+    D.pv.prefs = (const int2*)pl->prefs.p;
     D.const_vals = (const cplx*)pl->const_vals.p;
     D.ops = (const int*)pl->ops.p;
     D.coops = (const int*)pl->coops.p;
@@ -227,11 +255,11 @@ static HvbDev make_dev(const hvb_plan* pl) {
     D.cell_ent = (const int*)pl->cell_ent.p;
     D.port_rows = (const int*)pl->port_rows.p;
     D.port_zpref = (const int*)pl->port_zpref.p;
-    D.spl_t = (const double*)pl->spl_t.p;
-    D.spl_c = (const cplx*)pl->spl_c.p;
-    D.spl_trace = (const int4*)pl->spl_trace.p;
-    D.spl_fill = (const cplx*)pl->spl_fill.p;
-    D.spl_range = (const double2*)pl->spl_range.p;
+    D.pv.spl_t = (const double*)pl->spl_t.p;
+    D.pv.spl_c = (const cplx*)pl->spl_c.p;
+    D.pv.spl_trace = (const int4*)pl->spl_trace.p;
+    D.pv.spl_fill = (const cplx*)pl->spl_fill.p;
+    D.pv.spl_range = (const double2*)pl->spl_range.p;
     D.W = (cplx*)pl->work.p;
     return D;
 }
@@ -257,7 +285,8 @@ static int launch(hvb_plan* pl, HvbDev& D, cudaStream_t st) {
     if (total <= 0) return HVB_OK;
     long long blocks;
     if (pl->kclass == 0) {
-        const int spb = (pl->threads / 32) * (32 / pl->G);
+        const int N = pl->G;
+        const int spb = (pl->threads / 32) * (32 / (N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32));
         blocks = (total + spb - 1) / spb;
     } else {
         blocks = total;
@@ -280,14 +309,14 @@ static int check_args(const hvb_plan* pl, const hvb_run_args* a) {
 extern "C" int hvb_run_device(hvb_plan* pl, const hvb_run_args* a, double* d_S, int64_t ldS, int32_t* d_status, void* stream) {
     int rc = check_args(pl, a);
     if (rc) return rc;
-    if (pl->d.ncols != pl->d.n + pl->d.P) return fail(HVB_ERR_ARG, "plan has no right-hand sides (dump plan)");
+    if (pl->d.ncols <= pl->d.n || !pl->kernel) return fail(HVB_ERR_ARG, "plan has no right-hand sides (dump plan)");
     CU(cudaSetDevice(pl->device));
     cudaStream_t st = (cudaStream_t)stream;
     rc = push_params(pl, a, st);
     if (rc) return rc;
     HvbDev D = make_dev(pl);
-    D.nF = a->nF; D.nS = a->nS; D.ldS = ldS; D.table_ld = a->nF;
-    D.f = a->f; D.samples = a->samples; D.tables = (const cplx*)a->tables;
+    D.nF = a->nF; D.nS = a->nS; D.ldS = ldS; D.pv.table_ld = a->nF;
+    D.f = a->f; D.samples = a->samples; D.pv.tables = (const cplx*)a->tables;
     D.S = (cplx*)d_S; D.status = d_status;
     return launch(pl, D, st);
 }
@@ -297,7 +326,7 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     if (rc) return rc;
     if (!S_out) return fail(HVB_ERR_ARG, "S_out is NULL");
     const hvb_plan_desc& d = pl->d;
-    if (d.ncols != d.n + d.P) return fail(HVB_ERR_ARG, "plan has no right-hand sides (dump plan)");
+    if (d.ncols <= d.n || !pl->kernel) return fail(HVB_ERR_ARG, "plan has no right-hand sides (dump plan)");
     CU(cudaSetDevice(pl->device));
     const int64_t nF = a->nF, nS = a->nS;
     const int64_t PP = (int64_t)d.P * d.P;
@@ -343,10 +372,10 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
             const int64_t nf = std::min(Fc, nF - fb);
             cudaStream_t st = pl->streams[tile & 1];
             HvbDev D = make_dev(pl);
-            D.nF = nf; D.nS = ns; D.ldS = nf; D.table_ld = nF;
+            D.nF = nf; D.nS = ns; D.ldS = nf; D.pv.table_ld = nF;
             D.f = (const double*)pl->f.p + fb;
             D.samples = d.n_samples_cols ? (const double*)pl->samples.p + sb * d.n_samples_cols : nullptr;
-            D.tables = a->n_tables ? (const cplx*)pl->tables.p + fb : nullptr;
+            D.pv.tables = a->n_tables ? (const cplx*)pl->tables.p + fb : nullptr;
             D.S = (cplx*)pl->S[tile & 1].p;
             D.status = (int*)pl->status.p;
             rc = launch(pl, D, st);
@@ -390,10 +419,10 @@ extern "C" int hvb_assemble_host(hvb_plan* pl, const hvb_run_args* a, double* W_
     const size_t bytes = (size_t)pts * d.n * d.ncols * 16;
     CU(pl->dump.ensure(bytes));
     HvbDev D = make_dev(pl);
-    D.nF = nF; D.nS = nS; D.ldS = nF; D.table_ld = nF;
+    D.nF = nF; D.nS = nS; D.ldS = nF; D.pv.table_ld = nF;
     D.f = (const double*)pl->f.p;
     D.samples = (const double*)pl->samples.p;
-    D.tables = (const cplx*)pl->tables.p;
+    D.pv.tables = (const cplx*)pl->tables.p;
     D.W = (cplx*)pl->dump.p;
     D.region_a = std::max(d.n_dyn, 1);
     D.region_b = std::max(d.coop_scratch, 1);

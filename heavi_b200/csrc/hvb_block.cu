@@ -47,9 +47,10 @@ __global__ void __launch_bounds__(HVB_BLOCK_THREADS) hvb_block_kernel(const HvbD
         if (tid == 0) sh_bad = 0;
 
         // ---- values -------------------------------------------------------------------------
-        if (warp == 0)
-            for (int o = 0; o < D.ncoops; ++o)
-                bad |= coop_nport<32>(D, D.coops + o * HVB_COOP_WORDS, f, fi, srow, dyn, scratch, lane);
+        if (warp == 0 && D.ncoops > 0) {
+            CoopCtx ctx{D.pv, D.nvc, f, fi, srow, dyn, scratch};
+            for (int o = 0; o < D.ncoops; ++o) bad |= coop_nport<32>(&ctx, D.coops + o * HVB_COOP_WORDS, lane);
+        }
         for (int o = tid; o < D.nops; o += HVB_BLOCK_THREADS)
             eval_simple_op(D, D.ops + o * HVB_OP_WORDS, f, fi, srow, dyn);
         __syncthreads();
@@ -219,8 +220,8 @@ __global__ void __launch_bounds__(HVB_BLOCK_THREADS) hvb_block_kernel(const HvbD
         __syncthreads();
         for (int e = tid; e < P * P; e += HVB_BLOCK_THREADS) {
             const int j = e / P, i = e - j * P;
-            const cplx Zi = eval_param(D, __ldg(D.port_zpref + i), f, fi, srow);
-            const cplx Zj = eval_param(D, __ldg(D.port_zpref + j), f, fi, srow);
+            const cplx Zi = eval_param(D.pv, __ldg(D.port_zpref + i), f, fi, srow);
+            const cplx Zj = eval_param(D.pv, __ldg(D.port_zpref + j), f, fi, srow);
             const cplx sv = s_entry(D, xs, j, i, Zi, Zj);
             if (!(isfinite(sv.x) && isfinite(sv.y))) bad |= HVB_STATUS_NONFINITE_BIT;
             D.S[((s * P + j) * P + i) * D.ldS + fi] = sv;
@@ -246,8 +247,10 @@ __global__ void __launch_bounds__(32) hvb_dump_kernel(const HvbDev D) {
         const long long s = q / D.nF, fi = q - s * D.nF;
         const double f = __ldg(D.f + fi);
         const double* __restrict__ srow = D.samples + s * D.nR;
-        for (int o = 0; o < D.ncoops; ++o)
-            coop_nport<32>(D, D.coops + o * HVB_COOP_WORDS, f, fi, srow, dyn, scratch, lane);
+        if (D.ncoops > 0) {
+            CoopCtx ctx{D.pv, D.nvc, f, fi, srow, dyn, scratch};
+            for (int o = 0; o < D.ncoops; ++o) coop_nport<32>(&ctx, D.coops + o * HVB_COOP_WORDS, lane);
+        }
         for (int o = lane; o < D.nops; o += 32) eval_simple_op(D, D.ops + o * HVB_OP_WORDS, f, fi, srow, dyn);
         __syncwarp();
         for (int cell = lane; cell < cells; cell += 32) D.W[(size_t)q * cells + cell] = gather_cell(D, cell, dyn);

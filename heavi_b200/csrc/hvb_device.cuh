@@ -13,30 +13,39 @@
 
 typedef double2 cplx;
 
-struct HvbDev {
-    int n, ncols, P;
-    int nvc, ndyn, nops, ncoops, nR, coop_scratch;
-    int region_a, region_b;                 // per-system shared-memory regions (complex words)
-    long long nF, nS;                       // points of this launch: q = s*nF + fi
-    long long ldS;                          // frequency pitch of the S output (elements)
-    long long table_ld;                     // frequency pitch of the tables
-    const double* f;
-    const double* samples;
-    const cplx* tables;
+// what a parameter reference needs (kept separate so that out-of-line helpers can take a copy)
+struct ParamView {
     const cplx* consts;
     const int2* prefs;
-    const cplx* const_vals;
-    const int* ops;
-    const int* coops;
-    const int* cell_ptr;
-    const int* cell_ent;
-    const int* port_rows;
-    const int* port_zpref;
+    const cplx* tables;
+    long long table_ld;                     // frequency pitch of the tables
     const double* spl_t;
     const cplx* spl_c;
     const int4* spl_trace;
     const cplx* spl_fill;
     const double2* spl_range;
+};
+
+struct HvbDev {
+    int n, ncols, P;                        // rows, rows + RHS columns (both possibly padded), real ports
+    int PP;                                 // RHS columns = ncols - n (stride of the solution rows)
+    int nnz_rows;                           // entries in row_ent
+    int nvc, ndyn, nops, ncoops, nR, coop_scratch;
+    int region_a, region_b;                 // per-system shared-memory regions (complex words)
+    long long nF, nS;                       // points of this launch: q = s*nF + fi
+    long long ldS;                          // frequency pitch of the S output (elements)
+    ParamView pv;
+    const double* f;
+    const double* samples;
+    const cplx* const_vals;
+    const int* ops;
+    const int* coops;
+    const int* cell_ptr;
+    const int* cell_ent;
+    const int* row_ptr;                     // per-row entry lists (kernel A's assembly)
+    const int* row_ent;
+    const int* port_rows;
+    const int* port_zpref;
     cplx* S;
     cplx* W;                                // dense dump / block-kernel workspace
     int* status;
@@ -180,7 +189,7 @@ static __device__ __noinline__ cplx spline_eval(const double* __restrict__ spl_t
 // ------------------------------------------------------------------------------------------------
 // parameter reference -> complex value at (f, sample row, frequency index)
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ cplx eval_param(const HvbDev& D, int pi, double f, long long fi,
+__device__ __forceinline__ cplx eval_param(const ParamView& D, int pi, double f, long long fi,
                                            const double* __restrict__ srow) {
     const int2 pr = D.prefs[pi];
     switch (pr.x) {
@@ -245,7 +254,7 @@ __device__ __forceinline__ void eval_simple_op(const HvbDev& D, const int* __res
                                                cplx* __restrict__ dyn) {
     const int code = op[0];
     const int out = op[1] - D.nvc;
-    const cplx p0 = eval_param(D, op[2], f, fi, srow);
+    const cplx p0 = eval_param(D.pv, op[2], f, fi, srow);
     switch (code) {
         case OP_COPY:            // base/admittance.py:38-40
             dyn[out] = p0;
@@ -266,8 +275,8 @@ __device__ __forceinline__ void eval_simple_op(const HvbDev& D, const int* __res
             break;
         }
         case OP_TLINE: {         // base/tl.py:30-60
-            const cplx beta = eval_param(D, op[3], f, fi, srow);
-            eval_tline(p0, beta, D.consts[op[4]].x, dyn + out);
+            const cplx beta = eval_param(D.pv, op[3], f, fi, srow);
+            eval_tline(p0, beta, D.pv.consts[op[4]].x, dyn + out);
             break;
         }
     }
@@ -301,18 +310,18 @@ __device__ __forceinline__ cplx gather_cell(const HvbDev& D, int cell, const cpl
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ cplx port_volt(const HvbDev& D, const cplx* __restrict__ xs, int q, int which, int i) {
     const int r = __ldg(D.port_rows + 3 * q + which);
-    if (r >= 0) return xs[r * D.P + i];
+    if (r >= 0) return xs[r * D.PP + i];
     if (r == ROW_GROUND) return cmk(0.0, 0.0);
     // ROW_VIRTUAL_INT: V_int = V_ref + E, E = 1 V on the excited port and 0 V elsewhere
     const int rg = __ldg(D.port_rows + 3 * q + 2);
-    cplx v = rg >= 0 ? xs[rg * D.P + i] : cmk(0.0, 0.0);
+    cplx v = rg >= 0 ? xs[rg * D.PP + i] : cmk(0.0, 0.0);
     if (q == i) v.x += 1.0;
     return v;
 }
 
 __device__ __forceinline__ cplx cdiv_plain(cplx a, cplx b) {
     const double d = fma(b.x, b.x, b.y * b.y);
-    const double r = 1.0 / d;
+    const double r = rcp_fast(d);
     return cmk((a.x * b.x + a.y * b.y) * r, (a.y * b.x - a.x * b.y) * r);
 }
 
@@ -325,6 +334,7 @@ __device__ __forceinline__ cplx s_entry(const HvbDev& D, const cplx* __restrict_
     // denominator = (Vi1 - Vi2) - Zi * (Vi1 - Vi3) / Zi
     cplx den = csub(csub(Vi1, Vi2), cdiv_plain(cmul(Zi, csub(Vi1, Vi3)), Zi));
     cplx s = cdiv_plain(num, den);
+    if (Zi.x == Zj.x) return s;                        // sqrt|Re Zi| / sqrt|Re Zj| == 1
     const double sc = sqrt(fabs(Zi.x)) / sqrt(fabs(Zj.x));
     return cscale(s, sc);
 }

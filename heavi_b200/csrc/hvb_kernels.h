@@ -2,10 +2,14 @@
 #pragma once
 #include <stddef.h>
 
-const void* hvb_warp_kernel_ptr_g4(int pmax);
-const void* hvb_warp_kernel_ptr_g8(int pmax);
-const void* hvb_warp_kernel_ptr_g16(int pmax);
-const void* hvb_warp_kernel_ptr_g32(int pmax);
+const void* hvb_warp_kernel_ptr_s1(int n, int p);
+const void* hvb_warp_kernel_ptr_s2(int n, int p);
+const void* hvb_warp_kernel_ptr_m1(int n, int p);
+const void* hvb_warp_kernel_ptr_m2(int n, int p);
+const void* hvb_warp_kernel_ptr_b1(int n, int p);
+const void* hvb_warp_kernel_ptr_b2(int n, int p);
+const void* hvb_warp_kernel_ptr_b3(int n, int p);
+const void* hvb_warp_kernel_ptr_b4(int n, int p);
 int hvb_warp_threads();
 
 const void* hvb_block_kernel_ptr(int nb);

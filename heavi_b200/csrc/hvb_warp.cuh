@@ -2,21 +2,27 @@
 //
 // One system (one (sample, frequency) point) is owned by a group of G in {4,8,16,32} lanes, so a
 // warp works on 32/G points at once.  Lane r of the group holds row r of the augmented matrix
-// [A | B] in registers: G complex matrix columns + PMAX complex right-hand sides.  Per point:
+// [A | B] in registers: N complex matrix columns + P complex right-hand sides, N and P template
+// constants (the host pads the plan to an instantiated shape with identity rows / zero columns,
+// so the elimination loops carry no bounds checks at all).  Per point:
 //
 //   1. value program  -> per-point stamp values in shared memory (group-cooperative N-port ops,
 //                        then the simple ops distributed over the lanes)
-//   2. gather         -> each lane sums its row's cells from the cell program (component order)
-//   3. Gauss-Jordan   -> n pivot steps with implicit partial pivoting: rows never move; the pivot
+//   2. assembly       -> each lane walks its row's entry list (sorted by column, component order
+//                        inside a cell = the reference's order of `+=`), accumulates a cell in
+//                        registers and drops it into its shared-memory row; the row is then read
+//                        back with compile-time column indices
+//   3. Gauss-Jordan   -> N pivot steps with implicit partial pivoting: rows never move; the pivot
 //                        lane is found with a 32-bit key butterfly (|re|+|im| like LAPACK izamax,
 //                        ties to the lowest row), publishes its row through a double-buffered
 //                        shared-memory line, and every other row eliminates column k.  Because
 //                        rows above and below are eliminated there is no back substitution: after
-//                        n steps row r holds x[col(r)] = b_r / pivot_r for all P excitations.
+//                        N steps row r holds x[col(r)] = b_r / pivot_r for all P excitations.
 //   4. epilogue       -> S[j,i] from port voltages (solvers/spfn.py:159-176), stored with
 //                        frequency fastest so neighbouring groups/warps write neighbouring words.
 //
-// No __syncthreads anywhere: a group only ever synchronises with its own warp.
+// One __syncthreads at kernel start (plan tables staged into shared memory); after that a group
+// only ever synchronises with its own warp.
 #pragma once
 #include "hvb_device.cuh"
 
@@ -33,12 +39,15 @@ __device__ __forceinline__ void static_for(F&& fn) {
     }
 }
 
+__host__ __device__ constexpr int hvb_group_for(int n) { return n <= 4 ? 4 : n <= 8 ? 8 : n <= 16 ? 16 : 32; }
+
 // registers per thread are capped so that small systems keep many warps resident
-template <int G, int PMAX>
+template <int N, int P>
 struct WarpCfg {
-    static constexpr int kRegsWanted = 4 * (G + PMAX) + 44;
-    static constexpr int kMinBlocks = kRegsWanted <= 64 ? 8 : kRegsWanted <= 80 ? 6 : kRegsWanted <= 96 ? 5
-                                    : kRegsWanted <= 128 ? 4 : kRegsWanted <= 168 ? 3 : kRegsWanted <= 255 ? 2 : 1;
+    static constexpr int kRegsWanted = (4 * (N + P) + 48) < 88 ? 88 : (4 * (N + P) + 48);
+    static constexpr int kMinBlocks = kRegsWanted <= 64 ? 8 : kRegsWanted <= 72 ? 7 : kRegsWanted <= 80 ? 6
+                                    : kRegsWanted <= 96 ? 5 : kRegsWanted <= 128 ? 4 : kRegsWanted <= 168 ? 3
+                                    : kRegsWanted <= 255 ? 2 : 1;
 };
 
 template <int G>
@@ -55,11 +64,11 @@ __device__ __forceinline__ unsigned pivot_key(cplx v, bool excluded, int gl) {
     const unsigned hi = (unsigned)__double2hiint(mag);
     return excluded ? 0u : (((hi & ~31u) | (unsigned)(31 - gl)) + 32u);
 }
-__device__ __forceinline__ unsigned pivot_status(unsigned key) {
-    const unsigned top = (key - 32u) & ~31u;
+// smallest / largest winning key of a point -> status bits (zero pivot, NaN/Inf)
+__device__ __forceinline__ unsigned pivot_status(unsigned kmin, unsigned kmax) {
     unsigned bad = 0;
-    if (key < 32u || top == 0u) bad |= HVB_STATUS_ZERO_PIVOT_BIT;
-    if (top >= 0x7FF00000u) bad |= HVB_STATUS_NONFINITE_BIT;
+    if (kmin < 64u) bad |= HVB_STATUS_ZERO_PIVOT_BIT;               // |pivot| below 2^-1022
+    if (((kmax - 32u) & ~31u) >= 0x7FF00000u) bad |= HVB_STATUS_NONFINITE_BIT;
     return bad;
 }
 
@@ -68,14 +77,29 @@ __device__ __forceinline__ unsigned pivot_status(unsigned key) {
 //   S_ij(f) -> Y = (1/Z0) (I - S) (I + S)^-1 -> (P+1)x(P+1) indefinite block with the reference
 //   node's row / column.  The inverse is applied as a solve of (I+S)^T X^T = (I-S)^T with the
 //   same implicit-pivot Gauss-Jordan, rows in the group's shared-memory scratch.
+// Kept out of line: it is only reached by circuits that contain an N-port block.
 // ------------------------------------------------------------------------------------------------
+struct CoopCtx {
+    ParamView pv;
+    int nvc;
+    double f;
+    long long fi;
+    const double* srow;
+    cplx* dyn;
+    cplx* scratch;
+};
+
 template <int G>
-__device__ __forceinline__ unsigned coop_nport(const HvbDev& D, const int* __restrict__ op, double f, long long fi,
-                                               const double* __restrict__ srow, cplx* __restrict__ dyn,
-                                               cplx* __restrict__ scratch, int gl) {
-    const int code = op[0], out = op[1] - D.nvc, Pn = op[2], first = op[3];
+static __device__ __noinline__ unsigned coop_nport(const CoopCtx* ctx, const int* __restrict__ op, int gl) {
+    const ParamView& D = ctx->pv;
+    const double f = ctx->f;
+    const long long fi = ctx->fi;
+    const double* __restrict__ srow = ctx->srow;
+    cplx* __restrict__ dyn = ctx->dyn;
+    cplx* __restrict__ scratch = ctx->scratch;
+    const int code = op[0], out = op[1] - ctx->nvc, Pn = op[2], first = op[3];
     const int ldo = Pn + 1;
-    unsigned bad = 0;
+    unsigned kmin = 0xffffffffu, kmax = 0u;
     if (code == COOP_NPORT_Y) {
         for (int e = gl; e < Pn * Pn; e += G)
             dyn[out + (e / Pn) * ldo + (e % Pn)] = eval_param(D, first + e, f, fi, srow);
@@ -95,7 +119,7 @@ __device__ __forceinline__ unsigned coop_nport(const HvbDev& D, const int* __res
         for (int k = 0; k < Pn; ++k) {
             const cplx mine = (gl < Pn) ? scratch[gl * ld + k] : cmk(0.0, 0.0);
             const unsigned key = group_max_u32<G>(pivot_key(mine, done, gl));
-            bad |= pivot_status(key);
+            kmin = min(kmin, key); kmax = max(kmax, key);
             const int p = 31 - (int)(key & 31u);
             if (gl == p) { done = true; mycol = k; }
             const cplx inv = crecip_fast(scratch[p * ld + k]);
@@ -138,26 +162,43 @@ __device__ __forceinline__ unsigned coop_nport(const HvbDev& D, const int* __res
         dyn[out + Pn * ldo + Pn] = tot;
     }
     __syncwarp();
-    return bad;
+    return (code == COOP_NPORT_S) ? pivot_status(kmin, kmax) : 0u;
 }
+
+// row entry: bit 0 negate, bits 1..19 value id, bits 20..30 column, bit 31 last entry of its cell
+#define HVB_ENT_VID(e) (((e) >> 1) & 0x7FFFF)
+#define HVB_ENT_COL(e) (((e) >> 20) & 0x7FF)
 
 // ------------------------------------------------------------------------------------------------
 // kernel A
 // ------------------------------------------------------------------------------------------------
-template <int G, int PMAX>
-__global__ void __launch_bounds__(HVB_WARP_THREADS, WarpCfg<G, PMAX>::kMinBlocks) hvb_warp_kernel(const HvbDev D) {
+template <int N, int P>
+__global__ void __launch_bounds__(HVB_WARP_THREADS, WarpCfg<N, P>::kMinBlocks) hvb_warp_kernel(const HvbDev D) {
     extern __shared__ __align__(16) unsigned char hvb_smem[];
+    constexpr int G = hvb_group_for(N);
     constexpr int SPW = 32 / G;
-    constexpr int BROW = G + PMAX;                       // one broadcast line (complex words)
+    constexpr int NC = N + P;                            // columns of one augmented row
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane % G, grp = lane / G;
     const int sys_in_block = warp * SPW + grp;
-    const int sys_per_block = (HVB_WARP_THREADS / 32) * SPW;
-    cplx* regA = reinterpret_cast<cplx*>(hvb_smem) + (size_t)sys_in_block * (D.region_a + D.region_b);
+    constexpr int sys_per_block = (HVB_WARP_THREADS / 32) * SPW;
+    const int Pr = D.P;                                  // real ports (<= P)
+
+    // ---- block-shared copies of the small plan tables ------------------------------------------
+    cplx* cvS = reinterpret_cast<cplx*>(hvb_smem);                       // [nvc]
+    int* rowptrS = reinterpret_cast<int*>(cvS + D.nvc);                  // [N+1]
+    int* rowentS = rowptrS + (N + 1);                                    // [nnz_rows]
+    const int shared_words = D.nvc + (((N + 1 + D.nnz_rows) * 4 + 15) / 16);
+    for (int i = threadIdx.x; i < D.nvc; i += HVB_WARP_THREADS) cvS[i] = D.const_vals[i];
+    for (int i = threadIdx.x; i <= N; i += HVB_WARP_THREADS) rowptrS[i] = D.row_ptr[i];
+    for (int i = threadIdx.x; i < D.nnz_rows; i += HVB_WARP_THREADS) rowentS[i] = D.row_ent[i];
+    __syncthreads();
+
+    cplx* regA = reinterpret_cast<cplx*>(hvb_smem) + shared_words + (size_t)sys_in_block * (D.region_a + D.region_b);
     cplx* regB = regA + D.region_a;
-    const int n = D.n, P = D.P, ncols = D.ncols;
     const long long total = D.nS * D.nF;
     const int r = gl;
+    const int nvc = D.nvc;
 
     for (long long q0 = (long long)blockIdx.x * sys_per_block; q0 < total;
          q0 += (long long)gridDim.x * sys_per_block) {
@@ -170,95 +211,82 @@ __global__ void __launch_bounds__(HVB_WARP_THREADS, WarpCfg<G, PMAX>::kMinBlocks
         unsigned bad = 0;
 
         // ---- 1. value program ----------------------------------------------------------------
-        for (int o = 0; o < D.ncoops; ++o)
-            bad |= coop_nport<G>(D, D.coops + o * HVB_COOP_WORDS, f, fi, srow, regA, regB, gl);
+        if (D.ncoops > 0) {
+            CoopCtx ctx{D.pv, D.nvc, f, fi, srow, regA, regB};
+            for (int o = 0; o < D.ncoops; ++o) bad |= coop_nport<G>(&ctx, D.coops + o * HVB_COOP_WORDS, gl);
+        }
         for (int o = gl; o < D.nops; o += G) eval_simple_op(D, D.ops + o * HVB_OP_WORDS, f, fi, srow, regA);
         __syncwarp();
 
-        // ---- 2. gather this lane's row ---------------------------------------------------------
-        cplx a[G], b[PMAX];
+        // ---- 2. assemble this lane's row -------------------------------------------------------
+        cplx a[N], b[P];
         {
-            const bool live = r < n;
-            int lo = live ? __ldg(D.cell_ptr + r * ncols) : 0;
-            auto gather = [&](bool on, int cell_end) -> cplx {
+            cplx* __restrict__ rowbuf = regB + (r < N ? r : 0) * NC;
+            if (r < N) {
+                static_for<0, NC>([&](auto cc) { rowbuf[decltype(cc)::value] = cmk(0.0, 0.0); });
+                const int lo = rowptrS[r], hi = rowptrS[r + 1];
                 cplx acc = cmk(0.0, 0.0);
-                if (on) {
-                    const int hi = __ldg(D.cell_ptr + cell_end);
-                    for (int e = lo; e < hi; ++e) {
-                        const int ent = __ldg(D.cell_ent + e);
-                        const cplx v = load_value(D, ent >> 1, regA);
-                        if (ent & 1) { acc.x -= v.x; acc.y -= v.y; } else { acc.x += v.x; acc.y += v.y; }
-                    }
-                    lo = hi;
+                for (int e = lo; e < hi; ++e) {
+                    const int ent = rowentS[e];
+                    const int vid = HVB_ENT_VID(ent);
+                    const cplx v = (vid < nvc) ? cvS[vid] : regA[vid - nvc];
+                    if (ent & 1) { acc.x -= v.x; acc.y -= v.y; } else { acc.x += v.x; acc.y += v.y; }
+                    if (ent < 0) { rowbuf[HVB_ENT_COL(ent)] = acc; acc = cmk(0.0, 0.0); }
                 }
-                return acc;
-            };
-            static_for<0, G>([&](auto cc) {
+            }
+            static_for<0, N>([&](auto cc) {
                 constexpr int c = decltype(cc)::value;
-                a[c] = gather(live && c < n, r * ncols + c + 1);
+                a[c] = (r < N) ? rowbuf[c] : cmk(0.0, 0.0);
             });
-            static_for<0, PMAX>([&](auto ii) {
+            static_for<0, P>([&](auto ii) {
                 constexpr int i = decltype(ii)::value;
-                b[i] = gather(live && i < P, r * ncols + n + i + 1);
+                b[i] = (r < N) ? rowbuf[N + i] : cmk(0.0, 0.0);
             });
         }
-        __syncwarp();
+        __syncwarp();                                     // row buffers alias the broadcast lines
 
         // ---- 3. Gauss-Jordan with implicit partial pivoting ------------------------------------
-        bool done = r >= n;
+        bool done = r >= N;
         int mycol = 0;
         cplx myinv = cmk(0.0, 0.0);
-        static_for<0, G>([&](auto kk) {
+        unsigned kmin = 0xffffffffu, kmax = 0u;
+        static_for<0, N>([&](auto kk) {
             constexpr int k = decltype(kk)::value;
-            if (k < n) {
-                const unsigned key = group_max_u32<G>(pivot_key(a[k], done, gl));
-                bad |= pivot_status(key);
-                const int p = 31 - (int)(key & 31u);
-                const bool is_p = (gl == p);
-                cplx* __restrict__ brow = regB + (k & 1) * BROW;
-                if (is_p) {
-                    static_for<k, G>([&](auto cc) {
-                        constexpr int c = decltype(cc)::value;
-                        if (c < n) brow[c] = a[c];
-                    });
-                    static_for<0, PMAX>([&](auto ii) {
-                        constexpr int i = decltype(ii)::value;
-                        if (i < P) brow[G + i] = b[i];
-                    });
-                    done = true;
-                    mycol = k;
-                }
-                __syncwarp();
-                const cplx inv = crecip_fast(brow[k]);
-                cplx m = cmul(a[k], inv);
-                if (is_p) { myinv = inv; m = cmk(0.0, 0.0); }
-                static_for<k + 1, G>([&](auto cc) {
-                    constexpr int c = decltype(cc)::value;
-                    if (c < n) cfnma(a[c], m, brow[c]);
-                });
-                static_for<0, PMAX>([&](auto ii) {
-                    constexpr int i = decltype(ii)::value;
-                    if (i < P) cfnma(b[i], m, brow[G + i]);
-                });
+            const unsigned key = group_max_u32<G>(pivot_key(a[k], done, gl));
+            kmin = min(kmin, key); kmax = max(kmax, key);
+            const bool is_p = (gl == 31 - (int)(key & 31u));
+            cplx* __restrict__ brow = regB + (k & 1) * NC;
+            if (is_p) {
+                static_for<k, N>([&](auto cc) { brow[decltype(cc)::value] = a[decltype(cc)::value]; });
+                static_for<0, P>([&](auto ii) { brow[N + decltype(ii)::value] = b[decltype(ii)::value]; });
+                done = true;
+                mycol = k;
             }
+            __syncwarp();
+            const cplx inv = crecip_fast(brow[k]);
+            cplx m = cmul(a[k], inv);
+            if (is_p) { myinv = inv; m = cmk(0.0, 0.0); }
+            static_for<k + 1, N>([&](auto cc) { cfnma(a[decltype(cc)::value], m, brow[decltype(cc)::value]); });
+            static_for<0, P>([&](auto ii) { cfnma(b[decltype(ii)::value], m, brow[N + decltype(ii)::value]); });
         });
+        bad |= pivot_status(kmin, kmax);
 
         // ---- 4. solution rows -> shared, then S ------------------------------------------------
         __syncwarp();
-        if (r < n) {
-            static_for<0, PMAX>([&](auto ii) {
+        if (r < N) {
+            static_for<0, P>([&](auto ii) {
                 constexpr int i = decltype(ii)::value;
-                if (i < P) regA[mycol * P + i] = cmul(b[i], myinv);
+                regA[mycol * P + i] = cmul(b[i], myinv);
             });
         }
         __syncwarp();
-        for (int e = gl; e < P * P; e += G) {
-            const int j = e / P, i = e - j * P;
-            const cplx Zi = eval_param(D, __ldg(D.port_zpref + i), f, fi, srow);
-            const cplx Zj = eval_param(D, __ldg(D.port_zpref + j), f, fi, srow);
+        for (int e = gl; e < Pr * Pr; e += G) {
+            const int j = e / Pr, i = e - j * Pr;
+            const cplx Zi = eval_param(D.pv, __ldg(D.port_zpref + i), f, fi, srow);
+            const cplx Zj = eval_param(D.pv, __ldg(D.port_zpref + j), f, fi, srow);
             const cplx sv = s_entry(D, regA, j, i, Zi, Zj);
             if (!(isfinite(sv.x) && isfinite(sv.y))) bad |= HVB_STATUS_NONFINITE_BIT;
-            if (active) D.S[((s * P + j) * P + i) * D.ldS + fi] = sv;
+            if (active) D.S[((s * Pr + j) * Pr + i) * D.ldS + fi] = sv;
         }
         if (bad && active && D.status) atomicOr(D.status, (int)bad);
         __syncwarp();

@@ -29,9 +29,9 @@ _f64p = C.POINTER(C.c_double)
 class PlanDesc(C.Structure):
     _fields_ = [(k, C.c_int32) for k in (
         "n", "ncols", "P", "n_consts", "n_prefs", "n_const_vals", "n_dyn", "n_ops", "n_coops",
-        "n_samples_cols", "coop_scratch", "n_traces", "n_knots", "n_coefs")] + [
+        "n_samples_cols", "coop_scratch", "n_traces", "n_knots", "n_coefs", "n_row_ent", "reserved0")] + [
         ("const_vals", _f64p), ("ops", _i32p), ("coops", _i32p), ("cell_ptr", _i32p), ("cell_ent", _i32p),
-        ("port_rows", _i32p), ("port_zpref", _i32p), ("spl_t", _f64p), ("spl_c", _f64p),
+        ("row_ptr", _i32p), ("row_ent", _i32p), ("port_rows", _i32p), ("port_zpref", _i32p), ("spl_t", _f64p), ("spl_c", _f64p),
         ("spl_trace", _i32p), ("spl_fill", _f64p), ("spl_range", _f64p)]
 
 
@@ -45,7 +45,7 @@ class KernelInfo(C.Structure):
                                          "ctas_per_sm", "sm_count")] + [("launches", C.c_int64)]
 
 
-EXPORTS = ("hvb_plan_create", "hvb_plan_destroy", "hvb_run_host", "hvb_run_device", "hvb_assemble_host",
+EXPORTS = ("hvb_warp_shape", "hvb_plan_create", "hvb_plan_destroy", "hvb_run_host", "hvb_run_device", "hvb_assemble_host",
            "hvb_plan_kernel_info", "hvb_measure_dfma_peak", "hvb_last_error", "hvb_version")
 
 _lib = None
@@ -63,6 +63,8 @@ def load_library():
     lib = C.CDLL(LIB_PATH)
     lib.hvb_plan_create.argtypes = [C.POINTER(PlanDesc), C.c_int, C.POINTER(C.c_void_p)]
     lib.hvb_plan_create.restype = C.c_int
+    lib.hvb_warp_shape.argtypes = [C.c_int32, C.c_int32, C.c_int32, _i32p, _i32p]
+    lib.hvb_warp_shape.restype = C.c_int
     lib.hvb_plan_destroy.argtypes = [C.c_void_p]
     lib.hvb_plan_destroy.restype = None
     lib.hvb_run_host.argtypes = [C.c_void_p, C.POINTER(RunArgs), C.c_void_p, _i32p]
@@ -146,6 +148,9 @@ class DevicePlanHandle:
         d.coops = arr("coops", plan.coops, np.int32).ctypes.data_as(_i32p)
         d.cell_ptr = arr("cp", plan.cell_ptr, np.int32).ctypes.data_as(_i32p)
         d.cell_ent = arr("ce", plan.cell_ent, np.int32).ctypes.data_as(_i32p)
+        d.n_row_ent = len(plan.row_ent)
+        d.row_ptr = arr("rp", plan.row_ptr, np.int32).ctypes.data_as(_i32p)
+        d.row_ent = arr("re", plan.row_ent, np.int32).ctypes.data_as(_i32p)
         d.port_rows = arr("pr", plan.port_rows, np.int32).ctypes.data_as(_i32p)
         d.port_zpref = arr("pz", plan.port_zpref, np.int32).ctypes.data_as(_i32p)
         d.spl_t = arr("st", plan.spl_t, np.float64).ctypes.data_as(_f64p)
@@ -221,6 +226,14 @@ class DevicePlanHandle:
                                        C.c_void_p(st.cuda_stream)))
 
 
+def warp_shape(n: int, P: int, max_nport: int = 0):
+    """(rows, rhs columns) the register-resident kernel wants this system padded to, or None."""
+    lib = load_library()
+    a, b = C.c_int32(0), C.c_int32(0)
+    _check(lib.hvb_warp_shape(n, P, max_nport, C.byref(a), C.byref(b)))
+    return (a.value, b.value) if a.value > 0 else None
+
+
 def measure_dfma_peak(device: int | None = None) -> float:
     lib = load_library()
     out = C.c_double(0.0)
@@ -234,7 +247,11 @@ class CompiledNetwork:
     def __init__(self, net, mode: str | None = None, device: int | None = None):
         self.table = net.stamp_table()
         mode = mode or os.environ.get("HVB_MODE", "auto")
-        self.plan = pl.compile_plan(self.table, mode)
+        plan = pl.compile_plan(self.table, mode)
+        shape = warp_shape(plan.n_real, plan.P, plan.max_nport)
+        if shape is not None and shape != (plan.n, plan.ncols - plan.n):
+            plan = pl.compile_plan(self.table, plan.mode, pad_to=shape)
+        self.plan = plan
         self.handle = DevicePlanHandle(self.plan, device)
         self._dump = None
 

@@ -102,6 +102,8 @@ class DevicePlan:
     coops: np.ndarray           # int32 [nCoop, COOP_WORDS]
     cell_ptr: np.ndarray        # int32 [n*ncols+1]
     cell_ent: np.ndarray        # int32 [nnz]  (value id << 1) | negate
+    row_ptr: np.ndarray         # int32 [n+1]  per-row entry lists (kernel A's assembly format)
+    row_ent: np.ndarray         # int32 [nnz]  negate | value id << 1 | column << 20 | last-of-cell << 31
     port_rows: np.ndarray       # int32 [P,3] sig/int/gnd system rows, ROW_GROUND / ROW_VIRTUAL_INT
     port_zpref: np.ndarray      # int32 [P] pref index of Z0 per port
     # splines
@@ -115,6 +117,8 @@ class DevicePlan:
     table_params: list = field(default_factory=list)      # (pref index, const slot, callable)
     n_static_consts: int = 0
     coop_scratch: int = 0       # complex128 scratch words a cooperative op needs per point
+    n_real: int = 0             # unknowns before identity padding (the dimension actually needed)
+    max_nport: int = 0          # largest N-port block (a cooperative op needs that many lanes)
 
     @property
     def n_tables(self) -> int:
@@ -127,7 +131,7 @@ class DevicePlan:
     def flops_per_solve(self) -> float:
         """Algorithmic real flops of one point: complex LU + P substitutions on the dimension
         actually factored."""
-        n, P = self.n, self.P
+        n, P = self.n_real, self.P
         return (8.0 / 3.0) * n ** 3 + 8.0 * n * n * P
 
 
@@ -334,7 +338,10 @@ def norton_legal(table: StampTable) -> bool:
     return True
 
 
-def compile_plan(table: StampTable, mode: str = "auto") -> DevicePlan:
+def compile_plan(table: StampTable, mode: str = "auto", pad_to: tuple[int, int] | None = None) -> DevicePlan:
+    """`pad_to=(rows, rhs_columns)` lays the system out in a larger fixed shape: extra unknowns are
+    identity rows (x = 0) and extra right-hand sides are zero columns, so the solution of the real
+    unknowns is unchanged while the register-resident kernel runs without bounds checks."""
     if mode == "auto":
         mode = "norton" if norton_legal(table) else "full"
     if mode == "norton" and not norton_legal(table):
@@ -355,8 +362,12 @@ def compile_plan(table: StampTable, mode: str = "auto") -> DevicePlan:
         dropped = set(int(s) for s in table.port_src) | set(int(r[2]) for r in table.port_table)
         keep = [i for i in range(1, NM) if i not in dropped]
         rowmap[keep] = np.arange(len(keep))
-    n = int(rowmap.max()) + 1 if NM > 0 else 0
-    n_rhs = 0 if mode == "dump" else P
+    n_real = int(rowmap.max()) + 1 if NM > 0 else 0
+    n, n_rhs = n_real, (0 if mode == "dump" else P)
+    if pad_to is not None and mode != "dump":
+        if pad_to[0] < n_real or pad_to[1] < P:
+            raise ValueError(f"pad_to={pad_to} is smaller than the system ({n_real}, {P})")
+        n, n_rhs = int(pad_to[0]), int(pad_to[1])
     ncols = n + n_rhs
 
     cells: dict[tuple[int, int], list[tuple[int, int]]] = {}
@@ -415,6 +426,9 @@ def compile_plan(table: StampTable, mode: str = "auto") -> DevicePlan:
             if mode == "full":
                 add(rowmap[src], n + q, 0, 0)          # unit excitation on the port's source row
 
+    for r in range(n_real, n):                       # identity padding rows (value id 0 == 1+0j)
+        add(r, r, 0, 0)
+
     # ---- finalise value ids and CSR ----------------------------------------------------------
     nvc = len(b.const_vals)
 
@@ -429,6 +443,19 @@ def compile_plan(table: StampTable, mode: str = "auto") -> DevicePlan:
             for vid, neg in lst:
                 ent.append((final(vid) << 1) | neg)
             cell_ptr[r * ncols + c + 1] = len(ent)
+    # per-row lists: the same entries, sorted by column, with the column and an end-of-cell flag packed in
+    row_ptr = np.zeros(n + 1, dtype=np.int32)
+    rent = []
+    for r in range(n):
+        for c in range(ncols):
+            lst = cells.get((r, c), ())
+            for k, (vid, neg) in enumerate(lst):
+                v = final(vid)
+                if v >= (1 << 19) or c >= (1 << 11):
+                    raise ValueError("plan too large for the packed row-entry format")
+                word = (neg & 1) | (v << 1) | (c << 20) | ((1 << 31) if k == len(lst) - 1 else 0)
+                rent.append(word - (1 << 32) if word >= (1 << 31) else word)
+        row_ptr[r + 1] = len(rent)
     ops = np.array(b.ops, dtype=np.int32).reshape(len(b.ops), OP_WORDS)
     coops = np.array(b.coops, dtype=np.int32).reshape(len(b.coops), COOP_WORDS)
     if len(ops):
@@ -444,6 +471,7 @@ def compile_plan(table: StampTable, mode: str = "auto") -> DevicePlan:
         const_vals=np.array(b.const_vals, dtype=np.complex128),
         n_dyn=b.dyn_count, ops=ops, coops=coops,
         cell_ptr=cell_ptr, cell_ent=np.array(ent, dtype=np.int32),
+        row_ptr=row_ptr, row_ent=np.array(rent, dtype=np.int32),
         port_rows=port_rows, port_zpref=port_zpref,
         spl_t=np.concatenate(b.spl_t) if b.spl_t else np.zeros(0),
         spl_c=np.concatenate(b.spl_c) if b.spl_c else np.zeros(0, dtype=np.complex128),
@@ -452,6 +480,7 @@ def compile_plan(table: StampTable, mode: str = "auto") -> DevicePlan:
         spl_range=np.array(b.spl_range, dtype=np.float64).reshape(nT, 2),
         sample_owners=b.sample_owners, table_params=b.table_params,
         n_static_consts=len(b.consts), coop_scratch=b.coop_scratch,
+        n_real=n_real, max_nport=max([int(c[2]) for c in b.coops], default=0),
     )
 
 

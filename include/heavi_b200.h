@@ -49,9 +49,9 @@ enum hvb_status {
  * Replaces: the list of SP_matrix_compiler closures (network.py:385-386) plus `indices`
  * (network.py:400-404). */
 typedef struct hvb_plan_desc {
-    int32_t n;             /* system dimension actually factored                                */
-    int32_t ncols;         /* n + number of right-hand sides (== n for a dump-only plan)        */
-    int32_t P;             /* ports                                                             */
+    int32_t n;             /* rows of the system as laid out (incl. identity padding rows)      */
+    int32_t ncols;         /* n + right-hand-side columns (== n for a dump-only plan)           */
+    int32_t P;             /* ports (<= ncols - n; extra RHS columns are zero padding)          */
     int32_t n_consts;      /* length of the per-run `consts` array                              */
     int32_t n_prefs;       /* parameter references (kind, index) pairs                          */
     int32_t n_const_vals;  /* plan-time stamp values (id 0 is 1+0j)                             */
@@ -63,11 +63,15 @@ typedef struct hvb_plan_desc {
     int32_t n_traces;      /* B-spline traces                                                   */
     int32_t n_knots;       /* total knots                                                       */
     int32_t n_coefs;       /* total spline coefficients                                         */
+    int32_t n_row_ent;     /* entries of the per-row lists                                      */
+    int32_t reserved0;     /* keeps the pointer block 8-byte aligned                            */
     const double*  const_vals; /* [n_const_vals] complex                                        */
     const int32_t* ops;        /* [n_ops*8]                                                     */
     const int32_t* coops;      /* [n_coops*8]                                                   */
     const int32_t* cell_ptr;   /* [n*ncols+1] CSR over matrix cells, row-major                  */
     const int32_t* cell_ent;   /* [cell_ptr[n*ncols]]  (value id << 1) | negate                 */
+    const int32_t* row_ptr;    /* [n+1] per-row entry lists (same stamps as the cell CSR)       */
+    const int32_t* row_ent;    /* [n_row_ent] bit0 negate | value id<<1 | column<<20 | last<<31 */
     const int32_t* port_rows;  /* [P*3] sig,int,gnd system rows; -1 ground, -2 int = gnd + E    */
     const int32_t* port_zpref; /* [P] parameter reference of each port's Z0                     */
     const double*  spl_t;      /* [n_knots]                                                     */
@@ -116,11 +120,17 @@ int hvb_run_device(hvb_plan* plan, const hvb_run_args* args, double* d_S_out, in
  * `mna_matrix[:, :, f]` (network.py:392-394), used by the parity tests. */
 int hvb_assemble_host(hvb_plan* plan, const hvb_run_args* args, double* W_out);
 
+/* Shape query: the register-resident kernel exists for a fixed list of (rows, RHS columns)
+ * shapes.  Given the real system size, ports and the largest N-port block, returns the shape the
+ * host should pad the plan to (identity rows, zero RHS columns), or 0/0 when the system must go
+ * to the block kernel unpadded. */
+int hvb_warp_shape(int32_t n, int32_t P, int32_t max_nport, int32_t* n_pad, int32_t* p_pad);
+
 /* Introspection for the benchmark / tests. */
 typedef struct hvb_kernel_info {
     int32_t kernel_class;   /* 0 = warp kernel (n <= 32), 1 = block kernel                       */
-    int32_t group;          /* lanes per system (warp kernel)                                    */
-    int32_t pmax;           /* RHS register columns (warp kernel)                                */
+    int32_t group;          /* warp kernel: padded rows N;  block kernel: panel width NB         */
+    int32_t pmax;           /* warp kernel: padded RHS columns                                   */
     int32_t threads;        /* threads per CTA                                                   */
     int32_t smem_bytes;     /* dynamic shared memory per CTA                                     */
     int32_t regs;           /* registers per thread (cudaFuncGetAttributes)                      */

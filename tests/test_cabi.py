@@ -30,8 +30,8 @@ def test_version_and_error_strings():
 
 
 def test_struct_layouts_match_header():
-    # 14 int32 + 12 pointers; 8-byte aligned
-    assert ctypes.sizeof(engine.PlanDesc) == 14 * 4 + 12 * 8
+    # 16 int32 + 14 pointers; 8-byte aligned
+    assert ctypes.sizeof(engine.PlanDesc) == 16 * 4 + 14 * 8
     assert ctypes.sizeof(engine.RunArgs) == 8 * 8
     assert ctypes.sizeof(engine.KernelInfo) == 8 * 4 + 8
 

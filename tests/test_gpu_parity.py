@@ -58,7 +58,7 @@ def test_solver_modes_agree(name, mode):
     cn = CompiledNetwork(m, mode=mode)
     S = cn.run(g["f"])[0]
     assert np.max(np.abs(S - g["S_ext"])) < 5e-14
-    assert cn.plan.n == (m.n_nodes + len(m.sources) - 1 if mode == "full" else m.n_nodes - 1 - len(m.ports))
+    assert cn.plan.n_real == (m.n_nodes + len(m.sources) - 1 if mode == "full" else m.n_nodes - 1 - len(m.ports))
 
 
 @pytest.mark.parametrize("nb", ["8", "16"])
@@ -150,7 +150,7 @@ def test_config5_ladder_block_kernel_properties():
     from oracle import mna_oracle as orc
     m, f = circuits.build_c5(hv, nF=2048)
     cn = m._compiled()
-    assert cn.handle.kernel_info()["kernel_class"] == 1 and cn.plan.n == 191
+    assert cn.handle.kernel_info()["kernel_class"] == 1 and cn.plan.n_real == 191
     S = m.run_sp(f)._S
     assert np.max(np.abs(S - np.swapaxes(S, 0, 1))) < 1e-11
     sub = slice(0, None, 128)

@@ -94,3 +94,32 @@ def test_sample_parameters_and_batch_columns():
     frac, adj, ext = parity_report(S, g["mc_S"][:, :, :, :64], g["mc_S"][:, :, :, :64])
     assert frac >= 0.95
     assert np.max(np.abs(S - g["mc_S"][:, :, :, :64])) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["c1_readme", "c2_lowpass", "c3_touchstone", "rnd_05", "rnd_19"])
+def test_padded_plan_is_equivalent(name):
+    """Identity-row / zero-column padding (what the register kernel's fixed shapes need) must not
+    change the solution, and the per-row entry lists must describe the same matrix as the cell CSR."""
+    g = golden(name)
+    tab = REG[name]().stamp_table()
+    base = pl.compile_plan(tab, "auto")
+    padded = pl.compile_plan(tab, base.mode, pad_to=(base.n + 3, base.P + 2))
+    assert padded.n_real == base.n and padded.flops_per_solve() == base.flops_per_solve()
+    f = g["f"][:32]
+    assert np.array_equal(pi.run_plan(padded, f), pi.run_plan(base, f)) or \
+        np.max(np.abs(pi.run_plan(padded, f) - pi.run_plan(base, f))) < 1e-14
+    # row lists == cell CSR
+    for p in (base, padded):
+        cells = {}
+        for r in range(p.n):
+            col_seen = []
+            for e in p.row_ent[p.row_ptr[r]:p.row_ptr[r + 1]]:
+                e = int(e) & 0xFFFFFFFF
+                c, vid, neg, last = (e >> 20) & 0x7FF, (e >> 1) & 0x7FFFF, e & 1, e >> 31
+                cells.setdefault((r, c), []).append((vid << 1) | neg)
+                col_seen.append((c, last))
+            assert [c for c, _ in col_seen] == sorted(c for c, _ in col_seen)
+        for r in range(p.n):
+            for c in range(p.ncols):
+                lo, hi = p.cell_ptr[r * p.ncols + c], p.cell_ptr[r * p.ncols + c + 1]
+                assert list(p.cell_ent[lo:hi]) == cells.get((r, c), [])

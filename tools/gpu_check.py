@@ -34,7 +34,7 @@ def check(name, m, drivers=None, values=None, Sgold=None):
                 ref = g["S"][None] if Sgold is None else Sgold
                 ext = g["S_ext"][None] if Sgold is None else Sgold
                 ki = cn.handle.kernel_info()
-                out.append("%s/k%d.g%d: dref %.1e dext %.1e" % (mode, ki["kernel_class"], ki["group"],
+                out.append("%s/k%d.%dx%d: dref %.1e dext %.1e" % (mode, ki["kernel_class"], ki["group"], ki["pmax"],
                            np.abs(S - ref).max(), np.abs(S - ext).max()))
             except Exception as e:
                 out.append("%s/blk%s: EXC %r" % (mode, force_block, e))
