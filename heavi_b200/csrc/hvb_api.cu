@@ -55,7 +55,7 @@ struct hvb_plan {
     int device = 0;
     hvb_plan_desc d{};
     // device copies of the static plan arrays
-    DevBuf const_vals, ops, coops, cell_ptr, cell_ent, row_ptr, row_ent, port_rows, port_zpref, spl_t, spl_c, spl_trace, spl_fill, spl_range;
+    DevBuf const_vals, ops, coops, cell_ptr, cell_ent, row_ptr, row_ent, fop_code, fop_out, fop_arg, epi_por, epi_scale, port_rows, port_zpref, spl_t, spl_c, spl_trace, spl_fill, spl_range;
     // per-run parameter buffers (device) + pinned staging
     DevBuf consts, prefs;
     void* h_stage = nullptr; size_t h_stage_bytes = 0;
@@ -128,7 +128,7 @@ static int select_kernel(hvb_plan* pl) {
     pl->region_a = std::max(std::max(d.n_dyn, d.n * PP), 1);
     const void* wk = warp_kernel_ptr(d.n, PP);
     const char* force = getenv("HVB_FORCE_BLOCK");
-    const size_t staged = (size_t)d.n_const_vals * 16 + (size_t)(d.n + 1 + d.n_row_ent) * 4 + 16;
+    const size_t staged = (size_t)(d.n_const_vals + d.n_fast_ops) * 16 + (size_t)(2 * d.n + 1 + d.n_row_ent + 2 * d.n_fast_ops) * 4 + (size_t)d.P * d.P * 8 + 64;
     if (wk && max_nport <= d.n && staged <= 24576 && !(force && force[0] == '1')) {
         const int N = d.n;
         const int G = N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32;
@@ -137,7 +137,7 @@ static int select_kernel(hvb_plan* pl) {
         pl->threads = hvb_warp_threads();
         pl->region_b = std::max(d.coop_scratch, N * (N + PP));
         const int sys_per_block = (pl->threads / 32) * (32 / G);
-        const size_t shared_words = (size_t)d.n_const_vals + (((size_t)(N + 1 + d.n_row_ent) * 4 + 15) / 16);
+        const size_t shared_words = hvb_warp_shared_words(N, d.n_const_vals, d.n_row_ent, d.n_fast_ops, d.P);
         pl->smem = (shared_words + (size_t)sys_per_block * (pl->region_a + pl->region_b)) * sizeof(cplx);
     } else {
         pl->kclass = 1;
@@ -192,6 +192,11 @@ extern "C" int hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan**
     up(pl->cell_ent, d.cell_ent, (size_t)nnz * 4);
     up(pl->row_ptr, d.row_ptr, (size_t)(d.n + 1) * 4);
     up(pl->row_ent, d.row_ent, (size_t)d.n_row_ent * 4);
+    up(pl->fop_code, d.fop_code, (size_t)d.n_fast_ops * 4);
+    up(pl->fop_out, d.fop_out, (size_t)d.n_fast_ops * 4);
+    up(pl->fop_arg, d.fop_arg, (size_t)d.n_fast_ops * 8);
+    up(pl->epi_por, d.epi_port_of_row, (size_t)d.n * 4);
+    up(pl->epi_scale, d.epi_scale, (size_t)std::max(d.P * d.P, 1) * 8);
     up(pl->port_rows, d.port_rows, (size_t)d.P * 3 * 4);
     up(pl->port_zpref, d.port_zpref, (size_t)d.P * 4);
     up(pl->spl_t, d.spl_t, (size_t)d.n_knots * 8);
@@ -212,7 +217,7 @@ extern "C" int hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan**
         return fail(HVB_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(e));
     }
     // the descriptor's host pointers are not kept
-    pl->d.const_vals = nullptr; pl->d.ops = nullptr; pl->d.coops = nullptr; pl->d.cell_ptr = nullptr; pl->d.cell_ent = nullptr; pl->d.row_ptr = nullptr; pl->d.row_ent = nullptr;
+    pl->d.const_vals = nullptr; pl->d.ops = nullptr; pl->d.coops = nullptr; pl->d.cell_ptr = nullptr; pl->d.cell_ent = nullptr; pl->d.row_ptr = nullptr; pl->d.row_ent = nullptr; pl->d.fop_code = nullptr; pl->d.fop_out = nullptr; pl->d.fop_arg = nullptr; pl->d.epi_port_of_row = nullptr; pl->d.epi_scale = nullptr;
     pl->d.port_rows = nullptr; pl->d.port_zpref = nullptr; pl->d.spl_t = nullptr; pl->d.spl_c = nullptr; pl->d.spl_trace = nullptr;
     pl->d.spl_fill = nullptr; pl->d.spl_range = nullptr;
     if (d.ncols >= d.n + d.P && d.ncols > d.n) { // dump-only plans (no right-hand sides) never solve
@@ -226,7 +231,7 @@ extern "C" int hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan**
 extern "C" void hvb_plan_destroy(hvb_plan* pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
-    DevBuf* all[] = {&pl->const_vals, &pl->ops, &pl->coops, &pl->cell_ptr, &pl->cell_ent, &pl->row_ptr, &pl->row_ent, &pl->port_rows, &pl->port_zpref,
+    DevBuf* all[] = {&pl->const_vals, &pl->ops, &pl->coops, &pl->cell_ptr, &pl->cell_ent, &pl->row_ptr, &pl->row_ent, &pl->fop_code, &pl->fop_out, &pl->fop_arg, &pl->epi_por, &pl->epi_scale, &pl->port_rows, &pl->port_zpref,
                      &pl->spl_t, &pl->spl_c, &pl->spl_trace, &pl->spl_fill, &pl->spl_range, &pl->consts, &pl->prefs,
                      &pl->f, &pl->samples, &pl->tables, &pl->S[0], &pl->S[1], &pl->status, &pl->work, &pl->dump};
     for (DevBuf* b : all) b->release();
@@ -243,6 +248,12 @@ static HvbDev make_dev(const hvb_plan* pl) {
     D.PP = d.ncols - d.n; D.nnz_rows = d.n_row_ent;
     D.row_ptr = (const int*)pl->row_ptr.p;
     D.row_ent = (const int*)pl->row_ent.p;
+    D.nfast = d.n_fast_ops; D.epi_simple = d.epi_simple;
+    D.fop_code = (const int*)pl->fop_code.p;
+    D.fop_out = (const int*)pl->fop_out.p;
+    D.fop_arg = (const double*)pl->fop_arg.p;
+    D.epi_port_of_row = (const int*)pl->epi_por.p;
+    D.epi_scale = (const double*)pl->epi_scale.p;
     D.nvc = d.n_const_vals; D.ndyn = d.n_dyn; D.nops = d.n_ops; D.ncoops = d.n_coops; D.nR = d.n_samples_cols;
     D.coop_scratch = d.coop_scratch;
     D.region_a = pl->region_a; D.region_b = pl->region_b;

@@ -30,6 +30,7 @@ struct HvbDev {
     int n, ncols, P;                        // rows, rows + RHS columns (both possibly padded), real ports
     int PP;                                 // RHS columns = ncols - n (stride of the solution rows)
     int nnz_rows;                           // entries in row_ent
+    int nfast, epi_simple;                  // fast value ops; closed-form epilogue flag
     int nvc, ndyn, nops, ncoops, nR, coop_scratch;
     int region_a, region_b;                 // per-system shared-memory regions (complex words)
     long long nF, nS;                       // points of this launch: q = s*nF + fi
@@ -44,6 +45,11 @@ struct HvbDev {
     const int* cell_ent;
     const int* row_ptr;                     // per-row entry lists (kernel A's assembly)
     const int* row_ent;
+    const int* fop_code;
+    const int* fop_out;
+    const double* fop_arg;
+    const int* epi_port_of_row;
+    const double* epi_scale;
     const int* port_rows;
     const int* port_zpref;
     cplx* S;

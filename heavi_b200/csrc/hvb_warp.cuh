@@ -165,6 +165,12 @@ static __device__ __noinline__ unsigned coop_nport(const CoopCtx* ctx, const int
     return (code == COOP_NPORT_S) ? pivot_status(kmin, kmax) : 0u;
 }
 
+// complex words taken by the block-shared plan tables (same formula on host and device)
+__host__ __device__ constexpr size_t hvb_warp_shared_words_dev(int N, int nvc, int nnz_rows, int nfast, int P) {
+    return (size_t)nvc + (size_t)((nfast + 1) / 2) + (size_t)((P * P + 1) / 2) +
+           (size_t)((N + 1 + nnz_rows + 2 * nfast + N + 3) / 4);
+}
+
 // row entry: bit 0 negate, bits 1..19 value id, bits 20..30 column, bit 31 last entry of its cell
 #define HVB_ENT_VID(e) (((e) >> 1) & 0x7FFFF)
 #define HVB_ENT_COL(e) (((e) >> 20) & 0x7FF)
@@ -185,13 +191,24 @@ __global__ void __launch_bounds__(HVB_WARP_THREADS, WarpCfg<N, P>::kMinBlocks) h
     const int Pr = D.P;                                  // real ports (<= P)
 
     // ---- block-shared copies of the small plan tables ------------------------------------------
+    const int nfast = D.nfast;
     cplx* cvS = reinterpret_cast<cplx*>(hvb_smem);                       // [nvc]
-    int* rowptrS = reinterpret_cast<int*>(cvS + D.nvc);                  // [N+1]
+    double* fargS = reinterpret_cast<double*>(cvS + D.nvc);              // [nfast] (padded to even)
+    double* escS = fargS + ((nfast + 1) & ~1);                           // [Pr*Pr] (padded to even)
+    int* rowptrS = reinterpret_cast<int*>(escS + ((Pr * Pr + 1) & ~1));  // [N+1]
     int* rowentS = rowptrS + (N + 1);                                    // [nnz_rows]
-    const int shared_words = D.nvc + (((N + 1 + D.nnz_rows) * 4 + 15) / 16);
+    int* fcodeS = rowentS + D.nnz_rows;                                  // [nfast]
+    int* foutS = fcodeS + nfast;                                         // [nfast]
+    int* eporS = foutS + nfast;                                          // [N]
+    const int shared_words = (int)hvb_warp_shared_words_dev(N, D.nvc, D.nnz_rows, nfast, Pr);
     for (int i = threadIdx.x; i < D.nvc; i += HVB_WARP_THREADS) cvS[i] = D.const_vals[i];
+    for (int i = threadIdx.x; i < nfast; i += HVB_WARP_THREADS) {
+        fargS[i] = D.fop_arg[i]; fcodeS[i] = D.fop_code[i]; foutS[i] = D.fop_out[i];
+    }
+    for (int i = threadIdx.x; i < Pr * Pr; i += HVB_WARP_THREADS) escS[i] = D.epi_scale[i];
     for (int i = threadIdx.x; i <= N; i += HVB_WARP_THREADS) rowptrS[i] = D.row_ptr[i];
     for (int i = threadIdx.x; i < D.nnz_rows; i += HVB_WARP_THREADS) rowentS[i] = D.row_ent[i];
+    for (int i = threadIdx.x; i < N; i += HVB_WARP_THREADS) eporS[i] = D.epi_port_of_row[i];
     __syncthreads();
 
     cplx* regA = reinterpret_cast<cplx*>(hvb_smem) + shared_words + (size_t)sys_in_block * (D.region_a + D.region_b);
@@ -214,6 +231,20 @@ __global__ void __launch_bounds__(HVB_WARP_THREADS, WarpCfg<N, P>::kMinBlocks) h
         if (D.ncoops > 0) {
             CoopCtx ctx{D.pv, D.nvc, f, fi, srow, regA, regB};
             for (int o = 0; o < D.ncoops; ++o) bad |= coop_nport<G>(&ctx, D.coops + o * HVB_COOP_WORDS, gl);
+        }
+        {
+            // fast ops: real constant or plain sample argument (base/capacitor.py:31, inductor.py:32,
+            // impedance.py:29, admittance.py:39, port.py:39) -- branch-free
+            const double w = __dmul_rn(HVB_TWOPI, f);
+            for (int o = gl; o < nfast; o += G) {
+                const int code = fcodeS[o];
+                double p = fargS[o];
+                if (code & 4) p = srow[(int)p];
+                const double t = (code & 2) ? __dmul_rn(w, p) : p;           // CAP / IND act on w*p
+                const double v = (code & 1) ? 1.0 / t : t;                   // RECIP / IND invert
+                const bool imag = (code & 2) != 0;
+                regA[foutS[o]] = cmk(imag ? 0.0 : v, imag ? ((code & 1) ? -v : v) : 0.0);
+            }
         }
         for (int o = gl; o < D.nops; o += G) eval_simple_op(D, D.ops + o * HVB_OP_WORDS, f, fi, srow, regA);
         __syncwarp();
@@ -271,22 +302,42 @@ __global__ void __launch_bounds__(HVB_WARP_THREADS, WarpCfg<N, P>::kMinBlocks) h
         });
         bad |= pivot_status(kmin, kmax);
 
-        // ---- 4. solution rows -> shared, then S ------------------------------------------------
-        __syncwarp();
-        if (r < N) {
-            static_for<0, P>([&](auto ii) {
-                constexpr int i = decltype(ii)::value;
-                regA[mycol * P + i] = cmul(b[i], myinv);
-            });
-        }
-        __syncwarp();
-        for (int e = gl; e < Pr * Pr; e += G) {
-            const int j = e / Pr, i = e - j * Pr;
-            const cplx Zi = eval_param(D.pv, __ldg(D.port_zpref + i), f, fi, srow);
-            const cplx Zj = eval_param(D.pv, __ldg(D.port_zpref + j), f, fi, srow);
-            const cplx sv = s_entry(D, regA, j, i, Zi, Zj);
-            if (!(isfinite(sv.x) && isfinite(sv.y))) bad |= HVB_STATUS_NONFINITE_BIT;
-            if (active) D.S[((s * Pr + j) * Pr + i) * D.ldS + fi] = sv;
+        // ---- 4. epilogue --------------------------------------------------------------------------
+        if (D.epi_simple) {
+            // Norton plan, ground-referenced ports, constant real Z0: spfn.py:173-176 reduces to
+            // S_ji = (2 V_sig_j - delta_ij) sqrt|Zi| / sqrt|Zj| (denominator == V_int - V_gnd == 1 V);
+            // the lane that owns the solution row of port j's signal node writes S[j, :] directly.
+            const int pj = (r < N) ? eporS[mycol] : -1;
+            if (pj >= 0) {
+                static_for<0, P>([&](auto ii) {
+                    constexpr int i = decltype(ii)::value;
+                    if (i < Pr) {
+                        cplx x = cmul(b[i], myinv);
+                        x.x = fma(2.0, x.x, (i == pj) ? -1.0 : 0.0);
+                        x.y = 2.0 * x.y;
+                        const cplx sv = cscale(x, escS[pj * Pr + i]);
+                        if (!(isfinite(sv.x) && isfinite(sv.y))) bad |= HVB_STATUS_NONFINITE_BIT;
+                        if (active) D.S[((s * Pr + pj) * Pr + i) * D.ldS + fi] = sv;
+                    }
+                });
+            }
+        } else {
+            __syncwarp();
+            if (r < N) {
+                static_for<0, P>([&](auto ii) {
+                    constexpr int i = decltype(ii)::value;
+                    regA[mycol * P + i] = cmul(b[i], myinv);
+                });
+            }
+            __syncwarp();
+            for (int e = gl; e < Pr * Pr; e += G) {
+                const int j = e / Pr, i = e - j * Pr;
+                const cplx Zi = eval_param(D.pv, __ldg(D.port_zpref + i), f, fi, srow);
+                const cplx Zj = eval_param(D.pv, __ldg(D.port_zpref + j), f, fi, srow);
+                const cplx sv = s_entry(D, regA, j, i, Zi, Zj);
+                if (!(isfinite(sv.x) && isfinite(sv.y))) bad |= HVB_STATUS_NONFINITE_BIT;
+                if (active) D.S[((s * Pr + j) * Pr + i) * D.ldS + fi] = sv;
+            }
         }
         if (bad && active && D.status) atomicOr(D.status, (int)bad);
         __syncwarp();

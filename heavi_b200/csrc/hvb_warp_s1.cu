@@ -14,3 +14,6 @@ const void* hvb_warp_kernel_ptr_s1(int n, int p) {
     return nullptr;
 }
 int hvb_warp_threads() { return HVB_WARP_THREADS; }
+size_t hvb_warp_shared_words(int N, int nvc, int nnz_rows, int nfast, int P) {
+    return hvb_warp_shared_words_dev(N, nvc, nnz_rows, nfast, P);
+}

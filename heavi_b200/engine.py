@@ -29,9 +29,10 @@ _f64p = C.POINTER(C.c_double)
 class PlanDesc(C.Structure):
     _fields_ = [(k, C.c_int32) for k in (
         "n", "ncols", "P", "n_consts", "n_prefs", "n_const_vals", "n_dyn", "n_ops", "n_coops",
-        "n_samples_cols", "coop_scratch", "n_traces", "n_knots", "n_coefs", "n_row_ent", "reserved0")] + [
+        "n_samples_cols", "coop_scratch", "n_traces", "n_knots", "n_coefs", "n_row_ent", "n_fast_ops", "epi_simple", "reserved0")] + [
         ("const_vals", _f64p), ("ops", _i32p), ("coops", _i32p), ("cell_ptr", _i32p), ("cell_ent", _i32p),
-        ("row_ptr", _i32p), ("row_ent", _i32p), ("port_rows", _i32p), ("port_zpref", _i32p), ("spl_t", _f64p), ("spl_c", _f64p),
+        ("row_ptr", _i32p), ("row_ent", _i32p), ("fop_code", _i32p), ("fop_out", _i32p), ("fop_arg", _f64p),
+        ("epi_port_of_row", _i32p), ("epi_scale", _f64p), ("port_rows", _i32p), ("port_zpref", _i32p), ("spl_t", _f64p), ("spl_c", _f64p),
         ("spl_trace", _i32p), ("spl_fill", _f64p), ("spl_range", _f64p)]
 
 
@@ -151,6 +152,12 @@ class DevicePlanHandle:
         d.n_row_ent = len(plan.row_ent)
         d.row_ptr = arr("rp", plan.row_ptr, np.int32).ctypes.data_as(_i32p)
         d.row_ent = arr("re", plan.row_ent, np.int32).ctypes.data_as(_i32p)
+        d.n_fast_ops, d.epi_simple = len(plan.fop_code), plan.epi_simple
+        d.fop_code = arr("fc", plan.fop_code, np.int32).ctypes.data_as(_i32p)
+        d.fop_out = arr("fo", plan.fop_out, np.int32).ctypes.data_as(_i32p)
+        d.fop_arg = arr("fa", plan.fop_arg, np.float64).ctypes.data_as(_f64p)
+        d.epi_port_of_row = arr("epr", plan.epi_port_of_row, np.int32).ctypes.data_as(_i32p)
+        d.epi_scale = arr("eps", plan.epi_scale, np.float64).ctypes.data_as(_f64p)
         d.port_rows = arr("pr", plan.port_rows, np.int32).ctypes.data_as(_i32p)
         d.port_zpref = arr("pz", plan.port_zpref, np.int32).ctypes.data_as(_i32p)
         d.spl_t = arr("st", plan.spl_t, np.float64).ctypes.data_as(_f64p)

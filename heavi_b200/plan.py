@@ -117,6 +117,15 @@ class DevicePlan:
     table_params: list = field(default_factory=list)      # (pref index, const slot, callable)
     n_static_consts: int = 0
     coop_scratch: int = 0       # complex128 scratch words a cooperative op needs per point
+    # fast paths (kernel A): value ops whose parameter is a real constant or a plain sample column,
+    # and the closed-form epilogue S_ji = (2 V_sig_j - delta_ij) sqrt(Zi/Zj) of a Norton plan whose
+    # ports are ground-referenced with constant real Z0
+    fop_code: np.ndarray = None # int32 [nFast]  bits 0-1 op (COPY/RECIP/CAP/IND), bit 2: argument is a sample column
+    fop_out: np.ndarray = None  # int32 [nFast]  per-point value slot
+    fop_arg: np.ndarray = None  # float64 [nFast] constant, or the sample column
+    epi_simple: int = 0
+    epi_port_of_row: np.ndarray = None   # int32 [n]  port whose signal node is this row, else -1
+    epi_scale: np.ndarray = None         # float64 [P,P]  sqrt|Zi| / sqrt|Zj| at [j,i]
     n_real: int = 0             # unknowns before identity padding (the dimension actually needed)
     max_nport: int = 0          # largest N-port block (a cooperative op needs that many lanes)
 
@@ -463,6 +472,42 @@ def compile_plan(table: StampTable, mode: str = "auto", pad_to: tuple[int, int] 
     if len(coops):
         coops[:, 1] += nvc
 
+    # ---- fast value ops: split off the simple ops with a real-constant or plain-sample argument ----
+    consts_arr = np.array(b.consts, dtype=np.complex128).reshape(len(b.consts))
+    fcode, fout, farg, slow = [], [], [], []
+    for op in ops:
+        code, out, pi = int(op[0]), int(op[1]), int(op[2])
+        kind, idx = b.prefs[pi] if code in (OP_COPY, OP_RECIP, OP_CAP, OP_IND) else (None, None)
+        if kind == PK_CONST and consts_arr[idx].imag == 0.0:
+            fcode.append(code); fout.append(out - nvc); farg.append(float(consts_arr[idx].real))
+        elif kind == PK_SAMPLE:
+            fcode.append(code | 4); fout.append(out - nvc); farg.append(float(idx))
+        else:
+            slow.append(op)
+    ops = np.array(slow, dtype=np.int32).reshape(len(slow), OP_WORDS)
+
+    # ---- closed-form epilogue ------------------------------------------------------------------
+    epi_simple, epi_port_of_row, epi_scale = 0, np.full(max(n, 1), -1, dtype=np.int32), np.ones((max(P, 1), max(P, 1)))
+    if mode == "norton" and P > 0:
+        z = []
+        ok = True
+        for q in range(P):
+            kind, idx = b.prefs[port_zpref[q]]
+            if kind != PK_CONST or consts_arr[idx].imag != 0.0 or not (consts_arr[idx].real > 0.0):
+                ok = False
+                break
+            z.append(float(consts_arr[idx].real))
+            if port_rows[q, 2] != ROW_GROUND or port_rows[q, 0] < 0 or epi_port_of_row[port_rows[q, 0]] != -1:
+                ok = False
+                break
+            epi_port_of_row[port_rows[q, 0]] = q
+        if ok:
+            epi_simple = 1
+            zz = np.array(z)
+            epi_scale = np.sqrt(np.abs(zz))[None, :] / np.sqrt(np.abs(zz))[:, None]      # [j, i]
+        else:
+            epi_port_of_row[:] = -1
+
     nT = len(b.spl_trace)
     return DevicePlan(
         mode=mode, n=n, ncols=ncols, P=P, NM=NM,
@@ -480,6 +525,9 @@ def compile_plan(table: StampTable, mode: str = "auto", pad_to: tuple[int, int] 
         spl_range=np.array(b.spl_range, dtype=np.float64).reshape(nT, 2),
         sample_owners=b.sample_owners, table_params=b.table_params,
         n_static_consts=len(b.consts), coop_scratch=b.coop_scratch,
+        fop_code=np.array(fcode, dtype=np.int32), fop_out=np.array(fout, dtype=np.int32),
+        fop_arg=np.array(farg, dtype=np.float64),
+        epi_simple=epi_simple, epi_port_of_row=epi_port_of_row, epi_scale=np.ascontiguousarray(epi_scale, dtype=np.float64),
         n_real=n_real, max_nport=max([int(c[2]) for c in b.coops], default=0),
     )
 

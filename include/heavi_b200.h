@@ -64,6 +64,8 @@ typedef struct hvb_plan_desc {
     int32_t n_knots;       /* total knots                                                       */
     int32_t n_coefs;       /* total spline coefficients                                         */
     int32_t n_row_ent;     /* entries of the per-row lists                                      */
+    int32_t n_fast_ops;    /* value ops with a real-constant / plain-sample argument            */
+    int32_t epi_simple;    /* 1: closed-form epilogue S_ji = (2 V_sig_j - d_ij) sqrt(Zi/Zj)     */
     int32_t reserved0;     /* keeps the pointer block 8-byte aligned                            */
     const double*  const_vals; /* [n_const_vals] complex                                        */
     const int32_t* ops;        /* [n_ops*8]                                                     */
@@ -72,6 +74,11 @@ typedef struct hvb_plan_desc {
     const int32_t* cell_ent;   /* [cell_ptr[n*ncols]]  (value id << 1) | negate                 */
     const int32_t* row_ptr;    /* [n+1] per-row entry lists (same stamps as the cell CSR)       */
     const int32_t* row_ent;    /* [n_row_ent] bit0 negate | value id<<1 | column<<20 | last<<31 */
+    const int32_t* fop_code;   /* [n_fast_ops] bits 0-1 op, bit 2: argument is a sample column  */
+    const int32_t* fop_out;    /* [n_fast_ops] per-point value slot                             */
+    const double*  fop_arg;    /* [n_fast_ops] constant, or sample column                       */
+    const int32_t* epi_port_of_row; /* [n] port whose signal node is this row, else -1          */
+    const double*  epi_scale;  /* [P*P] sqrt|Zi|/sqrt|Zj| at [j*P+i]                            */
     const int32_t* port_rows;  /* [P*3] sig,int,gnd system rows; -1 ground, -2 int = gnd + E    */
     const int32_t* port_zpref; /* [P] parameter reference of each port's Z0                     */
     const double*  spl_t;      /* [n_knots]                                                     */

@@ -98,6 +98,17 @@ class Interp:
                 Y2[Pn, i] = -np.sum(Y[:, i, :], axis=0)
                 Y2[Pn, Pn] += np.sum(Y[i, :, :], axis=0)
             vals[out:out + (Pn + 1) ** 2] = Y2.reshape((Pn + 1) ** 2, -1)
+        for code, out, arg in zip(p.fop_code, p.fop_out, p.fop_arg):
+            v = self.s[int(arg)] * np.ones_like(f) if code & 4 else arg * np.ones_like(f)
+            op = code & 3
+            if op == pl.OP_COPY:
+                vals[nvc + out] = v
+            elif op == pl.OP_RECIP:
+                vals[nvc + out] = 1 / v
+            elif op == pl.OP_CAP:
+                vals[nvc + out] = 1j * 2 * np.pi * f * v
+            else:
+                vals[nvc + out] = 1 / (1j * 2 * np.pi * f * v)
         for op in p.ops:
             code, out = op[0], op[1]
             if code == pl.OP_COPY:
@@ -159,6 +170,16 @@ class Interp:
                 return volt(q, 2, i) + (1.0 if q == i else 0.0)
             return X[:, r, i]
 
+        if p.epi_simple and getattr(self, "use_closed_form", False):
+            # the closed-form epilogue kernel A uses: S_ji = (2 V_sig_j - delta_ij) sqrt|Zi|/sqrt|Zj|
+            S = np.zeros((p.P, p.P, nF), dtype=np.complex128)
+            for r in range(p.n):
+                j = p.epi_port_of_row[r]
+                if j < 0:
+                    continue
+                for i in range(p.P):
+                    S[j, i] = (2 * X[:, r, i] - (1.0 if i == j else 0.0)) * p.epi_scale[j, i]
+            return S
         S = np.zeros((p.P, p.P, nF), dtype=np.complex128)
         for i in range(p.P):
             Vi1, Vi3, Vi2 = volt(i, 0, i), volt(i, 1, i), volt(i, 2, i)

@@ -30,8 +30,8 @@ def test_version_and_error_strings():
 
 
 def test_struct_layouts_match_header():
-    # 16 int32 + 14 pointers; 8-byte aligned
-    assert ctypes.sizeof(engine.PlanDesc) == 16 * 4 + 14 * 8
+    # 18 int32 + 19 pointers; 8-byte aligned
+    assert ctypes.sizeof(engine.PlanDesc) == 18 * 4 + 19 * 8
     assert ctypes.sizeof(engine.RunArgs) == 8 * 8
     assert ctypes.sizeof(engine.KernelInfo) == 8 * 4 + 8
 

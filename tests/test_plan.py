@@ -123,3 +123,32 @@ def test_padded_plan_is_equivalent(name):
             for c in range(p.ncols):
                 lo, hi = p.cell_ptr[r * p.ncols + c], p.cell_ptr[r * p.ncols + c + 1]
                 assert list(p.cell_ent[lo:hi]) == cells.get((r, c), [])
+
+
+@pytest.mark.parametrize("name", ["c1_readme", "c2_bandpass", "c2_highpass", "c3_touchstone", "c5_ladder", "rnd_04"])
+def test_closed_form_epilogue_equals_reference_formula(name):
+    """Norton plan + ground-referenced constant-Z0 ports: the closed form must equal spfn.py:159-176."""
+    g = golden(name)
+    tab = REG[name]().stamp_table()
+    p = pl.compile_plan(tab, "norton")
+    assert p.epi_simple == 1 and sorted(x for x in p.epi_port_of_row if x >= 0) == list(range(p.P))
+    f = g["f"][:8]
+    consts, prefs, tables, samples = pl.resolve_run(p, f)
+    a = pi.Interp(p, f, consts, prefs, tables, samples[0])
+    general = a.solve()
+    a.use_closed_form = True
+    assert np.max(np.abs(a.solve() - general)) < 4e-15
+
+
+def test_closed_form_epilogue_not_used_when_port_is_not_ground_referenced():
+    import circuits
+    for seed in range(48):
+        m, _ = circuits.build_random(hv, seed)
+        tab = m.stamp_table()
+        if not pl.norton_legal(tab):
+            continue
+        p = pl.compile_plan(tab, "norton")
+        grounded = all(int(r[3]) == 0 for r in tab.port_table)
+        distinct = len({int(r[1]) for r in tab.port_table}) == tab.P
+        assert p.epi_simple == (1 if grounded and distinct else 0)
+    assert pl.compile_plan(REG["c1_readme"]().stamp_table(), "full").epi_simple == 0
