@@ -157,6 +157,7 @@ static int select_kernel(hvb_plan* pl) {
         return fail(HVB_ERR_UNSUPPORTED, "system too large: needs %zu bytes of shared memory per CTA (max %zu)", pl->smem,
                     (size_t)prop.sharedMemPerBlockOptin);
     CU(cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    CU(cudaFuncSetAttribute(pl->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
     cudaFuncAttributes fa;
     CU(cudaFuncGetAttributes(&fa, pl->kernel));
     pl->regs = fa.numRegs;

@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(HVB_BLOCK_THREADS) hvb_block_kernel(const HvbD
             CoopCtx ctx{D.pv, D.nvc, f, fi, srow, dyn, scratch};
             for (int o = 0; o < D.ncoops; ++o) bad |= coop_nport<32>(&ctx, D.coops + o * HVB_COOP_WORDS, lane);
         }
+        eval_fast_ops(D.fop_code, D.fop_out, D.fop_arg, D.nfast, f, srow, dyn, tid, HVB_BLOCK_THREADS);
         for (int o = tid; o < D.nops; o += HVB_BLOCK_THREADS)
             eval_simple_op(D, D.ops + o * HVB_OP_WORDS, f, fi, srow, dyn);
         __syncthreads();
@@ -251,6 +252,7 @@ __global__ void __launch_bounds__(32) hvb_dump_kernel(const HvbDev D) {
             CoopCtx ctx{D.pv, D.nvc, f, fi, srow, dyn, scratch};
             for (int o = 0; o < D.ncoops; ++o) coop_nport<32>(&ctx, D.coops + o * HVB_COOP_WORDS, lane);
         }
+        eval_fast_ops(D.fop_code, D.fop_out, D.fop_arg, D.nfast, f, srow, dyn, lane, 32);
         for (int o = lane; o < D.nops; o += 32) eval_simple_op(D, D.ops + o * HVB_OP_WORDS, f, fi, srow, dyn);
         __syncwarp();
         for (int cell = lane; cell < cells; cell += 32) D.W[(size_t)q * cells + cell] = gather_cell(D, cell, dyn);

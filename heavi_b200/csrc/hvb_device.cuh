@@ -288,6 +288,24 @@ __device__ __forceinline__ void eval_simple_op(const HvbDev& D, const int* __res
     }
 }
 
+// fast value ops (real constant or plain sample argument), branch-free; tables may live in shared
+// or global memory.  base/capacitor.py:31, inductor.py:32, impedance.py:29, admittance.py:39, port.py:39
+__device__ __forceinline__ void eval_fast_ops(const int* __restrict__ fcode, const int* __restrict__ fout,
+                                              const double* __restrict__ farg, int nfast, double f,
+                                              const double* __restrict__ srow, cplx* __restrict__ dyn,
+                                              int start, int stride) {
+    const double w = __dmul_rn(HVB_TWOPI, f);
+    for (int o = start; o < nfast; o += stride) {
+        const int code = fcode[o];
+        double p = farg[o];
+        if (code & 4) p = srow[(int)p];
+        const double t = (code & 2) ? __dmul_rn(w, p) : p;           // CAP / IND act on w*p
+        const double v = (code & 1) ? 1.0 / t : t;                   // RECIP / IND invert
+        const bool imag = (code & 2) != 0;
+        dyn[fout[o]] = cmk(imag ? 0.0 : v, imag ? ((code & 1) ? -v : v) : 0.0);
+    }
+}
+
 // value id -> value (constants come from global memory through the read-only path)
 __device__ __forceinline__ cplx load_value(const HvbDev& D, int vid, const cplx* __restrict__ dyn) {
     if (vid < D.nvc) {

@@ -44,8 +44,16 @@ __host__ __device__ constexpr int hvb_group_for(int n) { return n <= 4 ? 4 : n <
 // registers per thread are capped so that small systems keep many warps resident
 template <int N, int P>
 struct WarpCfg {
-    static constexpr int kRegsWanted = (4 * (N + P) + 48) < 88 ? 88 : (4 * (N + P) + 48);
-    static constexpr int kMinBlocks = kRegsWanted <= 64 ? 8 : kRegsWanted <= 72 ? 7 : kRegsWanted <= 80 ? 6
+#ifndef HVB_REG_FLOOR
+#define HVB_REG_FLOOR 88
+#endif
+    static constexpr int kRegsWanted = (4 * (N + P) + 48) < HVB_REG_FLOOR ? HVB_REG_FLOOR : (4 * (N + P) + 48);
+#ifdef HVB_MINB_SMALL
+    static constexpr int kMinBlocks = (N <= 8 && P <= 4) ? HVB_MINB_SMALL :
+#else
+    static constexpr int kMinBlocks =
+#endif
+                                      kRegsWanted <= 64 ? 8 : kRegsWanted <= 72 ? 7 : kRegsWanted <= 80 ? 6
                                     : kRegsWanted <= 96 ? 5 : kRegsWanted <= 128 ? 4 : kRegsWanted <= 168 ? 3
                                     : kRegsWanted <= 255 ? 2 : 1;
 };
@@ -232,20 +240,7 @@ __global__ void __launch_bounds__(HVB_WARP_THREADS, WarpCfg<N, P>::kMinBlocks) h
             CoopCtx ctx{D.pv, D.nvc, f, fi, srow, regA, regB};
             for (int o = 0; o < D.ncoops; ++o) bad |= coop_nport<G>(&ctx, D.coops + o * HVB_COOP_WORDS, gl);
         }
-        {
-            // fast ops: real constant or plain sample argument (base/capacitor.py:31, inductor.py:32,
-            // impedance.py:29, admittance.py:39, port.py:39) -- branch-free
-            const double w = __dmul_rn(HVB_TWOPI, f);
-            for (int o = gl; o < nfast; o += G) {
-                const int code = fcodeS[o];
-                double p = fargS[o];
-                if (code & 4) p = srow[(int)p];
-                const double t = (code & 2) ? __dmul_rn(w, p) : p;           // CAP / IND act on w*p
-                const double v = (code & 1) ? 1.0 / t : t;                   // RECIP / IND invert
-                const bool imag = (code & 2) != 0;
-                regA[foutS[o]] = cmk(imag ? 0.0 : v, imag ? ((code & 1) ? -v : v) : 0.0);
-            }
-        }
+        eval_fast_ops(fcodeS, foutS, fargS, nfast, f, srow, regA, gl, G);
         for (int o = gl; o < D.nops; o += G) eval_simple_op(D, D.ops + o * HVB_OP_WORDS, f, fi, srow, regA);
         __syncwarp();
 
