@@ -143,14 +143,19 @@ static int select_kernel(hvb_plan* pl) {
         pl->kclass = 1;
         const char* nbs = getenv("HVB_BLOCK_NB");
         pl->NB = (nbs && atoi(nbs) == 8) ? 8 : 16;
+        pl->region_a = std::max(d.n_dyn, 1);             // solution rows live in the U12 buffer
         pl->region_b = std::max(d.coop_scratch, 1);
+        if (d.n > 1023) return fail(HVB_ERR_UNSUPPORTED, "systems with more than 1023 unknowns are not supported (n=%d)", d.n);
         pl->threads = hvb_block_threads();
         pl->smem = hvb_block_smem_bytes(pl->NB, d.n, d.ncols, pl->region_a, pl->region_b);
         if (pl->smem > (size_t)prop.sharedMemPerBlockOptin && pl->NB == 16) {
             pl->NB = 8;
             pl->smem = hvb_block_smem_bytes(pl->NB, d.n, d.ncols, pl->region_a, pl->region_b);
         }
-        pl->kernel = hvb_block_kernel_ptr(pl->NB);
+        {
+            const char* mb = getenv("HVB_BLOCK_MINB");
+            pl->kernel = hvb_block_kernel_ptr(pl->NB, (mb && atoi(mb) == 1) ? 1 : 2);
+        }
     }
     if (!pl->kernel) return fail(HVB_ERR_UNSUPPORTED, "no kernel for n=%d P=%d", d.n, P);
     if (pl->smem > (size_t)prop.sharedMemPerBlockOptin)
@@ -169,7 +174,11 @@ static int select_kernel(hvb_plan* pl) {
     if (pl->kclass == 1) {
         const char* cps = getenv("HVB_BLOCK_CTAS_PER_SM");
         if (cps && atoi(cps) > 0) pl->max_grid = std::min(pl->max_grid, atoi(cps) * pl->sm_count);
-        CU(pl->work.ensure((size_t)pl->max_grid * d.n * d.ncols * sizeof(cplx)));
+        {
+            const size_t ldw = ((size_t)d.ncols + 3) & ~(size_t)3;
+            CU(pl->work.ensure((size_t)pl->max_grid * (d.n + 3) * ldw * sizeof(cplx)));
+            CU(cudaMemset(pl->work.p, 0, pl->work.bytes));   // padding rows / columns stay finite
+        }
     }
     return HVB_OK;
 }
@@ -258,6 +267,7 @@ static HvbDev make_dev(const hvb_plan* pl) {
     D.nvc = d.n_const_vals; D.ndyn = d.n_dyn; D.nops = d.n_ops; D.ncoops = d.n_coops; D.nR = d.n_samples_cols;
     D.coop_scratch = d.coop_scratch;
     D.region_a = pl->region_a; D.region_b = pl->region_b;
+    D.block_main = pl->kclass == 1 ? (int)hvb_block_main_words(pl->NB, d.n, d.ncols, pl->region_a, pl->region_b) : 0;
     D.pv.consts = (const cplx*)pl->consts.p;
     D.pv.prefs = (const int2*)pl->prefs.p;
     D.const_vals = (const cplx*)pl->const_vals.p;

@@ -18,25 +18,38 @@
 #include "hvb_warp.cuh"
 #include "hvb_kernels.h"
 
+#include <algorithm>
+
 #define HVB_BLOCK_THREADS 256
 #define HVB_BLOCK_WARPS (HVB_BLOCK_THREADS / 32)
 
-template <int NB>
-__global__ void __launch_bounds__(HVB_BLOCK_THREADS) hvb_block_kernel(const HvbDev D) {
+// pivot key of a panel row: high word of |re|+|im| with the low 10 bits replaced by (1023 - row),
+// so one integer max gives the largest magnitude (to 10 mantissa bits) and its lowest-index row.
+__device__ __forceinline__ unsigned block_pivot_key(cplx v, int row) {
+    const double mag = fabs(v.x) + fabs(v.y);
+    const unsigned hi = (unsigned)__double2hiint(mag);
+    return ((hi & ~1023u) | (unsigned)(1023 - row)) + 1024u;
+}
+
+template <int NB, int MINB>
+__global__ void __launch_bounds__(HVB_BLOCK_THREADS, MINB) hvb_block_kernel(const HvbDev D) {
     extern __shared__ __align__(16) unsigned char hvb_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n = D.n, P = D.P, ncols = D.ncols, ld = D.ncols;
-    // shared-memory carve-up (complex words unless noted)
-    cplx* dyn = reinterpret_cast<cplx*>(hvb_smem);                 // region_a: values, later x rows
+    const int n = D.n, P = D.P, ncols = D.ncols;
+    const int ld = (D.ncols + 3) & ~3;                   // W has ld columns and n+3 rows: GEMM tiles never need guards
+    // shared-memory carve-up (complex words).  The per-point values are dead once W is assembled,
+    // so they share storage with the panel / U12 buffers.
+    cplx* dyn = reinterpret_cast<cplx*>(hvb_smem);                 // region_a: values
     cplx* scratch = dyn + D.region_a;                              // region_b: coop scratch
-    cplx* panel = scratch + D.region_b;                            // [n][NB]
-    cplx* u12 = panel + (size_t)n * NB;                            // [NB][ncols]
-    double* redv = reinterpret_cast<double*>(u12 + (size_t)NB * ncols);   // [warps]
-    int* redi = reinterpret_cast<int*>(redv + HVB_BLOCK_WARPS);    // [warps]
-    int* ipiv = redi + HVB_BLOCK_WARPS;                            // [NB]
+    cplx* panel = reinterpret_cast<cplx*>(hvb_smem);               // [n][NB]      (aliases dyn)
+    cplx* u12 = panel + (size_t)(n + 3) * NB;                      // [NB][ld]  (later: solution rows)
+    cplx* urow = reinterpret_cast<cplx*>(hvb_smem) + D.block_main; // [NB] pivot row of the current column
+    cplx* jrow = urow + NB;                                        // [NB] old row j
+    int* ipiv = reinterpret_cast<int*>(jrow + NB);                 // [NB]
     __shared__ unsigned sh_bad;
+    __shared__ unsigned sh_key[2];
 
-    cplx* __restrict__ W = D.W + (size_t)blockIdx.x * n * ld;
+    cplx* __restrict__ W = D.W + (size_t)blockIdx.x * (n + 3) * ld;
     const long long total = D.nS * D.nF;
 
     for (long long q = blockIdx.x; q < total; q += gridDim.x) {
@@ -57,59 +70,67 @@ __global__ void __launch_bounds__(HVB_BLOCK_THREADS) hvb_block_kernel(const HvbD
         __syncthreads();
 
         // ---- assemble W -----------------------------------------------------------------------
-        for (int cell = tid; cell < n * ncols; cell += HVB_BLOCK_THREADS) W[cell] = gather_cell(D, cell, dyn);
+        for (int cell = tid; cell < n * ncols; cell += HVB_BLOCK_THREADS) {
+            const int rr = cell / ncols, cc = cell - rr * ncols;
+            W[(size_t)rr * ld + cc] = gather_cell(D, cell, dyn);
+        }
         __syncthreads();
 
         // ---- blocked LU -----------------------------------------------------------------------
         for (int kb = 0; kb < n; kb += NB) {
             const int nb = min(NB, n - kb), m = n - kb;
-            for (int idx = tid; idx < m * NB; idx += HVB_BLOCK_THREADS) {
+            if (tid < 2) sh_key[tid] = 0u;
+            for (int idx = tid; idx < (m + 3) * NB; idx += HVB_BLOCK_THREADS) {
                 const int rr = idx / NB, j = idx - rr * NB;
-                panel[rr * NB + j] = (j < nb) ? W[(size_t)(kb + rr) * ld + kb + j] : cmk(0.0, 0.0);
+                panel[rr * NB + j] = (j < nb && rr < m) ? W[(size_t)(kb + rr) * ld + kb + j] : cmk(0.0, 0.0);
+            }
+            if (nb < NB)                                  // short last panel: the unused U12 rows must be finite
+                for (int idx = tid; idx < (NB - nb) * ld; idx += HVB_BLOCK_THREADS) u12[nb * ld + idx] = cmk(0.0, 0.0);
+            __syncthreads();
+            // key of column 0
+            {
+                unsigned key = 0u;
+                for (int rr = tid; rr < m; rr += HVB_BLOCK_THREADS) key = max(key, block_pivot_key(panel[rr * NB], rr));
+                key = __reduce_max_sync(0xffffffffu, key);
+                if (lane == 0 && key) atomicMax(&sh_key[0], key);
             }
             __syncthreads();
             for (int j = 0; j < nb; ++j) {
-                // pivot search over rows j..m-1 of column j
-                double best = -1.0;
-                int bi = j;
-                for (int rr = j + tid; rr < m; rr += HVB_BLOCK_THREADS) {
-                    const cplx v = panel[rr * NB + j];
-                    const double mag = fabs(v.x) + fabs(v.y);
-                    if (mag > best || !(mag == mag)) { best = (mag == mag) ? mag : INFINITY; bi = rr; }
-                }
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) {
-                    const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-                }
-                if (lane == 0) { redv[warp] = best; redi[warp] = bi; }
+                // ---- phase 1: winner of column j is known; stash pivot row and old row j ----
+                const unsigned key = sh_key[j & 1];
+                const int p = 1023 - (int)((key - 1024u) & 1023u);
+                const unsigned top = (key - 1024u) & ~1023u;
+                if (key < 1024u || top == 0u) bad |= HVB_STATUS_ZERO_PIVOT_BIT;
+                if (top >= 0x7FF00000u) bad |= HVB_STATUS_NONFINITE_BIT;
+                if (tid < NB) { urow[tid] = panel[p * NB + tid]; jrow[tid] = panel[j * NB + tid]; }
+                if (tid == 0) { ipiv[j] = p; sh_key[(j + 1) & 1] = 0u; }
                 __syncthreads();
-                best = redv[0]; bi = redi[0];
-#pragma unroll
-                for (int w = 1; w < HVB_BLOCK_WARPS; ++w) {
-                    const double ob = redv[w];
-                    const int oi = redi[w];
-                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-                }
-                if (!(best > 0.0)) bad |= HVB_STATUS_ZERO_PIVOT_BIT;
-                if (!isfinite(best)) bad |= HVB_STATUS_NONFINITE_BIT;
-                if (tid == 0) ipiv[j] = bi;
-                if (bi != j && tid < NB) {
-                    const cplx t = panel[j * NB + tid];
-                    panel[j * NB + tid] = panel[bi * NB + tid];
-                    panel[bi * NB + tid] = t;
-                }
-                __syncthreads();
-                const cplx inv = crecip_fast(panel[j * NB + j]);
+                // ---- phase 2: row j := pivot row; every other row below eliminates column j
+                //      (the thread that owns row p works on the old row j); next column's key ----
+                const cplx inv = crecip_fast(urow[j]);
+                unsigned nkey = 0u;
+                if (tid < NB) panel[j * NB + tid] = urow[tid];
                 for (int rr = j + 1 + tid; rr < m; rr += HVB_BLOCK_THREADS) {
-                    const cplx l = cmul(panel[rr * NB + j], inv);
+                    const cplx* src = (rr == p) ? jrow : (panel + rr * NB);
+                    const cplx l = cmul(src[j], inv);
+                    cplx nxt = cmk(0.0, 0.0);
                     panel[rr * NB + j] = l;
-                    for (int c = j + 1; c < nb; ++c) {
-                        cplx v = panel[rr * NB + c];
-                        cfnma(v, l, panel[j * NB + c]);
-                        panel[rr * NB + c] = v;
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) {
+                        if (c > j) {
+                            cplx v = src[c];
+                            cfnma(v, l, urow[c]);
+                            panel[rr * NB + c] = v;
+                            if (c == j + 1) nxt = v;
+                        } else if (c < j && rr == p) {
+                            panel[rr * NB + c] = src[c];      // the swapped row carries its multipliers along
+                        }
                     }
+                    if (j + 1 < nb) nkey = max(nkey, block_pivot_key(nxt, rr));
+                }
+                if (j + 1 < nb) {
+                    nkey = __reduce_max_sync(0xffffffffu, nkey);
+                    if (lane == 0 && nkey) atomicMax(&sh_key[(j + 1) & 1], nkey);
                 }
                 __syncthreads();
             }
@@ -139,7 +160,7 @@ __global__ void __launch_bounds__(HVB_BLOCK_THREADS) hvb_block_kernel(const HvbD
                 for (int j = 0; j < NB; ++j) {
                     if (j < nb) {
                         W[(size_t)(kb + j) * ld + c0 + c] = u[j];
-                        u12[j * ncols + c] = u[j];
+                        u12[j * ld + c] = u[j];
                     }
                 }
             }
@@ -149,7 +170,8 @@ __global__ void __launch_bounds__(HVB_BLOCK_THREADS) hvb_block_kernel(const HvbD
                 if (c >= j) W[(size_t)(kb + j) * ld + kb + c] = panel[j * NB + c];
             }
             __syncthreads();
-            // trailing update A22 -= L21 * U12, 4x4 complex register tiles, columns fastest across lanes
+            // trailing update A22 -= L21 * U12, 4x4 complex register tiles, columns fastest across lanes.
+            // W, the panel and U12 are padded, so edge tiles run the same unguarded code.
             const int mrows = m - nb;
             if (mrows > 0 && ntrail > 0) {
                 constexpr int TR = 4, TC = 4;
@@ -158,20 +180,18 @@ __global__ void __launch_bounds__(HVB_BLOCK_THREADS) hvb_block_kernel(const HvbD
                     const int tr = t / tiles_c, tc = t - tr * tiles_c;
                     const int r0 = nb + tr * TR, cc0 = tc * TC;
                     cplx acc[TR][TC];
+                    cplx* __restrict__ wt = W + (size_t)(kb + r0) * ld + c0 + cc0;
 #pragma unroll
                     for (int i = 0; i < TR; ++i)
 #pragma unroll
-                        for (int j = 0; j < TC; ++j) {
-                            const bool ok = (r0 + i < m) && (cc0 + j < ntrail);
-                            acc[i][j] = ok ? W[(size_t)(kb + r0 + i) * ld + c0 + cc0 + j] : cmk(0.0, 0.0);
-                        }
+                        for (int j = 0; j < TC; ++j) acc[i][j] = wt[(size_t)i * ld + j];
 #pragma unroll 4
                     for (int k = 0; k < NB; ++k) {
                         cplx l[TR], u[TC];
 #pragma unroll
-                        for (int i = 0; i < TR; ++i) l[i] = (r0 + i < m) ? panel[(r0 + i) * NB + k] : cmk(0.0, 0.0);
+                        for (int i = 0; i < TR; ++i) l[i] = panel[(r0 + i) * NB + k];
 #pragma unroll
-                        for (int j = 0; j < TC; ++j) u[j] = (cc0 + j < ntrail && k < nb) ? u12[k * ncols + cc0 + j] : cmk(0.0, 0.0);
+                        for (int j = 0; j < TC; ++j) u[j] = u12[k * ld + cc0 + j];
 #pragma unroll
                         for (int i = 0; i < TR; ++i)
 #pragma unroll
@@ -180,29 +200,47 @@ __global__ void __launch_bounds__(HVB_BLOCK_THREADS) hvb_block_kernel(const HvbD
 #pragma unroll
                     for (int i = 0; i < TR; ++i)
 #pragma unroll
-                        for (int j = 0; j < TC; ++j)
-                            if ((r0 + i < m) && (cc0 + j < ntrail)) W[(size_t)(kb + r0 + i) * ld + c0 + cc0 + j] = acc[i][j];
+                        for (int j = 0; j < TC; ++j) wt[(size_t)i * ld + j] = acc[i][j];
                 }
             }
             __syncthreads();
         }
 
         // ---- blocked back substitution, x left in W[:, n+i] -------------------------------------
-        cplx* xb = u12;                                   // [NB][P]
+        cplx* xb = panel;                                 // [NB][P] solution of the current block
+        cplx* ub = panel + NB * P;                        // [NB][NB] U11 of the current block
         const int last = ((n - 1) / NB) * NB;
         for (int kb = last; kb >= 0; kb -= NB) {
             const int nb = min(NB, n - kb);
-            if (tid < P) {
-                const int i = tid;
+            for (int idx = tid; idx < nb * NB; idx += HVB_BLOCK_THREADS) {
+                const int j = idx / NB, c = idx - j * NB;
+                ub[idx] = (c < nb) ? W[(size_t)(kb + j) * ld + kb + c] : cmk(0.0, 0.0);
+            }
+            for (int idx = tid; idx < nb * P; idx += HVB_BLOCK_THREADS) {
+                const int j = idx / P, i = idx - j * P;
+                xb[idx] = W[(size_t)(kb + j) * ld + n + i];
+            }
+            __syncthreads();
+            if (warp == 0) {
+                // column-oriented triangular solve inside one warp: x_j = y_j / u_jj, then y_i -= u_ij x_j
                 for (int j = nb - 1; j >= 0; --j) {
-                    cplx acc = W[(size_t)(kb + j) * ld + n + i];
-                    for (int c = j + 1; c < nb; ++c) cfnma(acc, W[(size_t)(kb + j) * ld + kb + c], xb[c * P + i]);
-                    const cplx x = cmul(acc, crecip_fast(W[(size_t)(kb + j) * ld + kb + j]));
-                    xb[j * P + i] = x;
-                    W[(size_t)(kb + j) * ld + n + i] = x;
+                    const cplx inv = crecip_fast(ub[j * NB + j]);
+                    for (int i = lane; i < P; i += 32) xb[j * P + i] = cmul(xb[j * P + i], inv);
+                    __syncwarp();
+                    for (int e = lane; e < j * P; e += 32) {
+                        const int rr = e / P, i = e - rr * P;
+                        cplx v = xb[rr * P + i];
+                        cfnma(v, ub[rr * NB + j], xb[j * P + i]);
+                        xb[rr * P + i] = v;
+                    }
+                    __syncwarp();
                 }
             }
             __syncthreads();
+            for (int idx = tid; idx < nb * P; idx += HVB_BLOCK_THREADS) {
+                const int j = idx / P, i = idx - j * P;
+                W[(size_t)(kb + j) * ld + n + i] = xb[idx];
+            }
             for (int idx = tid; idx < kb * P; idx += HVB_BLOCK_THREADS) {
                 const int rr = idx / P, i = idx - rr * P;
                 cplx acc = W[(size_t)rr * ld + n + i];
@@ -213,7 +251,7 @@ __global__ void __launch_bounds__(HVB_BLOCK_THREADS) hvb_block_kernel(const HvbD
         }
 
         // ---- S epilogue -------------------------------------------------------------------------
-        cplx* xs = dyn;                                   // region_a >= n*P
+        cplx* xs = u12;                                   // [n][P] (the host sizes u12 for it)
         for (int idx = tid; idx < n * P; idx += HVB_BLOCK_THREADS) {
             const int rr = idx / P, i = idx - rr * P;
             xs[idx] = W[(size_t)rr * ld + n + i];
@@ -277,15 +315,24 @@ __global__ void __launch_bounds__(256) hvb_dfma_probe(double* out, int iters) {
 // ------------------------------------------------------------------------------------------------
 // host-visible lookups
 // ------------------------------------------------------------------------------------------------
-const void* hvb_block_kernel_ptr(int nb) {
-    if (nb == 8) return (const void*)hvb_block_kernel<8>;
-    if (nb == 16) return (const void*)hvb_block_kernel<16>;
+const void* hvb_block_kernel_ptr(int nb, int minb) {
+    if (nb == 8 && minb == 1) return (const void*)hvb_block_kernel<8, 1>;
+    if (nb == 8 && minb == 2) return (const void*)hvb_block_kernel<8, 2>;
+    if (nb == 16 && minb == 1) return (const void*)hvb_block_kernel<16, 1>;
+    if (nb == 16 && minb == 2) return (const void*)hvb_block_kernel<16, 2>;
     return nullptr;
 }
 const void* hvb_dump_kernel_ptr() { return (const void*)hvb_dump_kernel; }
 const void* hvb_dfma_probe_ptr() { return (const void*)hvb_dfma_probe; }
 int hvb_block_threads() { return HVB_BLOCK_THREADS; }
+size_t hvb_block_main_words(int nb, int n, int ncols, int region_a, int region_b) {
+    // values + coop scratch share storage with panel + max(U12, solution rows)
+    const size_t P = (size_t)(ncols - n);
+    const size_t ld = ((size_t)ncols + 3) & ~(size_t)3;
+    const size_t u12 = std::max((size_t)nb * ld, (size_t)n * P);
+    const size_t panel = std::max((size_t)(n + 3) * nb, (size_t)nb * P + (size_t)nb * nb);
+    return std::max((size_t)region_a + region_b, panel + u12);
+}
 size_t hvb_block_smem_bytes(int nb, int n, int ncols, int region_a, int region_b) {
-    size_t words = (size_t)region_a + region_b + (size_t)n * nb + (size_t)nb * ncols;
-    return words * sizeof(cplx) + HVB_BLOCK_WARPS * (sizeof(double) + sizeof(int)) + nb * sizeof(int) + 16;
+    return (hvb_block_main_words(nb, n, ncols, region_a, region_b) + 2 * (size_t)nb) * sizeof(cplx) + (size_t)nb * sizeof(int) + 16;
 }

@@ -33,6 +33,7 @@ struct HvbDev {
     int nfast, epi_simple;                  // fast value ops; closed-form epilogue flag
     int nvc, ndyn, nops, ncoops, nR, coop_scratch;
     int region_a, region_b;                 // per-system shared-memory regions (complex words)
+    int block_main;                         // kernel B: complex words before its small per-column buffers
     long long nF, nS;                       // points of this launch: q = s*nF + fi
     long long ldS;                          // frequency pitch of the S output (elements)
     ParamView pv;

@@ -13,9 +13,10 @@ const void* hvb_warp_kernel_ptr_b4(int n, int p);
 int hvb_warp_threads();
 size_t hvb_warp_shared_words(int N, int nvc, int nnz_rows, int nfast, int P);
 
-const void* hvb_block_kernel_ptr(int nb);
+const void* hvb_block_kernel_ptr(int nb, int minb);
 int hvb_block_threads();
 size_t hvb_block_smem_bytes(int nb, int n, int ncols, int region_a, int region_b);
+size_t hvb_block_main_words(int nb, int n, int ncols, int region_a, int region_b);
 
 const void* hvb_dump_kernel_ptr();
 const void* hvb_dfma_probe_ptr();
