@@ -64,7 +64,7 @@ struct hvb_plan {
     cudaStream_t streams[2] = {nullptr, nullptr};
     cudaEvent_t upload_done = nullptr;
     // kernel choice
-    int kclass = 0, G = 0, PMAX = 0, NB = 0, threads = 0, ctas_per_sm = 0, sm_count = 0, regs = 0;
+    int kclass = 0, G = 0, PMAX = 0, NB = 0, lanes = 0, rows_per_lane = 1, threads = 0, ctas_per_sm = 0, sm_count = 0, regs = 0;
     size_t smem = 0;
     int region_a = 0, region_b = 0;
     const void* kernel = nullptr;
@@ -134,9 +134,13 @@ static int select_kernel(hvb_plan* pl) {
         const int G = N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32;
         pl->kclass = 0; pl->G = N; pl->PMAX = PP;
         pl->kernel = wk;
+        pl->lanes = G; pl->rows_per_lane = 1;
+        const char* r1 = getenv("HVB_WARP_R");
+        const void* wk2 = (d.n_coops == 0 && !(r1 && atoi(r1) == 1)) ? hvb_warp2_kernel_ptr(N, PP) : nullptr;
+        if (wk2) { pl->kernel = wk2; pl->lanes = hvb_warp2_group(N); pl->rows_per_lane = 2; }
         pl->threads = hvb_warp_threads();
         pl->region_b = std::max(d.coop_scratch, N * (N + PP));
-        const int sys_per_block = (pl->threads / 32) * (32 / G);
+        const int sys_per_block = (pl->threads / 32) * (32 / pl->lanes);
         const size_t shared_words = hvb_warp_shared_words(N, d.n_const_vals, d.n_row_ent, d.n_fast_ops, d.P);
         pl->smem = (shared_words + (size_t)sys_per_block * (pl->region_a + pl->region_b)) * sizeof(cplx);
     } else {
@@ -307,8 +311,7 @@ static int launch(hvb_plan* pl, HvbDev& D, cudaStream_t st) {
     if (total <= 0) return HVB_OK;
     long long blocks;
     if (pl->kclass == 0) {
-        const int N = pl->G;
-        const int spb = (pl->threads / 32) * (32 / (N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32));
+        const int spb = (pl->threads / 32) * (32 / pl->lanes);
         blocks = (total + spb - 1) / spb;
     } else {
         blocks = total;

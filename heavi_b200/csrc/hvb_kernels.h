@@ -10,6 +10,8 @@ const void* hvb_warp_kernel_ptr_b1(int n, int p);
 const void* hvb_warp_kernel_ptr_b2(int n, int p);
 const void* hvb_warp_kernel_ptr_b3(int n, int p);
 const void* hvb_warp_kernel_ptr_b4(int n, int p);
+const void* hvb_warp2_kernel_ptr(int n, int p);
+int hvb_warp2_group(int n);
 int hvb_warp_threads();
 size_t hvb_warp_shared_words(int N, int nvc, int nnz_rows, int nfast, int P);
 

@@ -1,0 +1,22 @@
+// hvb_warp2_s.cu -- kernel A2 (two rows per lane) instantiations for small systems.
+#include "hvb_warp2.cuh"
+#include "hvb_kernels.h"
+
+const void* hvb_warp2_kernel_ptr(int n, int p) {
+    if (n == 2 && p == 2) return (const void*)hvb_warp2_kernel<2, 2>;
+    if (n == 3 && p == 2) return (const void*)hvb_warp2_kernel<3, 2>;
+    if (n == 4 && p == 2) return (const void*)hvb_warp2_kernel<4, 2>;
+    if (n == 5 && p == 2) return (const void*)hvb_warp2_kernel<5, 2>;
+    if (n == 6 && p == 2) return (const void*)hvb_warp2_kernel<6, 2>;
+    if (n == 7 && p == 2) return (const void*)hvb_warp2_kernel<7, 2>;
+    if (n == 8 && p == 2) return (const void*)hvb_warp2_kernel<8, 2>;
+    if (n == 2 && p == 4) return (const void*)hvb_warp2_kernel<2, 4>;
+    if (n == 3 && p == 4) return (const void*)hvb_warp2_kernel<3, 4>;
+    if (n == 4 && p == 4) return (const void*)hvb_warp2_kernel<4, 4>;
+    if (n == 5 && p == 4) return (const void*)hvb_warp2_kernel<5, 4>;
+    if (n == 6 && p == 4) return (const void*)hvb_warp2_kernel<6, 4>;
+    if (n == 7 && p == 4) return (const void*)hvb_warp2_kernel<7, 4>;
+    if (n == 8 && p == 4) return (const void*)hvb_warp2_kernel<8, 4>;
+    return nullptr;
+}
+int hvb_warp2_group(int n) { return hvb_group2_for(n); }
