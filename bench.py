@@ -63,8 +63,9 @@ def make_jobs(hv, workload: str, rank: int, world: int):
         desc = "configs[0]: README demo, 2001 points (per GPU)"
     elif workload == "c3":
         m, _ = circuits.build_c3(hv, nF=8)
-        jobs.append((m, slab(1e9, 6e9, 1_000_000), None, None))
-        desc = "configs[2]: synthetic 8-port Touchstone block in LC matching network, 1M points (per GPU)"
+        npts = int(os.environ.get("HVB_C3_POINTS", "1000000"))
+        jobs.append((m, slab(1e9, 6e9, npts), None, None))
+        desc = "configs[2]: synthetic 8-port Touchstone block in LC matching network, %d points (per GPU)" % npts
     elif workload == "c4":
         m, f, mc = circuits.build_c4(hv)
         nS = 10_000 // 8                      # the config shards 10k samples over 8 GPUs
@@ -167,14 +168,14 @@ def time_cpu(jobs, steps: int, warmup: int, per_step_seconds: float = 4.0):
     """Bounded sample of the same workload through the oracle port; returns (solves/s, info)."""
     from oracle import mna_oracle_numba as onb
     recs = [(j[0].records(), j[0].n_nodes, len(j[0].sources)) for j in jobs]
-    # size the sample: calibrate on a small run (also triggers the JIT once)
+    # size the sample: calibrate on tiny runs (the first also triggers the JIT once)
     for (r, N, M), j in zip(recs, jobs):
-        onb.run_sp(r, N, M, cpu_job_sample(j, 64))
+        onb.run_sp(r, N, M, cpu_job_sample(j, 4))
     t = time.perf_counter()
     for (r, N, M), j in zip(recs, jobs):
-        onb.run_sp(r, N, M, cpu_job_sample(j, 256))
-    rate = 256 * len(jobs) / max(time.perf_counter() - t, 1e-6)
-    budget = int(max(256, min(max(len(j[1]) for j in jobs), rate * per_step_seconds / len(jobs))))
+        onb.run_sp(r, N, M, cpu_job_sample(j, 32))
+    rate = 32 * len(jobs) / max(time.perf_counter() - t, 1e-6)
+    budget = int(max(32, min(max(len(j[1]) for j in jobs), rate * per_step_seconds / len(jobs))))
     samples = [cpu_job_sample(j, budget) for j in jobs]
     pts = sum(len(s) for s in samples)
     for _ in range(warmup):
@@ -343,7 +344,8 @@ def main():
         hbm_peak = mp["hbm_gbs"] if mp else 6650.0
         roof = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(args.workload),
-                "kernel": "hvb_%s_kernel<%d,%d>" % ("warp" if ki["kernel_class"] == 0 else "block", ki["group"], ki["pmax"]),
+                "kernel": ("hvb_warp%s_kernel<%d,%d>" % ("2" if ki["threads"] and st["cn"].rows_per_lane == 2 else "", ki["group"], ki["pmax"]))
+                          if ki["kernel_class"] == 0 else "hvb_block_kernel<%d>" % ki["group"],
                 "launch_ms": k_ms, "n_factored": plan.n, "solver_mode": plan.mode,
                 "flops_per_solve": plan.flops_per_solve(), "solves_per_launch": job_points(jobs[top]),
                 "peak_source": "DFMA probe measured in this run (hvb_measure_dfma_peak); MEASURED_PEAKS.json has no FP64 entry",

@@ -473,6 +473,8 @@ extern "C" int hvb_plan_kernel_info(hvb_plan* pl, hvb_kernel_info* out) {
     out->regs = pl->regs;
     out->ctas_per_sm = pl->ctas_per_sm;
     out->sm_count = pl->sm_count;
+    out->rows_per_lane = pl->rows_per_lane;
+    out->reserved0 = 0;
     out->launches = pl->launches;
     return HVB_OK;
 }

@@ -43,7 +43,7 @@ class RunArgs(C.Structure):
 
 class KernelInfo(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("kernel_class", "group", "pmax", "threads", "smem_bytes", "regs",
-                                         "ctas_per_sm", "sm_count")] + [("launches", C.c_int64)]
+                                         "ctas_per_sm", "sm_count", "rows_per_lane", "reserved0")] + [("launches", C.c_int64)]
 
 
 EXPORTS = ("hvb_warp_shape", "hvb_plan_create", "hvb_plan_destroy", "hvb_run_host", "hvb_run_device", "hvb_assemble_host",
@@ -260,6 +260,7 @@ class CompiledNetwork:
             plan = pl.compile_plan(self.table, plan.mode, pad_to=shape)
         self.plan = plan
         self.handle = DevicePlanHandle(self.plan, device)
+        self.rows_per_lane = self.handle.kernel_info()["rows_per_lane"]
         self._dump = None
 
     def resolve(self, f, drivers=None, values=None):

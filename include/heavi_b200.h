@@ -143,6 +143,8 @@ typedef struct hvb_kernel_info {
     int32_t regs;           /* registers per thread (cudaFuncGetAttributes)                      */
     int32_t ctas_per_sm;    /* occupancy                                                         */
     int32_t sm_count;
+    int32_t rows_per_lane;  /* warp kernel: matrix rows held by one lane (1 or 2)                */
+    int32_t reserved0;
     int64_t launches;       /* kernel launches issued by this plan so far                        */
 } hvb_kernel_info;
 int hvb_plan_kernel_info(hvb_plan* plan, hvb_kernel_info* out);
