@@ -70,9 +70,19 @@ __global__ void __launch_bounds__(HVB_BLOCK_THREADS, MINB) hvb_block_kernel(cons
         __syncthreads();
 
         // ---- assemble W -----------------------------------------------------------------------
-        for (int cell = tid; cell < n * ncols; cell += HVB_BLOCK_THREADS) {
-            const int rr = cell / ncols, cc = cell - rr * ncols;
-            W[(size_t)rr * ld + cc] = gather_cell(D, cell, dyn);
+        // the matrix is ~1 % dense for large netlists: clear the workspace with plain stores, then
+        // let each row's entry list (sorted by column, component order inside a cell) drop its cells
+        for (int idx = tid; idx < n * ld; idx += HVB_BLOCK_THREADS) W[idx] = cmk(0.0, 0.0);
+        __syncthreads();
+        for (int rr = tid; rr < n; rr += HVB_BLOCK_THREADS) {
+            const int lo = __ldg(D.row_ptr + rr), hi = __ldg(D.row_ptr + rr + 1);
+            cplx acc = cmk(0.0, 0.0);
+            for (int e = lo; e < hi; ++e) {
+                const int ent = __ldg(D.row_ent + e);
+                const cplx v = load_value(D, HVB_ENT_VID(ent), dyn);
+                if (ent & 1) { acc.x -= v.x; acc.y -= v.y; } else { acc.x += v.x; acc.y += v.y; }
+                if (ent < 0) { W[(size_t)rr * ld + HVB_ENT_COL(ent)] = acc; acc = cmk(0.0, 0.0); }
+            }
         }
         __syncthreads();
 
@@ -80,59 +90,122 @@ __global__ void __launch_bounds__(HVB_BLOCK_THREADS, MINB) hvb_block_kernel(cons
         for (int kb = 0; kb < n; kb += NB) {
             const int nb = min(NB, n - kb), m = n - kb;
             if (tid < 2) sh_key[tid] = 0u;
-            for (int idx = tid; idx < (m + 3) * NB; idx += HVB_BLOCK_THREADS) {
-                const int rr = idx / NB, j = idx - rr * NB;
-                panel[rr * NB + j] = (j < nb && rr < m) ? W[(size_t)(kb + rr) * ld + kb + j] : cmk(0.0, 0.0);
-            }
             if (nb < NB)                                  // short last panel: the unused U12 rows must be finite
                 for (int idx = tid; idx < (NB - nb) * ld; idx += HVB_BLOCK_THREADS) u12[nb * ld + idx] = cmk(0.0, 0.0);
-            __syncthreads();
-            // key of column 0
-            {
-                unsigned key = 0u;
-                for (int rr = tid; rr < m; rr += HVB_BLOCK_THREADS) key = max(key, block_pivot_key(panel[rr * NB], rr));
-                key = __reduce_max_sync(0xffffffffu, key);
-                if (lane == 0 && key) atomicMax(&sh_key[0], key);
-            }
-            __syncthreads();
-            for (int j = 0; j < nb; ++j) {
-                // ---- phase 1: winner of column j is known; stash pivot row and old row j ----
-                const unsigned key = sh_key[j & 1];
-                const int p = 1023 - (int)((key - 1024u) & 1023u);
-                const unsigned top = (key - 1024u) & ~1023u;
-                if (key < 1024u || top == 0u) bad |= HVB_STATUS_ZERO_PIVOT_BIT;
-                if (top >= 0x7FF00000u) bad |= HVB_STATUS_NONFINITE_BIT;
-                if (tid < NB) { urow[tid] = panel[p * NB + tid]; jrow[tid] = panel[j * NB + tid]; }
-                if (tid == 0) { ipiv[j] = p; sh_key[(j + 1) & 1] = 0u; }
-                __syncthreads();
-                // ---- phase 2: row j := pivot row; every other row below eliminates column j
-                //      (the thread that owns row p works on the old row j); next column's key ----
-                const cplx inv = crecip_fast(urow[j]);
-                unsigned nkey = 0u;
-                if (tid < NB) panel[j * NB + tid] = urow[tid];
-                for (int rr = j + 1 + tid; rr < m; rr += HVB_BLOCK_THREADS) {
-                    const cplx* src = (rr == p) ? jrow : (panel + rr * NB);
-                    const cplx l = cmul(src[j], inv);
-                    cplx nxt = cmk(0.0, 0.0);
-                    panel[rr * NB + j] = l;
+            if (m <= HVB_BLOCK_THREADS) {
+                // ---- register-resident panel: thread t owns panel row t for all NB columns ----
+                cplx rowv[NB];
+                const bool has = tid < m;
 #pragma unroll
-                    for (int c = 0; c < NB; ++c) {
-                        if (c > j) {
-                            cplx v = src[c];
-                            cfnma(v, l, urow[c]);
-                            panel[rr * NB + c] = v;
-                            if (c == j + 1) nxt = v;
-                        } else if (c < j && rr == p) {
-                            panel[rr * NB + c] = src[c];      // the swapped row carries its multipliers along
-                        }
-                    }
-                    if (j + 1 < nb) nkey = max(nkey, block_pivot_key(nxt, rr));
-                }
-                if (j + 1 < nb) {
-                    nkey = __reduce_max_sync(0xffffffffu, nkey);
-                    if (lane == 0 && nkey) atomicMax(&sh_key[(j + 1) & 1], nkey);
+                for (int c = 0; c < NB; ++c)
+                    rowv[c] = (has && c < nb) ? W[(size_t)(kb + tid) * ld + kb + c] : cmk(0.0, 0.0);
+                if (tid < 3 * NB) panel[(m + tid / NB) * NB + (tid % NB)] = cmk(0.0, 0.0);   // GEMM pad rows
+                __syncthreads();
+                {
+                    unsigned key = has ? block_pivot_key(rowv[0], tid) : 0u;
+                    key = __reduce_max_sync(0xffffffffu, key);
+                    if (lane == 0 && key) atomicMax(&sh_key[0], key);
                 }
                 __syncthreads();
+                static_for<0, NB>([&](auto jj) {
+                    constexpr int j = decltype(jj)::value;
+                    if (j < nb) {
+                        const unsigned key = sh_key[j & 1];
+                        const int p = 1023 - (int)((key - 1024u) & 1023u);
+                        const unsigned top = (key - 1024u) & ~1023u;
+                        if (key < 1024u || top == 0u) bad |= HVB_STATUS_ZERO_PIVOT_BIT;
+                        if (top >= 0x7FF00000u) bad |= HVB_STATUS_NONFINITE_BIT;
+                        if (tid == p) {
+#pragma unroll
+                            for (int c = 0; c < NB; ++c) urow[c] = rowv[c];
+                        }
+                        if (tid == j) {
+#pragma unroll
+                            for (int c = 0; c < NB; ++c) jrow[c] = rowv[c];
+                        }
+                        if (tid == 0) { ipiv[j] = p; sh_key[(j + 1) & 1] = 0u; }
+                        __syncthreads();
+                        const cplx inv = crecip_fast(urow[j]);
+                        if (tid == j && p != j) {
+#pragma unroll
+                            for (int c = 0; c < NB; ++c) rowv[c] = urow[c];        // row j := pivot row
+                        } else if (tid == p && p != j) {
+#pragma unroll
+                            for (int c = 0; c < NB; ++c) rowv[c] = jrow[c];        // row p := old row j (multipliers included)
+                        }
+                        unsigned nkey = 0u;
+                        if (has && tid > j) {
+                            const cplx l = cmul(rowv[j], inv);
+                            rowv[j] = l;
+#pragma unroll
+                            for (int c = j + 1; c < NB; ++c) cfnma(rowv[c], l, urow[c]);
+                            if (j + 1 < NB) nkey = block_pivot_key(rowv[j + 1 < NB ? j + 1 : j], tid);
+                        }
+                        if (j + 1 < nb) {
+                            nkey = __reduce_max_sync(0xffffffffu, nkey);
+                            if (lane == 0 && nkey) atomicMax(&sh_key[(j + 1) & 1], nkey);
+                        }
+                        __syncthreads();
+                    }
+                });
+                if (has) {
+#pragma unroll
+                    for (int c = 0; c < NB; ++c) panel[tid * NB + c] = rowv[c];
+                }
+                __syncthreads();
+            } else {
+                for (int idx = tid; idx < (m + 3) * NB; idx += HVB_BLOCK_THREADS) {
+                    const int rr = idx / NB, j = idx - rr * NB;
+                    panel[rr * NB + j] = (j < nb && rr < m) ? W[(size_t)(kb + rr) * ld + kb + j] : cmk(0.0, 0.0);
+                }
+                __syncthreads();
+                // key of column 0
+                {
+                    unsigned key = 0u;
+                    for (int rr = tid; rr < m; rr += HVB_BLOCK_THREADS) key = max(key, block_pivot_key(panel[rr * NB], rr));
+                    key = __reduce_max_sync(0xffffffffu, key);
+                    if (lane == 0 && key) atomicMax(&sh_key[0], key);
+                }
+                __syncthreads();
+                for (int j = 0; j < nb; ++j) {
+                    // ---- phase 1: winner of column j is known; stash pivot row and old row j ----
+                    const unsigned key = sh_key[j & 1];
+                    const int p = 1023 - (int)((key - 1024u) & 1023u);
+                    const unsigned top = (key - 1024u) & ~1023u;
+                    if (key < 1024u || top == 0u) bad |= HVB_STATUS_ZERO_PIVOT_BIT;
+                    if (top >= 0x7FF00000u) bad |= HVB_STATUS_NONFINITE_BIT;
+                    if (tid < NB) { urow[tid] = panel[p * NB + tid]; jrow[tid] = panel[j * NB + tid]; }
+                    if (tid == 0) { ipiv[j] = p; sh_key[(j + 1) & 1] = 0u; }
+                    __syncthreads();
+                    // ---- phase 2: row j := pivot row; every other row below eliminates column j
+                    //      (the thread that owns row p works on the old row j); next column's key ----
+                    const cplx inv = crecip_fast(urow[j]);
+                    unsigned nkey = 0u;
+                    if (tid < NB) panel[j * NB + tid] = urow[tid];
+                    for (int rr = j + 1 + tid; rr < m; rr += HVB_BLOCK_THREADS) {
+                        const cplx* src = (rr == p) ? jrow : (panel + rr * NB);
+                        const cplx l = cmul(src[j], inv);
+                        cplx nxt = cmk(0.0, 0.0);
+                        panel[rr * NB + j] = l;
+    #pragma unroll
+                        for (int c = 0; c < NB; ++c) {
+                            if (c > j) {
+                                cplx v = src[c];
+                                cfnma(v, l, urow[c]);
+                                panel[rr * NB + c] = v;
+                                if (c == j + 1) nxt = v;
+                            } else if (c < j && rr == p) {
+                                panel[rr * NB + c] = src[c];      // the swapped row carries its multipliers along
+                            }
+                        }
+                        if (j + 1 < nb) nkey = max(nkey, block_pivot_key(nxt, rr));
+                    }
+                    if (j + 1 < nb) {
+                        nkey = __reduce_max_sync(0xffffffffu, nkey);
+                        if (lane == 0 && nkey) atomicMax(&sh_key[(j + 1) & 1], nkey);
+                    }
+                    __syncthreads();
+                }
             }
             const int c0 = kb + nb;                      // first trailing column
             const int ntrail = ncols - c0;
