@@ -12,7 +12,7 @@ from .lib.touchstone import FileBasedNPort
 from .model import Model
 from .netlist import Network, Node
 from .params import Function, MonteCarlo, Param, ParameterSweep, set_print_frequency
-from .results import NDSparameters, Sparameters, StatSparam, StatSparameters, frange
+from .results import DeviceStatSparameters, NDSparameters, Sparameters, StatSparam, StatSparameters, frange
 
 PI = 3.141592653589793
 __all__ = ["Model", "Network", "Node", "frange", "Sparameters", "NDSparameters", "StatSparam", "StatSparameters",

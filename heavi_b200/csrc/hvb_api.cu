@@ -60,7 +60,7 @@ struct hvb_plan {
     DevBuf consts, prefs;
     void* h_stage = nullptr; size_t h_stage_bytes = 0;
     // host pipeline buffers
-    DevBuf f, samples, tables, S[2], status, work, dump;
+    DevBuf f, samples, tables, S[2], status, work, dump, stats;
     cudaStream_t streams[2] = {nullptr, nullptr};
     cudaEvent_t upload_done = nullptr;
     // kernel choice
@@ -247,7 +247,7 @@ extern "C" void hvb_plan_destroy(hvb_plan* pl) {
     cudaSetDevice(pl->device);
     DevBuf* all[] = {&pl->const_vals, &pl->ops, &pl->coops, &pl->cell_ptr, &pl->cell_ent, &pl->row_ptr, &pl->row_ent, &pl->fop_code, &pl->fop_out, &pl->fop_arg, &pl->epi_por, &pl->epi_scale, &pl->port_rows, &pl->port_zpref,
                      &pl->spl_t, &pl->spl_c, &pl->spl_trace, &pl->spl_fill, &pl->spl_range, &pl->consts, &pl->prefs,
-                     &pl->f, &pl->samples, &pl->tables, &pl->S[0], &pl->S[1], &pl->status, &pl->work, &pl->dump};
+                     &pl->f, &pl->samples, &pl->tables, &pl->S[0], &pl->S[1], &pl->status, &pl->work, &pl->dump, &pl->stats};
     for (DevBuf* b : all) b->release();
     if (pl->h_stage) cudaFreeHost(pl->h_stage);
     for (int i = 0; i < 2; ++i) if (pl->streams[i]) cudaStreamDestroy(pl->streams[i]);
@@ -414,6 +414,65 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     CU(cudaStreamSynchronize(s0));
     CU(cudaStreamSynchronize(s1));
     cudaEventDestroy(ready);
+    int32_t stw = 0;
+    CU(cudaMemcpy(&stw, pl->status.p, 4, cudaMemcpyDeviceToHost));
+    if (status_out) *status_out = stw;
+    return HVB_OK;
+}
+
+extern "C" int hvb_run_stats_host(hvb_plan* pl, const hvb_run_args* a, double* stats_out, int32_t* status_out) {
+    int rc = check_args(pl, a);
+    if (rc) return rc;
+    if (!stats_out) return fail(HVB_ERR_ARG, "stats_out is NULL");
+    const hvb_plan_desc& d = pl->d;
+    if (d.ncols <= d.n || !pl->kernel) return fail(HVB_ERR_ARG, "plan has no right-hand sides (dump plan)");
+    CU(cudaSetDevice(pl->device));
+    const int64_t nF = a->nF, nS = a->nS;
+    const int64_t PP = (int64_t)d.P * d.P;
+    if (nF == 0 || PP == 0) { if (status_out) *status_out = 0; return HVB_OK; }
+    cudaStream_t st = pl->streams[0];
+    CU(pl->f.ensure((size_t)nF * 8));
+    CU(cudaMemcpyAsync(pl->f.p, a->f, (size_t)nF * 8, cudaMemcpyHostToDevice, st));
+    if (d.n_samples_cols) {
+        CU(pl->samples.ensure((size_t)nS * d.n_samples_cols * 8));
+        CU(cudaMemcpyAsync(pl->samples.p, a->samples, (size_t)nS * d.n_samples_cols * 8, cudaMemcpyHostToDevice, st));
+    }
+    if (a->n_tables) {
+        CU(pl->tables.ensure((size_t)a->n_tables * nF * 16));
+        CU(cudaMemcpyAsync(pl->tables.p, a->tables, (size_t)a->n_tables * nF * 16, cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaMemsetAsync(pl->status.p, 0, 4, st));
+    rc = push_params(pl, a, st);
+    if (rc) return rc;
+    // frequency slabs: all samples of a slab stay resident in HBM until they are reduced
+    const char* env = getenv("HVB_STATS_MB");
+    const int64_t budget = (int64_t)(env && atoi(env) > 0 ? atoi(env) : 4096) << 20;
+    const int64_t Fc = std::max<int64_t>(std::min<int64_t>(nF, budget / (nS * PP * 16)), 1);
+    CU(pl->S[0].ensure((size_t)nS * PP * Fc * 16));
+    CU(pl->stats.ensure((size_t)6 * PP * Fc * 8));
+    const void* rk = hvb_stats_kernel_ptr();
+    for (int64_t fb = 0; fb < nF; fb += Fc) {
+        const int64_t nf = std::min(Fc, nF - fb);
+        HvbDev D = make_dev(pl);
+        D.nF = nf; D.nS = nS; D.ldS = nf; D.pv.table_ld = nF;
+        D.f = (const double*)pl->f.p + fb;
+        D.samples = d.n_samples_cols ? (const double*)pl->samples.p : nullptr;
+        D.pv.tables = a->n_tables ? (const cplx*)pl->tables.p + fb : nullptr;
+        D.S = (cplx*)pl->S[0].p;
+        D.status = (int*)pl->status.p;
+        rc = launch(pl, D, st);
+        if (rc) return rc;
+        const cplx* dS = (const cplx*)pl->S[0].p;
+        long long a_nS = nS, a_rows = PP, a_nF = nf, a_ld = nf, a_ldo = nf;
+        double* dout = (double*)pl->stats.p;
+        void* args[] = {&dS, &a_nS, &a_rows, &a_nF, &a_ld, &dout, &a_ldo};
+        const long long blocks = std::min<long long>((PP * nf + 255) / 256, (long long)pl->sm_count * 8);
+        CU(cudaLaunchKernel(rk, dim3((unsigned)blocks), dim3(256), args, 0, st));
+        pl->launches++;
+        CU(cudaMemcpy2DAsync((char*)stats_out + (size_t)fb * 8, (size_t)nF * 8, pl->stats.p, (size_t)nf * 8,
+                             (size_t)nf * 8, (size_t)(6 * PP), cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
     int32_t stw = 0;
     CU(cudaMemcpy(&stw, pl->status.p, 4, cudaMemcpyDeviceToHost));
     if (status_out) *status_out = stw;

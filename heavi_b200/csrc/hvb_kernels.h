@@ -21,4 +21,5 @@ size_t hvb_block_smem_bytes(int nb, int n, int ncols, int region_a, int region_b
 size_t hvb_block_main_words(int nb, int n, int ncols, int region_a, int region_b);
 
 const void* hvb_dump_kernel_ptr();
+const void* hvb_stats_kernel_ptr();
 const void* hvb_dfma_probe_ptr();

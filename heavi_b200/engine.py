@@ -46,7 +46,8 @@ class KernelInfo(C.Structure):
                                          "ctas_per_sm", "sm_count", "rows_per_lane", "reserved0")] + [("launches", C.c_int64)]
 
 
-EXPORTS = ("hvb_warp_shape", "hvb_plan_create", "hvb_plan_destroy", "hvb_run_host", "hvb_run_device", "hvb_assemble_host",
+EXPORTS = ("hvb_warp_shape", "hvb_plan_create", "hvb_plan_destroy", "hvb_run_host", "hvb_run_device",
+           "hvb_run_stats_host", "hvb_assemble_host",
            "hvb_plan_kernel_info", "hvb_measure_dfma_peak", "hvb_last_error", "hvb_version")
 
 _lib = None
@@ -70,6 +71,8 @@ def load_library():
     lib.hvb_plan_destroy.restype = None
     lib.hvb_run_host.argtypes = [C.c_void_p, C.POINTER(RunArgs), C.c_void_p, _i32p]
     lib.hvb_run_host.restype = C.c_int
+    lib.hvb_run_stats_host.argtypes = [C.c_void_p, C.POINTER(RunArgs), C.c_void_p, _i32p]
+    lib.hvb_run_stats_host.restype = C.c_int
     lib.hvb_run_device.argtypes = [C.c_void_p, C.POINTER(RunArgs), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
     lib.hvb_run_device.restype = C.c_int
     lib.hvb_assemble_host.argtypes = [C.c_void_p, C.POINTER(RunArgs), C.c_void_p]
@@ -206,6 +209,19 @@ class DevicePlanHandle:
         _check(self.lib.hvb_run_host(self.handle, C.byref(a), out.ctypes.data_as(C.c_void_p), C.byref(status)))
         return out, status.value
 
+    def run_stats_host(self, f, consts, prefs, tables, samples):
+        """Monte-Carlo moments reduced on the device: float64 [6, P, P, nF]."""
+        p = self.plan
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        nF, nS = f.shape[0], samples.shape[0]
+        out = pinned_empty((6, p.P, p.P, nF), dtype=np.float64)
+        tables = np.ascontiguousarray(tables, dtype=np.complex128)
+        samples = np.ascontiguousarray(samples, dtype=np.float64)
+        a = self._args(consts, prefs, _ptr(f), nF, _ptr(samples), nS, _ptr(tables), tables.shape[0])
+        status = C.c_int32(0)
+        _check(self.lib.hvb_run_stats_host(self.handle, C.byref(a), out.ctypes.data_as(C.c_void_p), C.byref(status)))
+        return out, status.value
+
     def assemble_host(self, f, consts, prefs, tables, samples) -> np.ndarray:
         p = self.plan
         f = np.ascontiguousarray(f, dtype=np.float64)
@@ -277,6 +293,21 @@ class CompiledNetwork:
             warnings.warn("singular MNA system at one or more points: the reference returns the SVD "
                           "minimum-norm solution there, the LU solver cannot", RuntimeWarning)
         return S
+
+    def _raise_for_status(self, status: int):
+        if status & HVB_STATUS_NONFINITE:
+            raise np.linalg.LinAlgError("MNA matrix or S-parameters contain NaN/Inf (e.g. f = 0 with an inductor)")
+        if status & HVB_STATUS_ZERO_PIVOT:
+            warnings.warn("singular MNA system at one or more points: the reference returns the SVD "
+                          "minimum-norm solution there, the LU solver cannot", RuntimeWarning)
+
+    def run_stats(self, f: np.ndarray, drivers, values) -> np.ndarray:
+        """Moments over the sample axis, reduced on the device: float64 [6, P, P, nF] in the order
+        amplitude mean/std, power mean/std, rms mean/std (StatSparam, sparam.py:215-243)."""
+        consts, prefs, tables, samples = self.resolve(f, drivers, values)
+        out, status = self.handle.run_stats_host(f, consts, prefs, tables, samples)
+        self._raise_for_status(status)
+        return out
 
     def assemble(self, f: np.ndarray, drivers=None, values=None) -> np.ndarray:
         """Dense reference-layout MNA tensor [(N+M), (N+M), nF] of the first sample (debug/parity)."""

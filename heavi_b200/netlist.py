@@ -17,7 +17,7 @@ import numpy as np
 from .elements import (Admittance, Capacitor, Element, Impedance, Inductor, MatSource, NPortS, NPortY,
                        Port, Resistor, TransmissionLine)
 from .params import PhaseConstant, SimParam, enforce_simparam
-from .results import Sparameters, StatSparameters
+from .results import DeviceStatSparameters, Sparameters, StatSparameters
 
 try:                                    # same logger the reference uses; optional here
     from loguru import logger
@@ -239,6 +239,17 @@ class Network:
         mc.S = StatSparameters(N)
         mc.S.add_batch(S4)
         return mc.S
+
+    def run_mc_stats(self, frequencies: np.ndarray, mc, N: int) -> DeviceStatSparameters:
+        """Monte-Carlo run whose statistics are reduced on the GPU: same draws as `run_mc`, but only
+        mean / std of |S|, |S|^2 and sqrt(|S|^2) per (port pair, frequency) come back over PCIe."""
+        values = mc.draw(N)
+        compiled = self._compiled()
+        f64 = np.ascontiguousarray(np.asarray(frequencies, dtype=np.float64))
+        moments = compiled.run_stats(f64, mc._random_numbers, values)
+        for k, r in enumerate(mc._random_numbers):
+            r._value = values[-1, k] if N > 0 else r._value
+        return DeviceStatSparameters(moments, N, np.array(frequencies).astype(np.float32))
 
     def run_dc(self, *a, **k):
         raise NotImplementedError("DC analysis is outside the S-parameter hot path this package implements")

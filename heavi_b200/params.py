@@ -344,6 +344,7 @@ class MonteCarlo:
     def gaussian(self, mean: float, std: float) -> Random:
         r = Random(lambda: np.random.normal(mean, std))
         r._mean, r._std, r._value = mean, std, mean
+        r._kind = "gaussian"
         self._random_numbers.append(r)
         return r
 
@@ -361,6 +362,14 @@ class MonteCarlo:
 
     def draw(self, N: int) -> np.ndarray:
         """[N, nRandom] matrix of draws in the order `iterate(N)` would make them."""
+        rs = self._random_numbers
+        if rs and all(getattr(r, "_kind", None) == "gaussian" for r in rs):
+            # np.random.normal(m, s) is m + s * legacy_gauss(); a sized standard_normal call walks the
+            # same legacy stream in the same order, so this is bit-identical to the scalar loop
+            z = np.random.standard_normal(size=(N, len(rs)))
+            mean = np.array([r._mean for r in rs], dtype=np.float64)
+            std = np.array([r._std for r in rs], dtype=np.float64)
+            return mean[None, :] + std[None, :] * z
         out = np.empty((N, len(self._random_numbers)), dtype=np.float64)
         for i in range(N):
             for k, r in enumerate(self._random_numbers):

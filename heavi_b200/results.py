@@ -140,6 +140,42 @@ class StatSparameters(Sparameters):
         return Sparameters.__getattr__(self, name)
 
 
+class StatMoments:
+    """The six StatSparam statistics of one S_ij, already reduced over the trials (on the GPU)."""
+
+    def __init__(self, moments: np.ndarray, ntrials: int):
+        self._m = moments            # [6, nF]
+        self.ntrials = ntrials
+
+    amplitude_mean = property(lambda self: self._m[0])
+    amplitude_std = property(lambda self: self._m[1])
+    power_mean = property(lambda self: self._m[2])
+    power_std = property(lambda self: self._m[3])
+    rms_mean = property(lambda self: self._m[4])
+    rms_std = property(lambda self: self._m[5])
+
+
+class DeviceStatSparameters:
+    """`StatSparameters` look-alike for a batched Monte-Carlo run whose per-trial S never left the
+    GPU: `S(p1, p2)` returns the same six statistics `StatSparam` offers (sparam.py:215-243)."""
+
+    def __init__(self, moments: np.ndarray, ntrials: int, f: np.ndarray):
+        self._moments = moments      # [6, P, P, nF]
+        self.Ntrials = ntrials
+        self.f = f
+        self.nports = moments.shape[1]
+        self.nfreqs = moments.shape[3]
+
+    def S(self, p1: int, p2: int) -> StatMoments:
+        for p in (p1, p2):
+            if p < 1 or p > self.nports:
+                raise ValueError(f"Port {p} out of range")
+        return StatMoments(self._moments[:, p1 - 1, p2 - 1, :], self.Ntrials)
+
+    def __call__(self, p1: int, p2: int) -> StatMoments:
+        return self.S(p1, p2)
+
+
 class NDSparameters(Sparameters):
     """S data on an N-dimensional parameter grid, shape (..., P, P, nF) (sparam.py:299-358)."""
 

@@ -122,6 +122,14 @@ int hvb_run_host(hvb_plan* plan, const hvb_run_args* args, double* S_out, int32_
 int hvb_run_device(hvb_plan* plan, const hvb_run_args* args, double* d_S_out, int64_t ldS,
                    int32_t* d_status, void* stream);
 
+/* Monte-Carlo statistics with HOST buffers: solves all nS samples like hvb_run_host but keeps S in
+ * HBM and reduces over the sample axis on the device.  stats_out[6][P][P][nF] (float64) receives
+ * mean and population std of |S|, of |S|^2 and of sqrt(|S|^2) in that order -- the six properties
+ * of StatSparam (sparam.py:215-243).  Only 48 B per (j,i,f) cross PCIe instead of 16 B per sample.
+ * Replaces: MonteCarlo.iterate / submit_S + StatSparameters.S(p1,p2) (numeric.py:498-507,
+ * sparam.py:246-295) for the statistics use case. */
+int hvb_run_stats_host(hvb_plan* plan, const hvb_run_args* args, double* stats_out, int32_t* status_out);
+
 /* Assemble only: writes the dense matrix the plan describes, W[nS][nF][n][ncols] complex128, to
  * HOST memory.  With a "dump" plan (n = ncols = N+M, ground kept) this is the reference's
  * `mna_matrix[:, :, f]` (network.py:392-394), used by the parity tests. */

@@ -216,3 +216,26 @@ def test_library_is_the_path_that_ran():
     assert m._compiled().handle.kernel_info()["launches"] == before + 1
     with open("/proc/self/maps") as fh:
         assert "libheavi_b200.so" in fh.read()
+
+
+def test_device_monte_carlo_statistics_match_numpy_reduction():
+    """run_mc_stats (reduced on the GPU) == StatSparam properties of the per-trial run (sparam.py:215-243)."""
+    import circuits
+    m, f, mc = circuits.build_c4(hv, nF=501)
+    np.random.seed(11)
+    full = m.run_mc(f, mc, 37)
+    np.random.seed(11)
+    dev = m.run_mc_stats(f, mc, 37)
+    assert dev.Ntrials == 37 and dev.nports == 2 and dev.nfreqs == 501
+    for (p1, p2) in ((1, 1), (2, 1), (1, 2), (2, 2)):
+        a, b = full.S(p1, p2), dev.S(p1, p2)
+        for name in ("amplitude_mean", "amplitude_std", "power_mean", "power_std", "rms_mean", "rms_std"):
+            x, y = getattr(a, name), getattr(b, name)
+            assert y.shape == x.shape
+            assert np.max(np.abs(x - y)) <= 1e-12 * max(1.0, np.max(np.abs(x))), name
+    # slabbed reduction (small device budget) is bit-identical
+    os.environ["HVB_STATS_MB"] = "1"
+    np.random.seed(11)
+    dev2 = m.run_mc_stats(f, mc, 37)
+    os.environ.pop("HVB_STATS_MB")
+    assert np.array_equal(dev2._moments, dev._moments)
