@@ -251,6 +251,27 @@ class Network:
             r._value = values[-1, k] if N > 0 else r._value
         return DeviceStatSparameters(moments, N, np.array(frequencies).astype(np.float32))
 
+    def run_sweep(self, frequencies: np.ndarray, sweep):
+        """`for ix, vals in sweep.iterate(): sweep.submit(run_sp(f), f)` (numeric.py:418-446, :386-390)
+        as one batch: every grid point of the ParameterSweep is one sample.  Returns `sweep.S`
+        (an NDSparameters of shape dims + [P, P, nF]) with the same contents the serial loop builds."""
+        from .results import NDSparameters
+        combos = sweep.combinations()
+        params = sweep.params
+        values = np.array([[p._values[i] for i, dim in zip(ixs, sweep.sweep_dimensions) for p in dim]
+                           for ixs in combos], dtype=np.float64).reshape(len(combos), len(params))
+        S4 = self.run_sp_batch(frequencies, params, values)
+        shape = [len(dim[0]) for dim in sweep.sweep_dimensions]
+        ports = np.arange(1, S4.shape[1] + 1)
+        f32 = np.array(frequencies).astype(np.float32)
+        axes = [np.array([p._values for p in dim]) for dim in sweep.sweep_dimensions]
+        sweep._fdata = f32
+        sweep._mdim_data = NDSparameters(np.ascontiguousarray(S4).reshape(shape + list(S4.shape[1:])),
+                                         axes + [ports, ports, f32])
+        for p, v in zip(params, values[-1] if len(values) else []):       # state after the serial loop
+            p._value = v
+        return sweep._mdim_data
+
     def run_dc(self, *a, **k):
         raise NotImplementedError("DC analysis is outside the S-parameter hot path this package implements")
 

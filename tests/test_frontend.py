@@ -125,3 +125,19 @@ def test_run_sp_without_gpu_fails_loudly():
     m.resistor(a, m.gnd, 10.0)
     with pytest.raises(RuntimeError):
         m.run_sp(np.array([1e9]))
+
+
+def test_parameter_sweep_combinations_and_cap():
+    sweep = hv.ParameterSweep()
+    a = sweep.lin(1.0, 2.0).add(3)
+    b, c = sweep.lin(0.0, 1.0).lin(5.0, 6.0).add(2)
+    assert [p._values.tolist() for p in sweep.params] == [[1.0, 1.5, 2.0], [0.0, 1.0], [5.0, 6.0]]
+    assert sweep.combinations() == [(0, 0), (0, 1), (1, 0), (1, 1), (2, 0), (2, 1)]
+    seen = [vals for _, vals in sweep.iterate()]
+    assert seen[1] == (1.0, 1.0, 6.0) and len(seen) == 6
+    # quirk kept from the reference (numeric.py:423-429): the 10 000 cap multiplies the number of
+    # *parameters* per dimension, not the number of values, so a 101 x 100 grid does not trip it
+    big = hv.ParameterSweep()
+    big.lin(0, 1).add(101)
+    big.lin(0, 1).add(100)
+    assert len(big.combinations()) == 10_100

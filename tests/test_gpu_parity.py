@@ -239,3 +239,28 @@ def test_device_monte_carlo_statistics_match_numpy_reduction():
     dev2 = m.run_mc_stats(f, mc, 37)
     os.environ.pop("HVB_STATS_MB")
     assert np.array_equal(dev2._moments, dev._moments)
+
+
+def test_parameter_sweep_batch_matches_serial_loop():
+    """run_sweep == the reference's `for ix, v in sweep.iterate(): sweep.submit(run_sp(f), f)` loop."""
+    def build():
+        m = hv.Model(suppress_loadbar=True)
+        sweep = hv.ParameterSweep()
+        C = sweep.lin(0.5e-12, 2e-12).add(4)
+        L = sweep.lin(1e-9, 3e-9).add(3)
+        a, b = m.quick_port(50), m.quick_port(75)
+        mid = m.node()
+        m.inductor(a, mid, L)
+        m.capacitor(mid, m.gnd, C)
+        m.resistor(mid, b, 12.0)
+        return m, sweep
+    f = np.linspace(1e9, 4e9, 257)
+    m, sweep = build()
+    for ix, vals in sweep.iterate():
+        sweep.submit(m.run_sp(f), f)
+    serial = sweep.S
+    m2, sweep2 = build()
+    nd = m2.run_sweep(f, sweep2)
+    assert nd._sdata.shape == (4, 3, 2, 2, 257) == serial._sdata.shape
+    assert np.array_equal(nd._sdata, serial._sdata)
+    assert np.array_equal(nd.S(2, 1), serial.S(2, 1))
