@@ -59,8 +59,11 @@ struct hvb_plan {
     // per-run parameter buffers (device) + pinned staging
     DevBuf consts, prefs;
     void* h_stage = nullptr; size_t h_stage_bytes = 0;
+    void* h_in = nullptr; size_t h_in_bytes = 0;       // pinned staging for f / samples (pageable callers)
+    int32_t* h_status = nullptr;                       // pinned status word
+    cudaEvent_t ev_ready = nullptr, ev_tail = nullptr;
     // host pipeline buffers
-    DevBuf f, samples, tables, S[2], status, work, dump, stats;
+    DevBuf f, samples, tables, S[2], status, work, dump, stats, inbuf;
     cudaStream_t streams[2] = {nullptr, nullptr};
     cudaEvent_t upload_done = nullptr;
     // kernel choice
@@ -226,6 +229,9 @@ extern "C" int hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan**
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->streams[0], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&pl->streams[1], cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->upload_done, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&pl->ev_tail, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&pl->h_status, 16);
     if (e != cudaSuccess) {
         hvb_plan_destroy(pl);
         return fail(HVB_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(e));
@@ -247,9 +253,13 @@ extern "C" void hvb_plan_destroy(hvb_plan* pl) {
     cudaSetDevice(pl->device);
     DevBuf* all[] = {&pl->const_vals, &pl->ops, &pl->coops, &pl->cell_ptr, &pl->cell_ent, &pl->row_ptr, &pl->row_ent, &pl->fop_code, &pl->fop_out, &pl->fop_arg, &pl->epi_por, &pl->epi_scale, &pl->port_rows, &pl->port_zpref,
                      &pl->spl_t, &pl->spl_c, &pl->spl_trace, &pl->spl_fill, &pl->spl_range, &pl->consts, &pl->prefs,
-                     &pl->f, &pl->samples, &pl->tables, &pl->S[0], &pl->S[1], &pl->status, &pl->work, &pl->dump, &pl->stats};
+                     &pl->f, &pl->samples, &pl->tables, &pl->S[0], &pl->S[1], &pl->status, &pl->work, &pl->dump, &pl->stats, &pl->inbuf};
     for (DevBuf* b : all) b->release();
     if (pl->h_stage) cudaFreeHost(pl->h_stage);
+    if (pl->h_in) cudaFreeHost(pl->h_in);
+    if (pl->h_status) cudaFreeHost(pl->h_status);
+    if (pl->ev_ready) cudaEventDestroy(pl->ev_ready);
+    if (pl->ev_tail) cudaEventDestroy(pl->ev_tail);
     for (int i = 0; i < 2; ++i) if (pl->streams[i]) cudaStreamDestroy(pl->streams[i]);
     if (pl->upload_done) cudaEventDestroy(pl->upload_done);
     delete pl;
@@ -358,24 +368,41 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     if (nF == 0 || PP == 0) { if (status_out) *status_out = 0; return HVB_OK; }
     cudaStream_t s0 = pl->streams[0], s1 = pl->streams[1];
 
-    // inputs: uploaded once, on stream 0; stream 1 waits for them
-    CU(pl->f.ensure((size_t)nF * 8));
-    CU(cudaMemcpyAsync(pl->f.p, a->f, (size_t)nF * 8, cudaMemcpyHostToDevice, s0));
-    if (d.n_samples_cols) {
-        CU(pl->samples.ensure((size_t)nS * d.n_samples_cols * 8));
-        CU(cudaMemcpyAsync(pl->samples.p, a->samples, (size_t)nS * d.n_samples_cols * 8, cudaMemcpyHostToDevice, s0));
+    // inputs: ONE pinned staging block [status | consts | prefs | f | samples] and ONE async H2D on
+    // stream 0 (f and the sample matrix usually come from pageable numpy memory, where a direct
+    // cudaMemcpyAsync degrades to a synchronous staged copy, and every extra API call costs microseconds)
+    auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t off_consts = 16;
+    const size_t off_prefs = off_consts + up16((size_t)d.n_consts * 16);
+    const size_t off_f = off_prefs + up16((size_t)d.n_prefs * 8);
+    const size_t off_smp = off_f + up16((size_t)nF * 8);
+    const size_t in_bytes = off_smp + up16(d.n_samples_cols ? (size_t)nS * d.n_samples_cols * 8 : 0);
+    if ((d.n_consts && !a->consts) || (d.n_prefs && !a->prefs)) return fail(HVB_ERR_ARG, "consts/prefs missing");
+    if (pl->h_in_bytes < in_bytes) {
+        CU(cudaStreamSynchronize(s0));
+        if (pl->h_in) cudaFreeHost(pl->h_in);
+        pl->h_in = nullptr; pl->h_in_bytes = 0;
+        CU(cudaMallocHost(&pl->h_in, in_bytes + in_bytes / 4 + 4096));
+        pl->h_in_bytes = in_bytes + in_bytes / 4 + 4096;
     }
+    CU(pl->inbuf.ensure(in_bytes));
+    CU(cudaEventSynchronize(pl->ev_ready));              // the previous run's H2D out of h_in has finished
+    {
+        char* h = (char*)pl->h_in;
+        memset(h, 0, 16);
+        if (d.n_consts) memcpy(h + off_consts, a->consts, (size_t)d.n_consts * 16);
+        if (d.n_prefs) memcpy(h + off_prefs, a->prefs, (size_t)d.n_prefs * 8);
+        memcpy(h + off_f, a->f, (size_t)nF * 8);
+        if (d.n_samples_cols) memcpy(h + off_smp, a->samples, (size_t)nS * d.n_samples_cols * 8);
+    }
+    CU(cudaMemcpyAsync(pl->inbuf.p, pl->h_in, in_bytes, cudaMemcpyHostToDevice, s0));
     if (a->n_tables) {
         CU(pl->tables.ensure((size_t)a->n_tables * nF * 16));
         CU(cudaMemcpyAsync(pl->tables.p, a->tables, (size_t)a->n_tables * nF * 16, cudaMemcpyHostToDevice, s0));
     }
-    CU(cudaMemsetAsync(pl->status.p, 0, 4, s0));
-    rc = push_params(pl, a, s0);
-    if (rc) return rc;
-    cudaEvent_t ready;
-    CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-    CU(cudaEventRecord(ready, s0));
-    CU(cudaStreamWaitEvent(s1, ready, 0));
+    CU(cudaEventRecord(pl->ev_ready, s0));
+    CU(cudaStreamWaitEvent(s1, pl->ev_ready, 0));
+    const char* dbase = (const char*)pl->inbuf.p;
 
     // tiles: whole samples when several fit in a chunk, else frequency slabs of one sample
     const char* env = getenv("HVB_CHUNK_MB");
@@ -390,6 +417,8 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     }
     for (int b = 0; b < 2; ++b) CU(pl->S[b].ensure((size_t)Sc * PP * Fc * 16));
 
+    const char* c2d = getenv("HVB_COPY2D");
+    const bool copy2d = c2d && c2d[0] == '1';
     int tile = 0;
     for (int64_t sb = 0; sb < nS; sb += Sc) {
         const int64_t ns = std::min(Sc, nS - sb);
@@ -398,25 +427,38 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
             cudaStream_t st = pl->streams[tile & 1];
             HvbDev D = make_dev(pl);
             D.nF = nf; D.nS = ns; D.ldS = nf; D.pv.table_ld = nF;
-            D.f = (const double*)pl->f.p + fb;
-            D.samples = d.n_samples_cols ? (const double*)pl->samples.p + sb * d.n_samples_cols : nullptr;
+            D.pv.consts = (const cplx*)(dbase + off_consts);
+            D.pv.prefs = (const int2*)(dbase + off_prefs);
+            D.f = (const double*)(dbase + off_f) + fb;
+            D.samples = d.n_samples_cols ? (const double*)(dbase + off_smp) + sb * d.n_samples_cols : nullptr;
             D.pv.tables = a->n_tables ? (const cplx*)pl->tables.p + fb : nullptr;
             D.S = (cplx*)pl->S[tile & 1].p;
-            D.status = (int*)pl->status.p;
+            D.status = (int*)pl->inbuf.p;
             rc = launch(pl, D, st);
-            if (rc) { cudaEventDestroy(ready); return rc; }
+            if (rc) return rc;
             // rows of nf elements, one per (sample, j, i); destination pitch is the full nF
             char* dst = (char*)S_out + ((size_t)sb * PP * nF + (size_t)fb) * 16;
-            CU(cudaMemcpy2DAsync(dst, (size_t)nF * 16, D.S, (size_t)nf * 16, (size_t)nf * 16, (size_t)(ns * PP),
-                                 cudaMemcpyDeviceToHost, st));
+            // contiguous destination -> one plain copy; a few long rows -> one plain copy per row
+            // (both reach the full PCIe rate); many short rows -> strided 2-D copy
+            const int64_t rows = ns * PP;
+            if (nf == nF) {
+                CU(cudaMemcpyAsync(dst, D.S, (size_t)rows * nf * 16, cudaMemcpyDeviceToHost, st));
+            } else if (rows <= 64 && !copy2d) {
+                for (int64_t rr = 0; rr < rows; ++rr)
+                    CU(cudaMemcpyAsync(dst + (size_t)rr * nF * 16, (const char*)D.S + (size_t)rr * nf * 16, (size_t)nf * 16,
+                                       cudaMemcpyDeviceToHost, st));
+            } else {
+                CU(cudaMemcpy2DAsync(dst, (size_t)nF * 16, D.S, (size_t)nf * 16, (size_t)nf * 16, (size_t)rows,
+                                     cudaMemcpyDeviceToHost, st));
+            }
         }
     }
+    // stream 0 waits for stream 1's tail, fetches the status word, and is the only stream the host waits on
+    CU(cudaEventRecord(pl->ev_tail, s1));
+    CU(cudaStreamWaitEvent(s0, pl->ev_tail, 0));
+    CU(cudaMemcpyAsync(pl->h_status, pl->inbuf.p, 4, cudaMemcpyDeviceToHost, s0));
     CU(cudaStreamSynchronize(s0));
-    CU(cudaStreamSynchronize(s1));
-    cudaEventDestroy(ready);
-    int32_t stw = 0;
-    CU(cudaMemcpy(&stw, pl->status.p, 4, cudaMemcpyDeviceToHost));
-    if (status_out) *status_out = stw;
+    if (status_out) *status_out = *pl->h_status;
     return HVB_OK;
 }
 

@@ -215,11 +215,13 @@ class Network:
     def run_sp(self, frequencies: np.ndarray, reinitialize: bool = False) -> Sparameters:
         """S-parameter sweep at `frequencies` -> Sparameters(S[P,P,nF] complex128, f float32)."""
         compiled = self._compiled()
-        f64 = np.ascontiguousarray(np.asarray(frequencies, dtype=np.float64))
+        f64 = np.ascontiguousarray(frequencies, dtype=np.float64)
         S = compiled.run(f64)                                     # [1,P,P,nF] on pinned host memory
         if reinitialize:
             self._initialized = False
-        return Sparameters(S[0], np.array(frequencies).astype(np.float32))
+        # float32 copy of the frequency axis, the reference's quirk (network.py:407,421); float64 holds
+        # every float32-representable input exactly, so converting from f64 gives the same values
+        return Sparameters(S[0], f64.astype(np.float32))
 
     def run_sp_batch(self, frequencies: np.ndarray, drivers, values: np.ndarray) -> np.ndarray:
         """Batched Monte-Carlo / sweep evaluation: `values[s, k]` is the value of `drivers[k]`
