@@ -1,0 +1,231 @@
+"""GPU (-m gpu): edge cases of the CUDA path against the CPU oracle (LU variant, same float64
+matrices): degenerate sweep lengths, every right-hand-side padding class, the kernel-class
+boundaries, every parameter kind, and the state handling of repeated `run_sp` calls."""
+import os
+
+import numpy as np
+import pytest
+
+import heavi_b200 as hv
+from heavi_b200 import plan as pl
+from heavi_b200.engine import CompiledNetwork
+from oracle import mna_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-12
+
+
+def oracle_S(m, f):
+    return orc.run_sp(m.records(), m.n_nodes, len(m.sources), np.asarray(f, dtype=np.float64), method="lu_batched")
+
+
+def ladder(n_sections, n_ports, z0=50.0, seed=0):
+    """RLC ladder with `n_sections` internal nodes and `n_ports` ports spread along it."""
+    rng = np.random.default_rng(seed)
+    m = hv.Model(suppress_loadbar=True)
+    nodes = [m.node() for _ in range(n_sections)]
+    taps = sorted(set(int(round(i * (n_sections - 1) / max(n_ports - 1, 1))) for i in range(n_ports)))
+    for t in taps:
+        m.new_port(z0, nodes[t])
+    for k in range(n_sections - 1):
+        if k % 2:
+            m.inductor(nodes[k], nodes[k + 1], float(10 ** rng.uniform(-9.3, -8.3)))
+        else:
+            m.resistor(nodes[k], nodes[k + 1], float(rng.uniform(5, 80)))
+    for k in range(n_sections):
+        m.capacitor(nodes[k], m.gnd, float(10 ** rng.uniform(-12.5, -11.5)))
+    return m, len(taps)
+
+
+@pytest.mark.parametrize("nF", [0, 1, 2, 3, 5, 31, 33, 127, 129])
+def test_sweep_lengths(nF):
+    m, _ = ladder(6, 2)
+    f = np.linspace(0.5e9, 4e9, nF)
+    S = m.run_sp(f)
+    assert S._S.shape == (2, 2, nF) and S.f.shape == (nF,)
+    if nF:
+        assert np.max(np.abs(S._S - oracle_S(m, f))) < TOL
+
+
+@pytest.mark.parametrize("n_sections,n_ports", [(1, 1), (3, 1), (4, 3), (6, 4), (9, 5), (12, 8), (14, 9), (20, 12),
+                                               (30, 16), (24, 17), (31, 2), (32, 3), (33, 2), (40, 4), (70, 6)])
+def test_shapes_and_kernel_classes(n_sections, n_ports):
+    """P = 1..17 exercises every RHS padding class (2/4/8/16) and the P > 16 hand-over to kernel B;
+    n = 31..33 crosses the register-kernel limit."""
+    m, P = ladder(n_sections, n_ports, seed=n_sections)
+    f = np.array([0.3e9, 1.1e9, 2.7e9, 5.2e9, 7.9e9])
+    S = m.run_sp(f)._S
+    ref = oracle_S(m, f)
+    assert S.shape == (P, P, 5)
+    assert np.max(np.abs(S - ref)) < TOL
+    ki = m._compiled().handle.kernel_info()
+    plan = m._compiled().plan
+    expect_block = plan.n_real > 32 or P > 16
+    assert ki["kernel_class"] == (1 if expect_block else 0)
+
+
+def test_full_mode_forced_and_block_forced_agree():
+    m, P = ladder(10, 3, seed=5)
+    f = np.linspace(0.2e9, 6e9, 77)
+    ref = oracle_S(m, f)
+    for mode in ("full", "norton"):
+        for force in ("0", "1"):
+            os.environ["HVB_FORCE_BLOCK"] = force
+            try:
+                S = CompiledNetwork(m, mode=mode).run(f)[0]
+            finally:
+                os.environ.pop("HVB_FORCE_BLOCK")
+            assert np.max(np.abs(S - ref)) < TOL, (mode, force)
+
+
+def test_every_parameter_kind_in_one_circuit():
+    mc = hv.MonteCarlo()
+    m = hv.Model(suppress_loadbar=True)
+    a, b, c = m.quick_port(50), m.quick_port(75), m.quick_port(33.0)
+    x, y = m.node(), m.node()
+    Cr = mc.gaussian(1e-12, 5e-14)
+    Lr = mc.uniform(1e-9, 2e-9)
+    Lr._value = 1.5e-9            # a uniform Random is Uninitialized until drawn (numeric.py:233), and
+    #                               Impedance.__init__ evaluates its value once (impedance.py:18)
+    Gr = mc.gaussian(0.02, 0.001)                                          # a conductance, in siemens
+    Rn = mc.gaussian(-40.0, 1.0)                                           # used negated: +40 ohm
+    iL = mc.gaussian(5e8, 1e7)                                             # used inverted: 2 nH
+    m.capacitor(a, m.gnd, Cr)                                              # SAMPLE
+    m.inductor(a, x, Lr)                                                   # SAMPLE (uniform)
+    m.admittance(x, m.gnd, Gr.inverse().inverse())                         # Inverse(Inverse(Random)) -> Random
+    m.impedance(x, y, Rn.negative())                                       # SAMPLE_NEG
+    m.capacitor(y, m.gnd, lambda f: 1e-12 * (1 + f / 1e10))                # TABLE (real)
+    m.impedance(y, b, lambda f: 20 + 2j * np.pi * f * 1e-9)                # TABLE (complex)
+    m.admittance(b, c, 0.01 + 0.002j)                                      # CONST complex
+    m.resistor(c, m.gnd, 120.0)
+    m.transmissionline(x, c, 60.0, complex(3.0, -0.05), 7e-3)              # closed-form beta, lossy
+    m.TL(y, a, lambda f: 2 * np.pi * f / 299792458 * 1.5, 4e-3, 45.0)      # TABLE beta
+    m.inductor(b, m.gnd, iL.inverse())                                     # SAMPLE_INV
+    f = np.linspace(0.4e9, 5e9, 41)
+    np.random.seed(5)
+    vals = mc.draw(6)
+    S4 = m.run_sp_batch(f, mc._random_numbers, vals)
+    assert S4.shape == (6, 3, 3, 41)
+    for s in range(6):
+        for r, v in zip(mc._random_numbers, vals[s]):
+            r._value = v
+        assert np.max(np.abs(S4[s] - oracle_S(m, f))) < 5e-12, s
+    kinds = {k for k, _ in m._compiled().plan.prefs.tolist()}
+    assert {pl.PK_CONST, pl.PK_SAMPLE, pl.PK_SAMPLE_NEG, pl.PK_SAMPLE_INV, pl.PK_TABLE, pl.PK_BETA} <= kinds
+
+
+def test_nport_y_block_equals_discrete_admittances():
+    """The reference's NPortY cannot be constructed (App. B-4); ours must stamp the indefinite block."""
+    y12 = lambda f: 1 / (30 + 2j * np.pi * f * 2e-9)
+    y1g = lambda f: 2j * np.pi * f * 1e-12
+    y2g = lambda f: 1 / 150.0 + 0 * f
+    m1 = hv.Model(suppress_loadbar=True)
+    a, b = m1.quick_port(50), m1.quick_port(50)
+    Y = [[lambda f: y12(f) + y1g(f), lambda f: -y12(f)], [lambda f: -y12(f), lambda f: y12(f) + y2g(f)]]
+    m1.n_port_Y(m1.gnd, [a, b], Y, 50.0)
+    m1.resistor(a, m1.gnd, 1e6)
+    m1.resistor(b, m1.gnd, 1e6)
+    m2 = hv.Model(suppress_loadbar=True)
+    a2, b2 = m2.quick_port(50), m2.quick_port(50)
+    m2.admittance(a2, b2, y12)
+    m2.admittance(a2, m2.gnd, y1g)
+    m2.admittance(b2, m2.gnd, y2g)
+    m2.resistor(a2, m2.gnd, 1e6)
+    m2.resistor(b2, m2.gnd, 1e6)
+    f = np.linspace(0.5e9, 6e9, 33)
+    assert np.max(np.abs(m1.run_sp(f)._S - m2.run_sp(f)._S)) < 1e-12
+    assert np.max(np.abs(m2.run_sp(f)._S - oracle_S(m2, f))) < TOL
+
+
+def test_touchstone_two_port_ma_format_device_splines(tmp_path):
+    fs = np.linspace(1.0, 4.0, 31)                       # GHz
+    s11 = 0.3 * np.exp(-1j * fs)
+    s21 = 0.8 * np.exp(-2j * fs)
+    s12 = 0.1 * np.exp(-2j * fs)                          # non-reciprocal on purpose
+    s22 = 0.2 * np.exp(0.5j * fs)
+    path = tmp_path / "amp.s2p"
+    with open(path, "w") as fh:
+        fh.write("# GHz S MA R 50\n")
+        for k in range(len(fs)):
+            row = [fs[k]]
+            for v in (s11[k], s21[k], s12[k], s22[k]):   # touchstone 2-port order
+                row += [abs(v), np.degrees(np.angle(v))]
+            fh.write(" ".join("%.12g" % x for x in row) + "\n")
+    m = hv.Model(suppress_loadbar=True)
+    a, b = m.quick_port(50), m.quick_port(50)
+    n1, n2 = m.node(), m.node()
+    m.resistor(a, n1, 5.0)
+    m.capacitor(n2, m.gnd, 0.3e-12)
+    m.inductor(n2, b, 0.7e-9)
+    hv.FileBasedNPort(str(path)).connect(n1, n2)
+    # inside, at, and outside the data range (constant end fill)
+    f = np.concatenate([np.linspace(0.2e9, 5e9, 97), fs[:3] * 1e9, [1.0e9, 4.0e9]])
+    plan = m._compiled().plan
+    assert len(plan.spl_trace) == 4 and plan.n_tables == 0          # evaluated on the device, not tabulated
+    assert np.max(np.abs(m.run_sp(f)._S - oracle_S(m, f))) < 5e-12
+
+
+def test_repeated_runs_track_parameter_and_netlist_changes():
+    sweep_param = hv.Param(np.array([1e-12, 2e-12, 4e-12]))
+    m = hv.Model(suppress_loadbar=True)
+    a, b = m.quick_port(50), m.quick_port(50)
+    m.capacitor(a, m.gnd, sweep_param)
+    m.inductor(a, b, 2e-9)
+    f = np.linspace(1e9, 3e9, 64)
+    outs = []
+    for i in range(3):
+        sweep_param.set_index(i)
+        sweep_param.initialize()
+        S = m.run_sp(f)._S.copy()
+        assert np.max(np.abs(S - oracle_S(m, f))) < TOL
+        outs.append(S)
+    assert not np.array_equal(outs[0], outs[1])
+    first = m._compiled()
+    m.run_sp(f)
+    assert m._compiled() is first                                    # plan reused while the netlist is unchanged
+    m.resistor(b, m.gnd, 200.0)                                      # netlist edit after a run
+    S = m.run_sp(f)._S
+    assert m._compiled() is not first
+    assert np.max(np.abs(S - oracle_S(m, f))) < TOL
+
+
+def test_unsorted_duplicate_and_log_spaced_frequencies():
+    m, _ = ladder(7, 2, seed=3)
+    f = np.concatenate([np.logspace(6, 10.3, 50)[::-1], [2e9, 2e9, 1e6]])
+    S = m.run_sp(f)._S
+    assert np.max(np.abs(S - oracle_S(m, f))) < TOL
+    assert np.array_equal(S[:, :, 50], S[:, :, 51])
+
+
+def test_badly_scaled_admittances():
+    m = hv.Model(suppress_loadbar=True)
+    a, b = m.quick_port(50), m.quick_port(50)
+    x = m.node()
+    m.resistor(a, x, 1e-3)
+    m.resistor(x, b, 1e5)
+    m.capacitor(x, m.gnd, 1e-15)
+    m.inductor(x, m.gnd, 1e-3)
+    f = np.array([1e3, 1e6, 1e9, 1e11])
+    S = m.run_sp(f)._S
+    ref = oracle_S(m, f)
+    assert np.max(np.abs(S - ref)) < 1e-11
+
+
+def test_pageable_output_buffer_and_status_word():
+    m, _ = ladder(5, 2, seed=9)
+    cn = m._compiled()
+    f = np.linspace(1e9, 2e9, 1000)
+    consts, prefs, tables, samples = cn.resolve(f)
+    out = np.empty((1, 2, 2, 1000), dtype=np.complex128)             # ordinary (pageable) numpy memory
+    S, status = cn.handle.run_host(f, consts, prefs, tables, samples, out)
+    assert S is out and status == 0
+    assert np.max(np.abs(out[0] - oracle_S(m, f))) < TOL
+
+
+def test_two_models_interleaved():
+    m1, _ = ladder(5, 2, seed=1)
+    m2, _ = ladder(11, 3, seed=2)
+    f = np.linspace(1e9, 5e9, 200)
+    for _ in range(3):
+        assert np.max(np.abs(m1.run_sp(f)._S - oracle_S(m1, f))) < TOL
+        assert np.max(np.abs(m2.run_sp(f)._S - oracle_S(m2, f))) < TOL
