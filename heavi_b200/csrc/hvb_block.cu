@@ -20,7 +20,9 @@
 
 #include <algorithm>
 
+#ifndef HVB_BLOCK_THREADS
 #define HVB_BLOCK_THREADS 256
+#endif
 #define HVB_BLOCK_WARPS (HVB_BLOCK_THREADS / 32)
 
 // pivot key of a panel row: high word of |re|+|im| with the low 10 bits replaced by (1023 - row),

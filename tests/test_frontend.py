@@ -141,3 +141,22 @@ def test_parameter_sweep_combinations_and_cap():
     big.lin(0, 1).add(101)
     big.lin(0, 1).add(100)
     assert len(big.combinations()) == 10_100
+
+
+def test_optimiser_metrics_and_variables():
+    from heavi_b200.lib import optim
+    v = optim.OptimVar(-12.0, bounds=(-13, -6), mapping=lambda x: 10 ** x)
+    assert v(np.array([1.0, 2.0])).tolist() == [1e-12, 1e-12] and v.describe()[0] == "sample"
+    v.set(-11.0)
+    assert v._value == pytest.approx(1e-11)
+    with pytest.raises(TypeError):
+        optim.OptimVar(1.0, mapping=3)
+    S = np.array([0.1, 0.5, 1.0])
+    assert optim.dBbelow(-10)(S) == pytest.approx(np.sqrt(np.mean(np.clip(20 * np.log10(S) + 10, 0, None) ** 2)) / 10)
+    assert optim.dBabove(-3, optim.PNorm.MAX)(S) == pytest.approx(np.max(np.clip(-3 - 20 * np.log10(S), 0, None)) / 10)
+    with pytest.raises(ValueError):
+        optim.FrequencyLevel(1e9, 2e9, 5, (1, 1))
+    m = hv.Model()
+    opt = optim.Optimiser(m)
+    c, l = opt.cap(), opt.ind(logscale=False)
+    assert opt.bounds == [(-13, -6), (1e-12, 1e-5)] and opt.x0.tolist() == [-12.0, 1e-9]

@@ -264,3 +264,38 @@ def test_parameter_sweep_batch_matches_serial_loop():
     assert nd._sdata.shape == (4, 3, 2, 2, 257) == serial._sdata.shape
     assert np.array_equal(nd._sdata, serial._sdata)
     assert np.array_equal(nd.S(2, 1), serial.S(2, 1))
+
+
+def test_optimiser_population_objective_matches_serial_objective():
+    """One batched run over a population == the reference's one-run_sp-per-candidate objective
+    (lib/optim.py:424-436)."""
+    from heavi_b200.lib import optim
+
+    def build():
+        m = hv.Model(suppress_loadbar=True)
+        opt = optim.Optimiser(m)
+        C1, L1, C2 = opt.cap(initial=-12.0), opt.ind(initial=-8.7), opt.cap(logscale=False, initial=-12.3)
+        a, b = m.quick_port(50), m.quick_port(50)
+        x = m.node()
+        m.capacitor(a, m.gnd, C1)
+        m.inductor(a, x, L1)
+        m.capacitor(x, m.gnd, C2)
+        m.resistor(x, b, 3.0)
+        opt.add_splimit(1e9, 2e9, 21, (2, 1), lower_limit=optim.dBabove(-1))
+        opt.add_splimit(4e9, 6e9, 31, (2, 1), upper_limit=optim.dBbelow(-20))
+        opt.add_splimit(1e9, 2e9, 21, (1, 1), upper_limit=optim.dBbelow(-15), weight=0.5)
+        return m, opt
+
+    rng = np.random.default_rng(4)
+    X = np.stack([rng.uniform(-12.5, -11.5, 9), rng.uniform(-9.2, -8.4, 9), rng.uniform(2e-13, 2e-12, 9)])   # [vars, pop]
+    m1, o1 = build()
+    serial = o1.generate_objective()
+    ref = np.array([serial(X[:, k]) for k in range(X.shape[1])])
+    m2, o2 = build()
+    batched = o2.generate_population_objective()
+    got = batched(X)
+    assert got.shape == (9,) and np.allclose(got, ref, rtol=1e-12, atol=1e-14)
+    assert batched(X[:, 3]) == pytest.approx(ref[3], rel=1e-12)
+    d1, d2 = build()[1], build()[1]
+    assert d2.generate_population_objective(differential_weighting=0.3)(X)[2] == pytest.approx(
+        d1.generate_objective(differential_weighting=0.3)(X[:, 2]), rel=1e-12)
