@@ -141,17 +141,18 @@ __device__ __forceinline__ cplx csqrt_np(cplx z) {
 // B-spline trace evaluation: scipy's find_interval + _deBoor_D + dot, constant end fill
 // (src/heavi/lib/touchstone.py:253-260 -> scipy.interpolate.interp1d(kind='cubic'))
 // ------------------------------------------------------------------------------------------------
-static __device__ __noinline__ cplx spline_eval(const double* __restrict__ spl_t, const cplx* __restrict__ spl_c,
-                                                const int4* __restrict__ spl_trace, const cplx* __restrict__ spl_fill,
-                                                const double2* __restrict__ spl_range, int tr, double x) {
-    const double2 rng = spl_range[tr];
-    if (x < rng.x) return spl_fill[2 * tr];
-    if (x > rng.y) return spl_fill[2 * tr + 1];
-    const int4 d = spl_trace[tr];                   // t_off, nt, c_off, k
-    const double* __restrict__ t = spl_t + d.x;
-    const cplx* __restrict__ c = spl_c + d.z;
-    const int k = d.w;
-    const int nb = d.y - k - 1;                     // number of basis functions
+// knot interval + the k+1 non-zero basis values at x: identical for every trace that shares a knot
+// vector (all P^2 traces of one Touchstone block do), so callers that evaluate many traces at one
+// frequency compute this once and only redo the coefficient dot product per trace.
+struct SplineBasis {
+    int t_off, nt, k, ell;
+    double h[HVB_MAX_SPLINE_K + 1];
+};
+
+static __device__ __noinline__ void spline_basis(const double* __restrict__ spl_t, int t_off, int nt, int k, double x,
+                                                 SplineBasis* __restrict__ out) {
+    const double* __restrict__ t = spl_t + t_off;
+    const int nb = nt - k - 1;                      // number of basis functions
     // largest ell in [k, nb-1] with t[ell] <= x
     int lo = k, hi = nb - 1;
     while (lo < hi) {
@@ -181,16 +182,34 @@ static __device__ __noinline__ cplx spline_eval(const double* __restrict__ spl_t
             }
         }
     }
+    out->t_off = t_off; out->nt = nt; out->k = k; out->ell = ell;
+#pragma unroll
+    for (int a = 0; a <= HVB_MAX_SPLINE_K; ++a) out->h[a] = (a <= k) ? h[a] : 0.0;
+}
+
+__device__ __forceinline__ cplx spline_dot(const cplx* __restrict__ c, const SplineBasis& b) {
     cplx out = cmk(0.0, 0.0);
 #pragma unroll
     for (int a = 0; a <= HVB_MAX_SPLINE_K; ++a) {
-        if (a <= k) {
-            const cplx ca = c[ell - k + a];
-            out.x = __dadd_rn(out.x, __dmul_rn(ca.x, h[a]));
-            out.y = __dadd_rn(out.y, __dmul_rn(ca.y, h[a]));
+        if (a <= b.k) {
+            const cplx ca = c[b.ell - b.k + a];
+            out.x = __dadd_rn(out.x, __dmul_rn(ca.x, b.h[a]));
+            out.y = __dadd_rn(out.y, __dmul_rn(ca.y, b.h[a]));
         }
     }
     return out;
+}
+
+static __device__ __noinline__ cplx spline_eval(const double* __restrict__ spl_t, const cplx* __restrict__ spl_c,
+                                                const int4* __restrict__ spl_trace, const cplx* __restrict__ spl_fill,
+                                                const double2* __restrict__ spl_range, int tr, double x) {
+    const double2 rng = spl_range[tr];
+    if (x < rng.x) return spl_fill[2 * tr];
+    if (x > rng.y) return spl_fill[2 * tr + 1];
+    const int4 d = spl_trace[tr];                   // t_off, nt, c_off, k
+    SplineBasis b;
+    spline_basis(spl_t, d.x, d.y, d.w, x, &b);
+    return spline_dot(spl_c + d.z, b);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -97,77 +97,115 @@ struct CoopCtx {
     cplx* scratch;
 };
 
+// complex array in shared memory addressed through the shared window (an out-of-line function only
+// sees generic pointers; explicit ld.shared / st.shared keeps these accesses on the LDS/STS path)
+struct SmemCplx {
+    unsigned base;
+    __device__ __forceinline__ explicit SmemCplx(const cplx* p) : base((unsigned)__cvta_generic_to_shared(p)) {}
+    __device__ __forceinline__ cplx ld(int i) const {
+        cplx v;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(base + 16u * (unsigned)i));
+        return v;
+    }
+    __device__ __forceinline__ void st(int i, cplx v) const {
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(base + 16u * (unsigned)i), "d"(v.x), "d"(v.y) : "memory");
+    }
+};
+
 template <int G>
 static __device__ __noinline__ unsigned coop_nport(const CoopCtx* ctx, const int* __restrict__ op, int gl) {
     const ParamView& D = ctx->pv;
     const double f = ctx->f;
     const long long fi = ctx->fi;
     const double* __restrict__ srow = ctx->srow;
-    cplx* __restrict__ dyn = ctx->dyn;
-    cplx* __restrict__ scratch = ctx->scratch;
+    const SmemCplx dyn(ctx->dyn), W(ctx->scratch);
     const int code = op[0], out = op[1] - ctx->nvc, Pn = op[2], first = op[3];
     const int ldo = Pn + 1;
+    // lanes form a (row, column-slice) grid: PR row slots (power of two >= Pn), LPR lanes per row
+    int PR = 1;
+    while (PR < Pn) PR <<= 1;
+    const int LPR = G / PR > 0 ? G / PR : 1;
+    const int r = gl % PR, cg = gl / PR;
+    const bool row_live = r < Pn;
     unsigned kmin = 0xffffffffu, kmax = 0u;
     if (code == COOP_NPORT_Y) {
         for (int e = gl; e < Pn * Pn; e += G)
-            dyn[out + (e / Pn) * ldo + (e % Pn)] = eval_param(D, first + e, f, fi, srow);
+            dyn.st(out + (e / Pn) * ldo + (e % Pn), eval_param(D, first + e, f, fi, srow));
         __syncwarp();
     } else {
         const int ld = 2 * Pn;
+        SplineBasis sb;
+        sb.t_off = -1; sb.nt = 0; sb.k = 0; sb.ell = 0;
         for (int e = gl; e < Pn * Pn; e += G) {
             const int i = e / Pn, j = e % Pn;
-            const cplx s = eval_param(D, first + e, f, fi, srow);
+            cplx s;
+            const int2 pr = D.prefs[first + e];
+            if (pr.x == PK_SPLINE) {
+                // all traces of a Touchstone block share one knot vector: interval search and basis
+                // values are done once per lane, each further trace is a 4-term dot product
+                const double2 rng = D.spl_range[pr.y];
+                if (f < rng.x) s = D.spl_fill[2 * pr.y];
+                else if (f > rng.y) s = D.spl_fill[2 * pr.y + 1];
+                else {
+                    const int4 d4 = D.spl_trace[pr.y];
+                    if (d4.x != sb.t_off || d4.y != sb.nt || d4.w != sb.k) spline_basis(D.spl_t, d4.x, d4.y, d4.w, f, &sb);
+                    s = spline_dot(D.spl_c + d4.z, sb);
+                }
+            } else {
+                s = eval_param(D, first + e, f, fi, srow);
+            }
             const double d = (i == j) ? 1.0 : 0.0;
-            scratch[j * ld + i] = cmk(d + s.x, s.y);              // (I+S)^T
-            scratch[j * ld + Pn + i] = cmk(d - s.x, -s.y);        // (I-S)^T
+            W.st(j * ld + i, cmk(d + s.x, s.y));              // (I+S)^T
+            W.st(j * ld + Pn + i, cmk(d - s.x, -s.y));        // (I-S)^T
         }
         __syncwarp();
-        bool done = gl >= Pn;
+        bool done = !row_live;
         int mycol = 0;
         for (int k = 0; k < Pn; ++k) {
-            const cplx mine = (gl < Pn) ? scratch[gl * ld + k] : cmk(0.0, 0.0);
-            const unsigned key = group_max_u32<G>(pivot_key(mine, done, gl));
+            const cplx mine = row_live ? W.ld(r * ld + k) : cmk(0.0, 0.0);
+            const unsigned key = group_max_u32<G>(pivot_key(mine, done, r));
             kmin = min(kmin, key); kmax = max(kmax, key);
             const int p = 31 - (int)(key & 31u);
-            if (gl == p) { done = true; mycol = k; }
-            const cplx inv = crecip_fast(scratch[p * ld + k]);
-            if (gl < Pn && gl != p) {
+            if (r == p) { done = true; mycol = k; }
+            const cplx inv = crecip_fast(W.ld(p * ld + k));
+            if (row_live && r != p) {
                 const cplx m = cmul(mine, inv);
-                for (int c = k + 1; c < ld; ++c) {
-                    cplx v = scratch[gl * ld + c];
-                    cfnma(v, m, scratch[p * ld + c]);
-                    scratch[gl * ld + c] = v;
+                for (int c = k + 1 + cg; c < ld; c += LPR) {
+                    cplx v = W.ld(r * ld + c);
+                    cfnma(v, m, W.ld(p * ld + c));
+                    W.st(r * ld + c, v);
                 }
             }
             __syncwarp();
         }
-        if (gl < Pn) {
-            const cplx inv = crecip_fast(scratch[gl * ld + mycol]);
-            const cplx z0 = D.consts[op[4]];
-            const cplx iz = crecip_np(z0);                          // (1/Z0), nport.py:32
-            for (int c = 0; c < Pn; ++c) {
-                const cplx x = cmul(scratch[gl * ld + Pn + c], inv);   // X^T[mycol][c] = X[c][mycol]
-                dyn[out + c * ldo + mycol] = (iz.y == 0.0) ? cscale(x, iz.x) : cmul(iz, x);
+        if (row_live) {
+            const cplx inv = crecip_fast(W.ld(r * ld + mycol));
+            const cplx iz = crecip_np(D.consts[op[4]]);            // (1/Z0), nport.py:32
+            for (int c = cg; c < Pn; c += LPR) {
+                const cplx x = cmul(W.ld(r * ld + Pn + c), inv);   // X^T[mycol][c] = X[c][mycol]
+                dyn.st(out + c * ldo + mycol, (iz.y == 0.0) ? cscale(x, iz.x) : cmul(iz, x));
             }
         }
         __syncwarp();
     }
-    // reference-node row / column: -row sums, -column sums, +total (nport.py:35-38)
-    for (int i = gl; i < Pn; i += G) {
-        cplx rs = cmk(0.0, 0.0), cs = cmk(0.0, 0.0);
-        for (int j = 0; j < Pn; ++j) {
-            rs = cadd(rs, dyn[out + i * ldo + j]);
-            cs = cadd(cs, dyn[out + j * ldo + i]);
+    // reference-node row / column: -row sums, -column sums, +total (nport.py:35-38), sums in index order
+    for (int t = gl; t < 2 * Pn; t += G) {
+        const int i = t >> 1;
+        cplx acc = cmk(0.0, 0.0);
+        if (t & 1) {
+            for (int j = 0; j < Pn; ++j) acc = cadd(acc, dyn.ld(out + j * ldo + i));
+            dyn.st(out + Pn * ldo + i, cneg(acc));
+        } else {
+            for (int j = 0; j < Pn; ++j) acc = cadd(acc, dyn.ld(out + i * ldo + j));
+            dyn.st(out + i * ldo + Pn, cneg(acc));
+            W.st(i, acc);
         }
-        dyn[out + i * ldo + Pn] = cneg(rs);
-        dyn[out + Pn * ldo + i] = cneg(cs);
-        scratch[i] = rs;
     }
     __syncwarp();
     if (gl == 0) {
         cplx tot = cmk(0.0, 0.0);
-        for (int i = 0; i < Pn; ++i) tot = cadd(tot, scratch[i]);
-        dyn[out + Pn * ldo + Pn] = tot;
+        for (int i = 0; i < Pn; ++i) tot = cadd(tot, W.ld(i));
+        dyn.st(out + Pn * ldo + Pn, tot);
     }
     __syncwarp();
     return (code == COOP_NPORT_S) ? pivot_status(kmin, kmax) : 0u;
