@@ -44,6 +44,9 @@ __host__ __device__ constexpr int hvb_group_for(int n) { return n <= 4 ? 4 : n <
 // registers per thread are capped so that small systems keep many warps resident
 template <int N, int P>
 struct WarpCfg {
+#ifndef HVB_THREE_BLOCK_REGS
+#define HVB_THREE_BLOCK_REGS 180
+#endif
 #ifndef HVB_REG_FLOOR
 #define HVB_REG_FLOOR 88
 #endif
@@ -55,7 +58,7 @@ struct WarpCfg {
 #endif
                                       kRegsWanted <= 64 ? 8 : kRegsWanted <= 72 ? 7 : kRegsWanted <= 80 ? 6
                                     : kRegsWanted <= 96 ? 5 : kRegsWanted <= 128 ? 4 : kRegsWanted <= 168 ? 3
-                                    : kRegsWanted <= 255 ? 2 : 1;
+                                    : kRegsWanted <= HVB_THREE_BLOCK_REGS ? 3 : kRegsWanted <= 255 ? 2 : 1;
 };
 
 template <int G>
