@@ -1,2 +1,2 @@
 """Part libraries (host-side netlist builders) and the optimiser: `smd`, `tl`, `libgen`, `touchstone`, `optim`."""
-from . import libgen, optim, smd, tl, touchstone  # noqa: F401
+from . import libgen, optim, smd, subcircuit, tl, touchstone  # noqa: F401

@@ -160,3 +160,39 @@ def test_optimiser_metrics_and_variables():
     opt = optim.Optimiser(m)
     c, l = opt.cap(), opt.ind(logscale=False)
     assert opt.bounds == [(-13, -6), (1e-12, 1e-5)] and opt.x0.tolist() == [-12.0, 1e-9]
+
+
+def test_subcircuit_framework():
+    from heavi_b200.lib.libgen import SubCircuit, TwoNodeSubCircuit, ThreeNodeSubCircuit, FourNodeSubCircuit
+
+    class Pad(TwoNodeSubCircuit):
+        def __on_connect__(self):
+            self.network.resistor(self.node(1), self.node(2), 10.0)
+
+    m = hv.Model()
+    a, b, c = m.quick_port(50), m.node(), m.quick_port(50)
+    p1 = Pad()
+    assert (p1 < a) is p1 and (p1 > b) is b              # attach 1, attach 2 -> expands, returns the node
+    assert len([x for x in m.components if x.kind == "resistor"]) == 1
+    Pad().connect(b, c)
+    assert len([x for x in m.components if x.kind == "resistor"]) == 2
+    with pytest.raises(NotImplementedError):
+        SubCircuit().__on_connect__()
+    with pytest.raises(ValueError, match="at least one node"):
+        s = SubCircuit(); s.network = m; s.connect()
+    other = hv.Model()
+    with pytest.raises(ValueError, match="same Network"):
+        Pad().connect(a, other.node())
+    assert ThreeNodeSubCircuit().n_nodes == 3 and FourNodeSubCircuit().n_nodes == 4
+
+    class Tee(ThreeNodeSubCircuit):
+        def __on_connect__(self):
+            for i in (1, 2, 3):
+                self.network.resistor(self.node(i), self.network.gnd, 100.0)
+
+    t = Tee()
+    t.t(1) > a
+    t.t(3) < c
+    assert t.first_node == 2 and not t._complete()
+    t.partial_connect(2, b)
+    assert len([x for x in m.components if x.kind == "resistor"]) == 5
