@@ -405,15 +405,28 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     const char* dbase = (const char*)pl->inbuf.p;
 
     // tiles: whole samples when several fit in a chunk, else frequency slabs of one sample
+    // Tile size: large enough for the copy to run at the full PCIe rate (>= a few MB), small enough
+    // that the first copy starts early and the exposed head (first kernel) / tail stay short; tiles
+    // are equal-sized so no short tile trails the pipeline.
     const char* env = getenv("HVB_CHUNK_MB");
-    const int64_t chunk_bytes = (int64_t)(env && atoi(env) > 0 ? atoi(env) : 128) << 20;
-    const int64_t max_pts = std::max<int64_t>(chunk_bytes / (PP * 16), 1);
-    int64_t Sc = 1, Fc = nF;
-    if (nF <= max_pts) Sc = std::min<int64_t>(nS, std::max<int64_t>(max_pts / nF, 1));
-    else Fc = max_pts;
-    // small jobs still get two tiles so that the copy-out of the first overlaps the second kernel
-    if (Sc >= nS && Fc >= nF && nS * nF >= 65536) {
-        if (nS >= 2) Sc = (nS + 1) / 2; else Fc = (nF + 1) / 2;
+    const int64_t chunk_bytes = (int64_t)(env && atoi(env) > 0 ? atoi(env) : 16) << 20;
+    const int64_t total_bytes = nS * nF * PP * 16;
+    int64_t ntiles = std::max<int64_t>((total_bytes + chunk_bytes - 1) / chunk_bytes, 1);
+    if (ntiles == 1 && nS * nF >= 65536) ntiles = 2;      // small jobs: overlap copy 1 with kernel 2
+    int64_t Sc = nS, Fc = nF;
+    if (nS >= ntiles) {
+        Sc = (nS + ntiles - 1) / ntiles;                  // whole samples per tile
+    } else {
+        Sc = 1;                                           // frequency slabs of one sample
+        const int64_t per_sample = (ntiles + nS - 1) / nS;
+        Fc = std::max<int64_t>((nF + per_sample - 1) / per_sample, 1);
+        // a slab is copied out as P*P separate row segments: keep each segment around 1 MB or the
+        // copy engine spends its time on per-copy overhead (measured: 128 KB segments halve the rate)
+        if (Fc < 65536 && nF > Fc) {
+            const int64_t want = std::min<int64_t>(nF, 65536);
+            const int64_t slabs = std::max<int64_t>(nF / want, 1);
+            Fc = (nF + slabs - 1) / slabs;
+        }
     }
     for (int b = 0; b < 2; ++b) CU(pl->S[b].ensure((size_t)Sc * PP * Fc * 16));
 
