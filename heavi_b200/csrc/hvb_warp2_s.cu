@@ -17,6 +17,18 @@ const void* hvb_warp2_kernel_ptr(int n, int p) {
     if (n == 6 && p == 4) return (const void*)hvb_warp2_kernel<6, 4>;
     if (n == 7 && p == 4) return (const void*)hvb_warp2_kernel<7, 4>;
     if (n == 8 && p == 4) return (const void*)hvb_warp2_kernel<8, 4>;
+    if (n == 10 && p == 2) return (const void*)hvb_warp2_kernel<10, 2>;
+    if (n == 12 && p == 2) return (const void*)hvb_warp2_kernel<12, 2>;
+    if (n == 14 && p == 2) return (const void*)hvb_warp2_kernel<14, 2>;
+    if (n == 16 && p == 2) return (const void*)hvb_warp2_kernel<16, 2>;
+    if (n == 10 && p == 4) return (const void*)hvb_warp2_kernel<10, 4>;
+    if (n == 12 && p == 4) return (const void*)hvb_warp2_kernel<12, 4>;
+    if (n == 14 && p == 4) return (const void*)hvb_warp2_kernel<14, 4>;
+    if (n == 16 && p == 4) return (const void*)hvb_warp2_kernel<16, 4>;
+    if (n == 8 && p == 8) return (const void*)hvb_warp2_kernel<8, 8>;
+    if (n == 10 && p == 8) return (const void*)hvb_warp2_kernel<10, 8>;
+    if (n == 12 && p == 8) return (const void*)hvb_warp2_kernel<12, 8>;
+    if (n == 14 && p == 8) return (const void*)hvb_warp2_kernel<14, 8>;
     return nullptr;
 }
 int hvb_warp2_group(int n) { return hvb_group2_for(n); }
