@@ -63,13 +63,15 @@ struct hvb_plan {
     int32_t* h_status = nullptr;                       // pinned status word
     cudaEvent_t ev_ready = nullptr, ev_tail = nullptr;
     // host pipeline buffers
-    DevBuf f, samples, tables, S[2], status, work, dump, stats, inbuf;
+    DevBuf f, samples, tables, S[2], status, work[2], dump, stats, inbuf;
     cudaStream_t streams[2] = {nullptr, nullptr};
     cudaEvent_t upload_done = nullptr;
     // kernel choice
     int kclass = 0, G = 0, PMAX = 0, NB = 0, lanes = 0, rows_per_lane = 1, threads = 0, ctas_per_sm = 0, sm_count = 0, regs = 0;
     size_t smem = 0;
     int region_a = 0, region_b = 0;
+    int band = -1;                                     // structural half bandwidth of the matrix block
+    size_t work_words = 0;                             // kernel C: workspace words per thread
     const void* kernel = nullptr;
     int max_grid = 0;
     int64_t launches = 0;
@@ -113,6 +115,30 @@ extern "C" int hvb_warp_shape(int32_t n, int32_t P, int32_t max_nport, int32_t* 
     return HVB_OK;
 }
 
+// kernel B's per-CTA workspaces; one set per pipeline slot because the two streams of hvb_run_host
+// may have a kernel each in flight
+static int ensure_block_work(hvb_plan* pl, int slot) {
+    const hvb_plan_desc& d = pl->d;
+    const size_t ldw = ((size_t)d.ncols + 3) & ~(size_t)3;
+    const size_t need = (size_t)pl->max_grid * (d.n + 3) * ldw * sizeof(cplx);
+    if (pl->work[slot].bytes >= need) return HVB_OK;
+    CU(pl->work[slot].ensure(need));
+    CU(cudaMemset(pl->work[slot].p, 0, pl->work[slot].bytes));   // padding rows / columns stay finite
+    return HVB_OK;
+}
+
+static bool band_kernel_ok(const hvb_plan* pl) {
+    const hvb_plan_desc& d = pl->d;
+    const char* off = getenv("HVB_NO_BAND");
+    if (off && off[0] == '1') return false;
+    const char* force = getenv("HVB_FORCE_BLOCK");          // tests: dense block kernel for any shape
+    if (force && force[0] == '1') return false;
+    if (pl->band < 0 || d.n_coops != 0) return false;
+    const int B = hvb_band_round_up(pl->band);
+    if (B == 0) return false;
+    return 2 * (3 * B + 1) <= d.n;                       // a narrow band, not a small dense block
+}
+
 static int select_kernel(hvb_plan* pl) {
     const hvb_plan_desc& d = pl->d;
     cudaDeviceProp prop;
@@ -146,6 +172,16 @@ static int select_kernel(hvb_plan* pl) {
         const int sys_per_block = (pl->threads / 32) * (32 / pl->lanes);
         const size_t shared_words = hvb_warp_shared_words(N, d.n_const_vals, d.n_row_ent, d.n_fast_ops, d.P);
         pl->smem = (shared_words + (size_t)sys_per_block * (pl->region_a + pl->region_b)) * sizeof(cplx);
+    } else if (band_kernel_ok(pl)) {
+        // kernel C: thread per point, banded LU (hvb_band.cu); the workspace is sized per launch
+        pl->kclass = 2;
+        pl->NB = hvb_band_round_up(pl->band);
+        pl->kernel = hvb_band_kernel_ptr(pl->NB);
+        pl->threads = hvb_band_threads();
+        pl->smem = 0;
+        pl->work_words = hvb_band_words_per_thread(pl->NB, d.n, PP, d.n_dyn);
+        pl->region_a = std::max(d.n_dyn, 1);
+        pl->region_b = 1;
     } else {
         pl->kclass = 1;
         const char* nbs = getenv("HVB_BLOCK_NB");
@@ -169,7 +205,8 @@ static int select_kernel(hvb_plan* pl) {
         return fail(HVB_ERR_UNSUPPORTED, "system too large: needs %zu bytes of shared memory per CTA (max %zu)", pl->smem,
                     (size_t)prop.sharedMemPerBlockOptin);
     CU(cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
-    CU(cudaFuncSetAttribute(pl->kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    CU(cudaFuncSetAttribute(pl->kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                            pl->kclass == 2 ? (int)cudaSharedmemCarveoutMaxL1 : (int)cudaSharedmemCarveoutMaxShared));
     cudaFuncAttributes fa;
     CU(cudaFuncGetAttributes(&fa, pl->kernel));
     pl->regs = fa.numRegs;
@@ -181,11 +218,14 @@ static int select_kernel(hvb_plan* pl) {
     if (pl->kclass == 1) {
         const char* cps = getenv("HVB_BLOCK_CTAS_PER_SM");
         if (cps && atoi(cps) > 0) pl->max_grid = std::min(pl->max_grid, atoi(cps) * pl->sm_count);
-        {
-            const size_t ldw = ((size_t)d.ncols + 3) & ~(size_t)3;
-            CU(pl->work.ensure((size_t)pl->max_grid * (d.n + 3) * ldw * sizeof(cplx)));
-            CU(cudaMemset(pl->work.p, 0, pl->work.bytes));   // padding rows / columns stay finite
-        }
+        { int rc = ensure_block_work(pl, 0); if (rc) return rc; }
+    }
+    if (pl->kclass == 2) {
+        // bound the workspace: by default at most 24 GB per pipeline slot
+        const char* wg = getenv("HVB_BAND_WORK_GB");
+        const size_t budget = (size_t)(wg && atoi(wg) > 0 ? atoi(wg) : 24) << 30;
+        const size_t per_cta = pl->work_words * sizeof(cplx) * pl->threads;
+        pl->max_grid = (int)std::max<size_t>(std::min<size_t>((size_t)pl->max_grid, budget / per_cta), 1);
     }
     return HVB_OK;
 }
@@ -236,6 +276,13 @@ extern "C" int hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan**
         hvb_plan_destroy(pl);
         return fail(HVB_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(e));
     }
+    {   // structural half bandwidth of the matrix block (right-hand-side columns excluded)
+        int band = 0;
+        for (int r = 0; r < d.n; ++r)
+            for (int c = 0; c < d.n; ++c)
+                if (d.cell_ptr[r * d.ncols + c + 1] > d.cell_ptr[r * d.ncols + c]) band = std::max(band, std::abs(r - c));
+        pl->band = band;
+    }
     // the descriptor's host pointers are not kept
     pl->d.const_vals = nullptr; pl->d.ops = nullptr; pl->d.coops = nullptr; pl->d.cell_ptr = nullptr; pl->d.cell_ent = nullptr; pl->d.row_ptr = nullptr; pl->d.row_ent = nullptr; pl->d.fop_code = nullptr; pl->d.fop_out = nullptr; pl->d.fop_arg = nullptr; pl->d.epi_port_of_row = nullptr; pl->d.epi_scale = nullptr;
     pl->d.port_rows = nullptr; pl->d.port_zpref = nullptr; pl->d.spl_t = nullptr; pl->d.spl_c = nullptr; pl->d.spl_trace = nullptr;
@@ -253,7 +300,7 @@ extern "C" void hvb_plan_destroy(hvb_plan* pl) {
     cudaSetDevice(pl->device);
     DevBuf* all[] = {&pl->const_vals, &pl->ops, &pl->coops, &pl->cell_ptr, &pl->cell_ent, &pl->row_ptr, &pl->row_ent, &pl->fop_code, &pl->fop_out, &pl->fop_arg, &pl->epi_por, &pl->epi_scale, &pl->port_rows, &pl->port_zpref,
                      &pl->spl_t, &pl->spl_c, &pl->spl_trace, &pl->spl_fill, &pl->spl_range, &pl->consts, &pl->prefs,
-                     &pl->f, &pl->samples, &pl->tables, &pl->S[0], &pl->S[1], &pl->status, &pl->work, &pl->dump, &pl->stats, &pl->inbuf};
+                     &pl->f, &pl->samples, &pl->tables, &pl->S[0], &pl->S[1], &pl->status, &pl->work[0], &pl->work[1], &pl->dump, &pl->stats, &pl->inbuf};
     for (DevBuf* b : all) b->release();
     if (pl->h_stage) cudaFreeHost(pl->h_stage);
     if (pl->h_in) cudaFreeHost(pl->h_in);
@@ -296,7 +343,7 @@ static HvbDev make_dev(const hvb_plan* pl) {
     D.pv.spl_trace = (const int4*)pl->spl_trace.p;
     D.pv.spl_fill = (const cplx*)pl->spl_fill.p;
     D.pv.spl_range = (const double2*)pl->spl_range.p;
-    D.W = (cplx*)pl->work.p;
+    D.W = (cplx*)pl->work[0].p;
     return D;
 }
 
@@ -316,17 +363,27 @@ static int push_params(hvb_plan* pl, const hvb_run_args* a, cudaStream_t st) {
     return HVB_OK;
 }
 
-static int launch(hvb_plan* pl, HvbDev& D, cudaStream_t st) {
+static int launch(hvb_plan* pl, HvbDev& D, cudaStream_t st, int slot = 0) {
     const long long total = D.nS * D.nF;
     if (total <= 0) return HVB_OK;
     long long blocks;
     if (pl->kclass == 0) {
         const int spb = (pl->threads / 32) * (32 / pl->lanes);
         blocks = (total + spb - 1) / spb;
+    } else if (pl->kclass == 2) {
+        blocks = (total + pl->threads - 1) / pl->threads;
     } else {
         blocks = total;
     }
     const int grid = (int)std::min<long long>(blocks, pl->max_grid);
+    if (pl->kclass == 1) {
+        int rc = ensure_block_work(pl, slot);
+        if (rc) return rc;
+        D.W = (cplx*)pl->work[slot].p;
+    } else if (pl->kclass == 2) {
+        CU(pl->work[slot].ensure((size_t)grid * pl->threads * pl->work_words * sizeof(cplx)));
+        D.W = (cplx*)pl->work[slot].p;
+    }
     void* args[] = {&D};
     CU(cudaLaunchKernel(pl->kernel, dim3(grid), dim3(pl->threads), args, pl->smem, st));
     pl->launches++;
@@ -447,7 +504,7 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
             D.pv.tables = a->n_tables ? (const cplx*)pl->tables.p + fb : nullptr;
             D.S = (cplx*)pl->S[tile & 1].p;
             D.status = (int*)pl->inbuf.p;
-            rc = launch(pl, D, st);
+            rc = launch(pl, D, st, tile & 1);
             if (rc) return rc;
             // rows of nf elements, one per (sample, j, i); destination pitch is the full nF
             char* dst = (char*)S_out + ((size_t)sb * PP * nF + (size_t)fb) * 16;
@@ -580,7 +637,7 @@ extern "C" int hvb_assemble_host(hvb_plan* pl, const hvb_run_args* a, double* W_
 extern "C" int hvb_plan_kernel_info(hvb_plan* pl, hvb_kernel_info* out) {
     if (!pl || !out) return fail(HVB_ERR_ARG, "null argument");
     out->kernel_class = pl->kclass;
-    out->group = pl->kclass == 0 ? pl->G : pl->NB;
+    out->group = pl->kclass == 0 ? pl->G : pl->NB;       // kernel C: the instantiated half bandwidth
     out->pmax = pl->PMAX;
     out->threads = pl->threads;
     out->smem_bytes = (int32_t)pl->smem;

@@ -20,6 +20,11 @@ int hvb_block_threads();
 size_t hvb_block_smem_bytes(int nb, int n, int ncols, int region_a, int region_b);
 size_t hvb_block_main_words(int nb, int n, int ncols, int region_a, int region_b);
 
+const void* hvb_band_kernel_ptr(int b);
+int hvb_band_threads();
+int hvb_band_round_up(int b);
+size_t hvb_band_words_per_thread(int b, int n, int pp, int n_dyn);
+
 const void* hvb_dump_kernel_ptr();
 const void* hvb_stats_kernel_ptr();
 const void* hvb_dfma_probe_ptr();

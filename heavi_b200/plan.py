@@ -128,6 +128,7 @@ class DevicePlan:
     epi_scale: np.ndarray = None         # float64 [P,P]  sqrt|Zi| / sqrt|Zj| at [j,i]
     n_real: int = 0             # unknowns before identity padding (the dimension actually needed)
     max_nport: int = 0          # largest N-port block (a cooperative op needs that many lanes)
+    band: int = -1              # half bandwidth after the RCM row ordering (-1: natural order kept)
 
     @property
     def n_tables(self) -> int:
@@ -347,10 +348,55 @@ def norton_legal(table: StampTable) -> bool:
     return True
 
 
-def compile_plan(table: StampTable, mode: str = "auto", pad_to: tuple[int, int] | None = None) -> DevicePlan:
+BAND_MIN_ROWS = 33        # systems the register-resident kernels cannot hold
+BAND_MAX_HALF_WIDTH = 8   # widest band the banded kernel is instantiated for
+
+
+def _band_order(table: StampTable, rowmap: np.ndarray, mode: str):
+    """Reverse Cuthill-McKee ordering of the system rows (a symmetric permutation of the unknowns,
+    which leaves S unchanged).  Returns (new rowmap, half bandwidth) or None when the structure
+    is not narrow-banded.  Chains -- ladders, cascaded lines, filters -- come out tri-/penta-diagonal."""
+    from scipy.sparse import coo_matrix
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+
+    n = int(rowmap.max()) + 1
+    rr, cc = [], []
+    for kind, ids in zip(table.kinds, table.ids):
+        ids = [int(i) for i in ids]
+        if kind == "port" and mode == "norton":
+            ids = [ids[0], ids[2]]                      # only sig and the reference node stay coupled
+        rows = [int(rowmap[i]) for i in ids if rowmap[i] >= 0]
+        for a in rows:
+            for c in rows:
+                rr.append(a); cc.append(c)
+    if not rr:
+        return None
+    A = coo_matrix((np.ones(len(rr), dtype=np.int8), (rr, cc)), shape=(n, n)).tocsr()
+    coo = A.tocoo()
+    perm = np.asarray(reverse_cuthill_mckee(A, symmetric_mode=True), dtype=np.int64)   # new -> old
+    pos = np.empty(n, dtype=np.int64)
+    pos[perm] = np.arange(n)                            # old -> new
+    band = int(np.abs(pos[coo.row] - pos[coo.col]).max())
+    natural = int(np.abs(coo.row - coo.col).max())
+    if natural <= band:                                 # the netlist was already written as a chain
+        pos, band = np.arange(n, dtype=np.int64), natural
+    if band > BAND_MAX_HALF_WIDTH or 2 * (3 * band + 1) > n:
+        return None
+    new = rowmap.copy()
+    live = rowmap >= 0
+    new[live] = pos[rowmap[live]]
+    return new, band
+
+
+def compile_plan(table: StampTable, mode: str = "auto", pad_to: tuple[int, int] | None = None,
+                 order: str = "auto") -> DevicePlan:
     """`pad_to=(rows, rhs_columns)` lays the system out in a larger fixed shape: extra unknowns are
     identity rows (x = 0) and extra right-hand sides are zero columns, so the solution of the real
-    unknowns is unchanged while the register-resident kernel runs without bounds checks."""
+    unknowns is unchanged while the register-resident kernel runs without bounds checks.
+
+    `order`: "natural" keeps the reference's node numbering for the system rows; "rcm" applies a
+    bandwidth-reducing ordering when the netlist is narrow-banded (what the banded kernel needs);
+    "auto" does so for systems too large for the register-resident kernels."""
     if mode == "auto":
         mode = "norton" if norton_legal(table) else "full"
     if mode == "norton" and not norton_legal(table):
@@ -372,6 +418,14 @@ def compile_plan(table: StampTable, mode: str = "auto", pad_to: tuple[int, int] 
         keep = [i for i in range(1, NM) if i not in dropped]
         rowmap[keep] = np.arange(len(keep))
     n_real = int(rowmap.max()) + 1 if NM > 0 else 0
+    if order not in ("auto", "natural", "rcm"):
+        raise ValueError(order)
+    band = -1
+    if mode != "dump" and pad_to is None and (order == "rcm" or (order == "auto" and n_real >= BAND_MIN_ROWS)):
+        if not any(k in ("nport_s", "nport_y") for k in table.kinds):
+            res = _band_order(table, rowmap, mode)
+            if res is not None:
+                rowmap, band = res
     n, n_rhs = n_real, (0 if mode == "dump" else P)
     if pad_to is not None and mode != "dump":
         if pad_to[0] < n_real or pad_to[1] < P:
@@ -528,7 +582,7 @@ def compile_plan(table: StampTable, mode: str = "auto", pad_to: tuple[int, int] 
         fop_code=np.array(fcode, dtype=np.int32), fop_out=np.array(fout, dtype=np.int32),
         fop_arg=np.array(farg, dtype=np.float64),
         epi_simple=epi_simple, epi_port_of_row=epi_port_of_row, epi_scale=np.ascontiguousarray(epi_scale, dtype=np.float64),
-        n_real=n_real, max_nport=max([int(c[2]) for c in b.coops], default=0),
+        n_real=n_real, max_nport=max([int(c[2]) for c in b.coops], default=0), band=band,
     )
 
 

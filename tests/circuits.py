@@ -152,6 +152,37 @@ def build_c5(hv, nF: int = 1_000_000, K: int = 190):
     return m, np.linspace(0.5e9, 6e9, nF)
 
 
+def build_band_ladder(hv, K: int = 60, reach: int = 2, nports: int = 3, seed: int = 0, nF: int = 40):
+    """Chain of K+1 nodes whose elements couple node k with k+1..k+reach: the MNA matrix is banded with
+    half bandwidth `reach` (after the plan compiler's ordering), the shape the banded kernel serves."""
+    rng = np.random.default_rng(1000 + seed)
+    m = _model(hv)
+    chain = [m.node() for _ in range(K + 1)]
+    for t in [round(i * K / max(nports - 1, 1)) for i in range(nports)]:
+        m.new_port(float(rng.choice([25.0, 50.0, 75.0])), chain[t])
+    for k in range(K):
+        for d in range(1, reach + 1):
+            if k + d > K:
+                continue
+            kind = rng.integers(0, 4)
+            if d > 1 and rng.random() < 0.3:
+                continue
+            if kind == 0:
+                m.inductor(chain[k], chain[k + d], 10 ** rng.uniform(-9.3, -8.3))
+            elif kind == 1:
+                m.resistor(chain[k], chain[k + d], rng.uniform(5, 500))
+            elif kind == 2:
+                m.capacitor(chain[k], chain[k + d], 10 ** rng.uniform(-12.5, -11.5))
+            else:
+                m.transmissionline(chain[k], chain[k + d], rng.uniform(30, 90), rng.uniform(2, 4), rng.uniform(1e-3, 10e-3))
+    for k in range(K + 1):
+        if k % 2 == 0:
+            m.capacitor(chain[k], m.gnd, 10 ** rng.uniform(-13, -12))
+        if k % 7 == 0:
+            m.resistor(chain[k], m.gnd, rng.uniform(500, 5000))
+    return m, np.linspace(0.5e9, 6e9, nF)
+
+
 # ---------------------------------------------------------------- analytic known answers (SURVEY section 4)
 def build_divider(hv):
     """10 ohm series resistor between a 50 ohm and a 75 ohm port."""

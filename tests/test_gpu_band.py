@@ -1,0 +1,141 @@
+"""Kernel C (banded LU, one thread per point) against the dense kernels, the oracle and the golden
+ladder.  The banded path is chosen by the library when the RCM-ordered system is narrow-banded
+(heavi_b200/csrc/hvb_band.cu); HVB_NO_BAND=1 forces the dense block kernel for the same plan."""
+import os
+
+import numpy as np
+import pytest
+
+import circuits
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+TOL_REL, TOL_ABS = 1e-10, 1e-12
+
+
+def _compile(hv, m, band: bool, mode=None):
+    from heavi_b200.engine import CompiledNetwork
+    old = os.environ.get("HVB_NO_BAND")
+    os.environ["HVB_NO_BAND"] = "0" if band else "1"
+    try:
+        return CompiledNetwork(m, mode=mode)
+    finally:
+        if old is None:
+            os.environ.pop("HVB_NO_BAND", None)
+        else:
+            os.environ["HVB_NO_BAND"] = old
+
+
+def _close(a, b):
+    return np.all(np.abs(a - b) <= TOL_ABS + TOL_REL * np.maximum(np.abs(a), np.abs(b)))
+
+
+def test_c5_uses_banded_kernel_and_matches_golden():
+    import heavi_b200 as hv
+    m, _ = circuits.build_c5(hv, nF=10)
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "c5_ladder.npz"))
+    cn = _compile(hv, m, band=True)
+    ki = cn.handle.kernel_info()
+    assert ki["kernel_class"] == 2 and ki["group"] == 1 and cn.plan.band == 1
+    S = cn.run(g["f"])[0]
+    assert _close(S, g["S_ext"])                      # 80-bit adjudicator
+    dense = _compile(hv, m, band=False)
+    assert dense.handle.kernel_info()["kernel_class"] == 1
+    assert _close(S, dense.run(g["f"])[0])
+
+
+@pytest.mark.parametrize("reach,K,nports,mode", [(1, 40, 2, None), (2, 60, 3, None), (3, 64, 4, None), (4, 80, 3, None),
+                                                  (5, 90, 2, None), (7, 120, 5, None), (8, 150, 8, None),
+                                                  (2, 50, 3, "full"), (1, 33, 2, "full"), (4, 70, 16, None)])
+def test_banded_matches_dense_and_oracle(reach, K, nports, mode):
+    import heavi_b200 as hv
+    from oracle import mna_oracle as orc
+    m, f = circuits.build_band_ladder(hv, K=K, reach=reach, nports=nports, seed=reach * 100 + K)
+    cn = _compile(hv, m, band=True, mode=mode)
+    ki = cn.handle.kernel_info()
+    assert ki["kernel_class"] == 2, ki
+    assert cn.plan.band <= ki["group"]
+    S = cn.run(f)[0]
+    dense = _compile(hv, m, band=False, mode=mode)
+    assert dense.handle.kernel_info()["kernel_class"] == 1
+    Sd = dense.run(f)[0]
+    assert _close(S, Sd)
+    So = orc.run_sp(m.records(), m.n_nodes, len(m.sources), np.asarray(f, dtype=np.float64), method="lu_batched")
+    assert _close(S, So)
+
+
+def test_banded_many_points_are_consistent():
+    """More points than threads in flight for a small grid: every thread reuses its workspace."""
+    import heavi_b200 as hv
+    m, _ = circuits.build_band_ladder(hv, K=48, reach=2, nports=2, seed=7)
+    f = np.linspace(0.5e9, 6e9, 70_001)
+    cn = _compile(hv, m, band=True)
+    S = cn.run(f)[0]
+    idx = np.array([0, 1, 127, 128, 4095, 35_000, 69_999, 70_000])
+    S_few = cn.run(f[idx])[0]
+    assert np.array_equal(S[..., idx], S_few)
+    dense = _compile(hv, m, band=False)
+    assert _close(S[..., ::997], dense.run(f[::997])[0])
+
+
+def test_banded_monte_carlo_samples():
+    import heavi_b200 as hv
+    m = hv.Model()
+    mc = hv.MonteCarlo()
+    chain = [m.node() for _ in range(41)]
+    m.new_port(50, chain[0]); m.new_port(50, chain[40])
+    for k in range(40):
+        if k % 2:
+            m.inductor(chain[k], chain[k + 1], mc.gaussian(2e-9, 1e-10))
+        else:
+            m.transmissionline(chain[k], chain[k + 1], 50.0, 2.9, 4e-3)
+        m.capacitor(chain[k + 1], m.gnd, mc.gaussian(1e-12, 5e-14))
+    f = np.linspace(1e9, 3e9, 33)
+    np.random.seed(5)
+    values = mc.draw(24)
+    Sb = _compile(hv, m, band=True).run(f, mc._random_numbers, values)
+    Sd = _compile(hv, m, band=False).run(f, mc._random_numbers, values)
+    assert Sb.shape == (24, 2, 2, 33)
+    assert _close(Sb, Sd)
+    assert not np.array_equal(Sb[0], Sb[1])
+
+
+def test_banded_singular_point_is_flagged():
+    import heavi_b200 as hv
+    m = hv.Model()
+    chain = [m.node() for _ in range(40)]
+    m.new_port(50, chain[0]); m.new_port(50, chain[39])
+    for k in range(39):
+        if k != 20:                                   # node 20..39 side floats from the rest: still fine
+            m.resistor(chain[k], chain[k + 1], 10.0)
+    floating = m.node()                               # a node nothing else touches but a zero admittance pair
+    m.admittance(floating, chain[5], 0.0)
+    import warnings
+    cn = _compile(hv, m, band=True)
+    assert cn.handle.kernel_info()["kernel_class"] == 2
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        try:
+            cn.run(np.array([1e9, 2e9]))
+            flagged = any("singular" in str(x.message) for x in w)
+        except np.linalg.LinAlgError:
+            flagged = True
+    assert flagged
+
+
+@pytest.mark.parametrize("band", [True, False])
+def test_two_pipeline_slots_do_not_share_a_workspace(band):
+    """hvb_run_host alternates two streams; kernels B and C keep their matrices in a global-memory
+    workspace, so each stream needs its own or the tail of one tile corrupts the head of the next."""
+    import heavi_b200 as hv
+    m, _ = circuits.build_c5(hv, nF=10)
+    f = np.linspace(0.5e9, 6e9, 140_000)
+    cn = _compile(hv, m, band=band)
+    os.environ["HVB_CHUNK_MB"] = "1"
+    try:
+        S = cn.run(f)[0].copy()
+    finally:
+        os.environ.pop("HVB_CHUNK_MB")
+    idx = np.unique(np.concatenate([np.arange(0, 140_000, 1511), np.arange(65_400, 65_700), np.arange(69_900, 70_100)]))
+    assert np.array_equal(S[..., idx], cn.run(f[idx])[0])

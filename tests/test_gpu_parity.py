@@ -145,17 +145,23 @@ def test_config3_touchstone_large_sweep_properties():
     assert frac == 1.0 and ext < 5e-14
 
 
-def test_config5_ladder_block_kernel_properties():
+def test_config5_ladder_block_and_banded_kernel_properties():
     import circuits
     from oracle import mna_oracle as orc
     m, f = circuits.build_c5(hv, nF=2048)
-    cn = m._compiled()
-    assert cn.handle.kernel_info()["kernel_class"] == 1 and cn.plan.n_real == 191
-    S = m.run_sp(f)._S
-    assert np.max(np.abs(S - np.swapaxes(S, 0, 1))) < 1e-11
+    os.environ["HVB_NO_BAND"] = "1"                                               # dense block kernel
+    try:
+        dense = CompiledNetwork(m)
+    finally:
+        os.environ.pop("HVB_NO_BAND")
+    assert dense.handle.kernel_info()["kernel_class"] == 1 and dense.plan.n_real == 191
+    cn = m._compiled()                                                            # default: banded kernel
+    assert cn.handle.kernel_info()["kernel_class"] == 2 and cn.plan.band == 1
     sub = slice(0, None, 128)
     ref = orc.run_sp(m.records(), m.n_nodes, len(m.sources), f[sub], method="lu_batched")
-    assert np.max(np.abs(S[:, :, sub] - ref)) < 1e-12
+    for S in (dense.run(f)[0], m.run_sp(f)._S):
+        assert np.max(np.abs(S - np.swapaxes(S, 0, 1))) < 1e-11
+        assert np.max(np.abs(S[:, :, sub] - ref)) < 1e-12
 
 
 def test_chunking_and_sharding_are_bit_identical():
