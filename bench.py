@@ -75,8 +75,8 @@ def make_jobs(hv, workload: str, rank: int, world: int):
         desc = "configs[3]: Monte-Carlo Cauer band-pass, 1250 samples x 2001 freqs per GPU"
     elif workload == "c5":
         m, _ = circuits.build_c5(hv, nF=8)
-        jobs.append((m, slab(0.5e9, 6e9, int(os.environ.get("HVB_C5_POINTS", "32768"))), None, None))
-        desc = "configs[4]: ladder/TL network n=207, 8 ports, %s points per GPU" % os.environ.get("HVB_C5_POINTS", "32768")
+        jobs.append((m, slab(0.5e9, 6e9, int(os.environ.get("HVB_C5_POINTS", "1000000"))), None, None))
+        desc = "configs[4]: ladder/TL network n=207, 8 ports, %s points per GPU" % os.environ.get("HVB_C5_POINTS", "1000000")
     else:
         raise SystemExit("unknown workload " + workload)
     return jobs, desc

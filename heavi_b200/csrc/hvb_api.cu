@@ -55,7 +55,7 @@ struct hvb_plan {
     int device = 0;
     hvb_plan_desc d{};
     // device copies of the static plan arrays
-    DevBuf const_vals, ops, coops, cell_ptr, cell_ent, row_ptr, row_ent, fop_code, fop_out, fop_arg, epi_por, epi_scale, port_rows, port_zpref, spl_t, spl_c, spl_trace, spl_fill, spl_range;
+    DevBuf const_vals, ops, coops, cell_ptr, cell_ent, row_ptr, row_ent, fop_code, fop_out, fop_arg, epi_por, epi_scale, port_rows, port_zpref, spl_t, spl_c, spl_trace, spl_fill, spl_range, band_slots;
     // per-run parameter buffers (device) + pinned staging
     DevBuf consts, prefs;
     void* h_stage = nullptr; size_t h_stage_bytes = 0;
@@ -72,6 +72,7 @@ struct hvb_plan {
     int region_a = 0, region_b = 0;
     int band = -1;                                     // structural half bandwidth of the matrix block
     size_t work_words = 0;                             // kernel C: workspace words per thread
+    int band_nslots = 0, band_min_row = 0, band_fused = 0;
     const void* kernel = nullptr;
     int max_grid = 0;
     int64_t launches = 0;
@@ -180,6 +181,15 @@ static int select_kernel(hvb_plan* pl) {
         pl->threads = hvb_band_threads();
         pl->smem = 0;
         pl->work_words = hvb_band_words_per_thread(pl->NB, d.n, PP, d.n_dyn);
+        const char* nf = getenv("HVB_BAND_FUSED");
+        const int ppad = d.P <= 2 ? 2 : d.P <= 4 ? 4 : d.P <= 8 ? 8 : 16;
+        const void* fk = (PP == d.P && d.P <= 16 && !(nf && nf[0] == '0')) ? hvb_bandf_kernel_ptr(pl->NB, ppad) : nullptr;
+        if (fk) {                                            // window rows in registers (B <= 2)
+            pl->kernel = fk;
+            pl->band_fused = 1;
+            pl->PMAX = ppad;
+            pl->work_words = hvb_bandf_words_per_thread(pl->NB, d.n, d.P, pl->band_nslots, d.n_dyn);
+        }
         pl->region_a = std::max(d.n_dyn, 1);
         pl->region_b = 1;
     } else {
@@ -283,6 +293,20 @@ extern "C" int hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan**
                 if (d.cell_ptr[r * d.ncols + c + 1] > d.cell_ptr[r * d.ncols + c]) band = std::max(band, std::abs(r - c));
         pl->band = band;
     }
+    {   // rows of the solution the S epilogue reads (port nodes): slot table for the fused band kernel
+        std::vector<int32_t> slot((size_t)d.n, -1);
+        int ns = 0, minrow = d.n;
+        for (int i = 0; i < 3 * d.P; ++i) {
+            const int r = d.port_rows[i];
+            if (r >= 0 && r < d.n && slot[r] < 0) { slot[r] = ns++; minrow = std::min(minrow, r); }
+        }
+        pl->band_nslots = std::max(ns, 1);
+        pl->band_min_row = ns ? minrow : d.n;
+        if (upload(pl->band_slots, slot.data(), slot.size() * 4) != cudaSuccess) {
+            hvb_plan_destroy(pl);
+            return fail(HVB_ERR_CUDA, "plan upload failed");
+        }
+    }
     // the descriptor's host pointers are not kept
     pl->d.const_vals = nullptr; pl->d.ops = nullptr; pl->d.coops = nullptr; pl->d.cell_ptr = nullptr; pl->d.cell_ent = nullptr; pl->d.row_ptr = nullptr; pl->d.row_ent = nullptr; pl->d.fop_code = nullptr; pl->d.fop_out = nullptr; pl->d.fop_arg = nullptr; pl->d.epi_port_of_row = nullptr; pl->d.epi_scale = nullptr;
     pl->d.port_rows = nullptr; pl->d.port_zpref = nullptr; pl->d.spl_t = nullptr; pl->d.spl_c = nullptr; pl->d.spl_trace = nullptr;
@@ -299,7 +323,7 @@ extern "C" void hvb_plan_destroy(hvb_plan* pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
     DevBuf* all[] = {&pl->const_vals, &pl->ops, &pl->coops, &pl->cell_ptr, &pl->cell_ent, &pl->row_ptr, &pl->row_ent, &pl->fop_code, &pl->fop_out, &pl->fop_arg, &pl->epi_por, &pl->epi_scale, &pl->port_rows, &pl->port_zpref,
-                     &pl->spl_t, &pl->spl_c, &pl->spl_trace, &pl->spl_fill, &pl->spl_range, &pl->consts, &pl->prefs,
+                     &pl->spl_t, &pl->spl_c, &pl->spl_trace, &pl->spl_fill, &pl->spl_range, &pl->band_slots, &pl->consts, &pl->prefs,
                      &pl->f, &pl->samples, &pl->tables, &pl->S[0], &pl->S[1], &pl->status, &pl->work[0], &pl->work[1], &pl->dump, &pl->stats, &pl->inbuf};
     for (DevBuf* b : all) b->release();
     if (pl->h_stage) cudaFreeHost(pl->h_stage);
@@ -344,6 +368,8 @@ static HvbDev make_dev(const hvb_plan* pl) {
     D.pv.spl_fill = (const cplx*)pl->spl_fill.p;
     D.pv.spl_range = (const double2*)pl->spl_range.p;
     D.W = (cplx*)pl->work[0].p;
+    D.band_slot_of_row = (const int*)pl->band_slots.p;
+    D.band_nslots = pl->band_nslots; D.band_min_row = pl->band_min_row;
     return D;
 }
 

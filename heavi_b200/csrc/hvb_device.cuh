@@ -54,7 +54,9 @@ struct HvbDev {
     const int* port_rows;
     const int* port_zpref;
     cplx* S;
-    cplx* W;                                // dense dump / block-kernel workspace
+    cplx* W;                                // dense dump / block-kernel / band-kernel workspace
+    const int* band_slot_of_row;            // kernel C (fused): solution rows the S epilogue reads -> slot
+    int band_nslots, band_min_row;
     int* status;
 };
 
