@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <functional>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -55,7 +56,7 @@ struct hvb_plan {
     int device = 0;
     hvb_plan_desc d{};
     // device copies of the static plan arrays
-    DevBuf const_vals, ops, coops, cell_ptr, cell_ent, row_ptr, row_ent, fop_code, fop_out, fop_arg, epi_por, epi_scale, port_rows, port_zpref, spl_t, spl_c, spl_trace, spl_fill, spl_range, band_slots;
+    DevBuf const_vals, ops, coops, cell_ptr, cell_ent, row_ptr, row_ent, fop_code, fop_out, fop_arg, epi_por, epi_scale, port_rows, port_zpref, spl_t, spl_c, spl_trace, spl_fill, spl_range, band_slots, band_sched_ptr, band_sched_op, band_fslot, band_oslot, band_ent, band_act;
     // per-run parameter buffers (device) + pinned staging
     DevBuf consts, prefs;
     void* h_stage = nullptr; size_t h_stage_bytes = 0;
@@ -73,6 +74,9 @@ struct hvb_plan {
     int band = -1;                                     // structural half bandwidth of the matrix block
     size_t work_words = 0;                             // kernel C: workspace words per thread
     int band_nslots = 0, band_min_row = 0, band_fused = 0;
+    int band_value_slots = 0, band_nsm = 0;            // value slots the schedule needs / held in shared memory
+    std::vector<int> rhs_minrow;                       // first row with an entry in each right-hand-side column
+    long long band_rec_words = 0;
     const void* kernel = nullptr;
     int max_grid = 0;
     int64_t launches = 0;
@@ -114,6 +118,76 @@ extern "C" int hvb_warp_shape(int32_t n, int32_t P, int32_t max_nport, int32_t* 
         if (*n_pad == 0 || cost < best) { best = cost; *n_pad = N; *p_pad = Pp; }
     }
     return HVB_OK;
+}
+
+// Kernel C's value schedule: evaluate each value op right before the first system row that sums
+// one of its outputs, recycle the outputs' slots after the last such row (linear scan over rows, the
+// lowest free slot first so that the busiest slots are the ones kept in shared memory).
+static cudaError_t build_band_schedule(hvb_plan* pl, const hvb_plan_desc& d) {
+    const int n = d.n, nvc = d.n_const_vals, ndyn = d.n_dyn;
+    std::vector<int> first(ndyn, n), last(ndyn, -1);
+    for (int r = 0; r < n; ++r)
+        for (int e = d.row_ptr[r]; e < d.row_ptr[r + 1]; ++e) {
+            const int vid = (d.row_ent[e] >> 1) & 0x7FFFF;
+            if (vid >= nvc) { first[vid - nvc] = std::min(first[vid - nvc], r); last[vid - nvc] = std::max(last[vid - nvc], r); }
+        }
+    struct Op { int ref, out, cnt; };
+    std::vector<std::vector<Op>> by_row(n);
+    for (int o = 0; o < d.n_fast_ops; ++o) {
+        const int v = d.fop_out[o];
+        if (last[v] >= 0) by_row[first[v]].push_back({o, v, 1});
+    }
+    for (int o = 0; o < d.n_ops; ++o) {
+        const int32_t* op = d.ops + (size_t)o * HVB_OP_WORDS;
+        const int out = op[1] - nvc, cnt = op[0] == OP_TLINE ? 9 : 1;
+        int fr = n;
+        for (int e = 0; e < cnt; ++e) if (last[out + e] >= 0) fr = std::min(fr, first[out + e]);
+        if (fr < n) by_row[fr].push_back({~o, out, cnt});
+    }
+    std::vector<int> slot(ndyn, -1), sched_ptr(n + 1, 0), sched_op, fslot(std::max(d.n_fast_ops, 1), 0), oslot((size_t)std::max(d.n_ops, 1) * 9, -1);
+    std::vector<std::vector<int>> expire(n + 1);
+    std::vector<int> free_slots;                           // min-heap
+    int nslots = 0;
+    for (int r = 0; r < n; ++r) {
+        for (int v : expire[r]) { free_slots.push_back(slot[v]); std::push_heap(free_slots.begin(), free_slots.end(), std::greater<int>()); }
+        for (const Op& op : by_row[r]) {
+            sched_op.push_back(op.ref);
+            for (int e = 0; e < op.cnt; ++e) {
+                const int v = op.out + e;
+                if (last[v] < 0) continue;
+                int sl;
+                if (!free_slots.empty()) { std::pop_heap(free_slots.begin(), free_slots.end(), std::greater<int>()); sl = free_slots.back(); free_slots.pop_back(); }
+                else sl = nslots++;
+                slot[v] = sl;
+                expire[last[v] + 1].push_back(v);
+                if (op.ref >= 0) fslot[op.ref] = sl; else oslot[(size_t)(~op.ref) * 9 + e] = sl;
+            }
+        }
+        sched_ptr[r + 1] = (int)sched_op.size();
+    }
+    pl->rhs_minrow.assign((size_t)std::max(d.ncols - d.n, 1), n);
+    for (int r = n - 1; r >= 0; --r)
+        for (int e = d.row_ptr[r]; e < d.row_ptr[r + 1]; ++e) {
+            const int col = (int)(((uint32_t)d.row_ent[e] >> 20) & 0x7FFu);
+            if (col >= n) pl->rhs_minrow[col - n] = r;
+        }
+    std::vector<int32_t> ent((size_t)std::max(d.n_row_ent, 1), 0);
+    for (int e = 0; e < d.n_row_ent; ++e) {
+        const int32_t w = d.row_ent[e];
+        const int vid = (w >> 1) & 0x7FFFF;
+        if (vid < nvc) { ent[e] = w; continue; }
+        const int nv = nvc + slot[vid - nvc];
+        if (nv >= (1 << 19)) return cudaErrorInvalidValue;
+        ent[e] = (int32_t)(((uint32_t)w & ~(0x7FFFFu << 1)) | ((uint32_t)nv << 1));
+    }
+    if (sched_op.empty()) sched_op.push_back(0);
+    pl->band_value_slots = nslots;
+    cudaError_t e = upload(pl->band_sched_ptr, sched_ptr.data(), sched_ptr.size() * 4);
+    if (e == cudaSuccess) e = upload(pl->band_sched_op, sched_op.data(), sched_op.size() * 4);
+    if (e == cudaSuccess) e = upload(pl->band_fslot, fslot.data(), fslot.size() * 4);
+    if (e == cudaSuccess) e = upload(pl->band_oslot, oslot.data(), oslot.size() * 4);
+    if (e == cudaSuccess) e = upload(pl->band_ent, ent.data(), ent.size() * 4);
+    return e;
 }
 
 // kernel B's per-CTA workspaces; one set per pipeline slot because the two streams of hvb_run_host
@@ -182,16 +256,33 @@ static int select_kernel(hvb_plan* pl) {
         pl->smem = 0;
         pl->work_words = hvb_band_words_per_thread(pl->NB, d.n, PP, d.n_dyn);
         const char* nf = getenv("HVB_BAND_FUSED");
-        const int ppad = d.P <= 2 ? 2 : d.P <= 4 ? 4 : d.P <= 8 ? 8 : 16;
-        const void* fk = (PP == d.P && d.P <= 16 && !(nf && nf[0] == '0')) ? hvb_bandf_kernel_ptr(pl->NB, ppad) : nullptr;
-        if (fk) {                                            // window rows in registers (B <= 2)
-            pl->kernel = fk;
-            pl->band_fused = 1;
-            pl->PMAX = ppad;
-            pl->work_words = hvb_bandf_words_per_thread(pl->NB, d.n, d.P, pl->band_nslots, d.n_dyn);
+        const void* fk = (PP == d.P && !(nf && nf[0] == '0')) ? hvb_bandf_kernel_ptr(pl->NB) : nullptr;
+        if (fk) {
+            // shared memory per thread: the right-hand-side ring + as many value slots as fit next to it
+            const int want_ctas = pl->NB == 1 ? 5 : pl->NB == 2 ? 4 : pl->NB == 3 ? 3 : 2;
+            const size_t per_cta = prop.sharedMemPerMultiprocessor / want_ctas - 1024;
+            const size_t per_word = (size_t)pl->threads * sizeof(cplx);
+            const int ring = hvb_bandf_ring_words(pl->NB, d.P);
+            if ((size_t)(ring + 1) * per_word <= per_cta) {
+                const int cap = (int)(per_cta / per_word) - ring;
+                pl->kernel = fk;
+                pl->band_fused = 1;
+                pl->band_nsm = std::min(pl->band_value_slots, cap);
+                pl->smem = (size_t)(ring + std::max(pl->band_nsm, 1)) * per_word;
+                // right-hand-side columns that can be non-zero in rows <= k+B, and the record stream they give
+                std::vector<int32_t> act((size_t)d.n, 0);
+                long long words = 0;
+                for (int k = 0; k < d.n; ++k) {
+                    int a = 0;
+                    for (int i = 0; i < d.P; ++i) if (pl->rhs_minrow[i] <= k + pl->NB) a = i + 1;
+                    act[k] = a;
+                    words += 2 * pl->NB + 1 + a;
+                }
+                pl->band_rec_words = words;
+                CU(upload(pl->band_act, act.data(), act.size() * 4));
+                pl->work_words = (size_t)words + (size_t)pl->band_nslots * d.P + (size_t)std::max(pl->band_value_slots - pl->band_nsm, 1);
+            }
         }
-        pl->region_a = std::max(d.n_dyn, 1);
-        pl->region_b = 1;
     } else {
         pl->kclass = 1;
         const char* nbs = getenv("HVB_BLOCK_NB");
@@ -216,7 +307,7 @@ static int select_kernel(hvb_plan* pl) {
                     (size_t)prop.sharedMemPerBlockOptin);
     CU(cudaFuncSetAttribute(pl->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
     CU(cudaFuncSetAttribute(pl->kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                            pl->kclass == 2 ? (int)cudaSharedmemCarveoutMaxL1 : (int)cudaSharedmemCarveoutMaxShared));
+                            (pl->kclass == 2 && !pl->band_fused) ? (int)cudaSharedmemCarveoutMaxL1 : (int)cudaSharedmemCarveoutMaxShared));
     cudaFuncAttributes fa;
     CU(cudaFuncGetAttributes(&fa, pl->kernel));
     pl->regs = fa.numRegs;
@@ -302,7 +393,8 @@ extern "C" int hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan**
         }
         pl->band_nslots = std::max(ns, 1);
         pl->band_min_row = ns ? minrow : d.n;
-        if (upload(pl->band_slots, slot.data(), slot.size() * 4) != cudaSuccess) {
+        if (upload(pl->band_slots, slot.data(), slot.size() * 4) != cudaSuccess ||
+            (d.n_coops == 0 && build_band_schedule(pl, d) != cudaSuccess)) {
             hvb_plan_destroy(pl);
             return fail(HVB_ERR_CUDA, "plan upload failed");
         }
@@ -323,7 +415,7 @@ extern "C" void hvb_plan_destroy(hvb_plan* pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
     DevBuf* all[] = {&pl->const_vals, &pl->ops, &pl->coops, &pl->cell_ptr, &pl->cell_ent, &pl->row_ptr, &pl->row_ent, &pl->fop_code, &pl->fop_out, &pl->fop_arg, &pl->epi_por, &pl->epi_scale, &pl->port_rows, &pl->port_zpref,
-                     &pl->spl_t, &pl->spl_c, &pl->spl_trace, &pl->spl_fill, &pl->spl_range, &pl->band_slots, &pl->consts, &pl->prefs,
+                     &pl->spl_t, &pl->spl_c, &pl->spl_trace, &pl->spl_fill, &pl->spl_range, &pl->band_slots, &pl->band_sched_ptr, &pl->band_sched_op, &pl->band_fslot, &pl->band_oslot, &pl->band_ent, &pl->band_act, &pl->consts, &pl->prefs,
                      &pl->f, &pl->samples, &pl->tables, &pl->S[0], &pl->S[1], &pl->status, &pl->work[0], &pl->work[1], &pl->dump, &pl->stats, &pl->inbuf};
     for (DevBuf* b : all) b->release();
     if (pl->h_stage) cudaFreeHost(pl->h_stage);
@@ -370,6 +462,18 @@ static HvbDev make_dev(const hvb_plan* pl) {
     D.W = (cplx*)pl->work[0].p;
     D.band_slot_of_row = (const int*)pl->band_slots.p;
     D.band_nslots = pl->band_nslots; D.band_min_row = pl->band_min_row;
+    {
+        const char* b = getenv("HVB_BAND_PFB");
+        D.band_pfb = b ? atoi(b) : 2;
+    }
+    D.band_nsm = pl->band_nsm;
+    D.band_sched_ptr = (const int*)pl->band_sched_ptr.p;
+    D.band_sched_op = (const int*)pl->band_sched_op.p;
+    D.band_fslot = (const int*)pl->band_fslot.p;
+    D.band_oslot = (const int*)pl->band_oslot.p;
+    D.band_ent = (const int*)pl->band_ent.p;
+    D.band_act = (const int*)pl->band_act.p;
+    D.band_rec_words = pl->band_rec_words;
     return D;
 }
 

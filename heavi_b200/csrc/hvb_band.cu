@@ -19,12 +19,6 @@
 #include "hvb_kernels.h"
 
 #define HVB_BAND_THREADS 128
-#ifndef HVB_BAND_PREFETCH
-#define HVB_BAND_PREFETCH 2            // rows of values prefetched ahead of the elimination front
-#endif
-#ifndef HVB_BAND_PREFETCH_BACK
-#define HVB_BAND_PREFETCH_BACK 6       // pivot-row records prefetched (to L2) ahead of the back substitution
-#endif
 
 struct BandView {
     cplx* __restrict__ base;      // W + t
@@ -193,67 +187,108 @@ __global__ void __launch_bounds__(HVB_BAND_THREADS) hvb_band_kernel(const HvbDev
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fused variant for B <= 2: the B+1 rows that are live at elimination step k (columns k .. k+2B and
-// the right-hand sides) stay in REGISTERS.  Row k+B is assembled straight into the window when step
-// k starts, every finished pivot row is written to global memory exactly once ([inv(u_kk), u_k,k+1..,
-// y_k]), and the back substitution reads it exactly once while the last 2B solution rows slide
-// through registers; only the rows the S epilogue needs (port nodes) are written back.  Traffic per
-// point drops from ~4 passes over the band to one write + one read.
+// Fused variant (B <= 4): nothing but finished pivot rows ever reaches global memory.
+//   * the matrix part of the B+1 rows live at elimination step k (columns k .. k+2B) stays in
+//     REGISTERS; their right-hand sides sit in a shared-memory ring (row exchanges and the slide of
+//     the window only permute ring indices);
+//   * row k+B is assembled straight into the window when step k starts, from per-point values that
+//     are evaluated just in time into a small pool of shared-memory slots (see BandVals);
+//   * every finished pivot row is appended once to a per-thread record stream
+//     [inv(u_kk), u_k,k+1 .. u_k,k+2B, y_k,0 .. y_k,act(k)-1] -- act(k) = right-hand-side columns that
+//     can be non-zero in rows <= k+B, a prefix because a port's excitation enters at its own row --
+//     and read once, back to front, by the substitution, whose last 2B solution rows live in the
+//     same shared-memory ring; only the rows the S epilogue needs (port nodes) are kept.
+// HBM traffic per point: one write + one read of n*(2B+1+<act>) complex words.
 // ------------------------------------------------------------------------------------------------
-template <int B, int PP>
-struct BandRow {
-    cplx a[2 * B + 1];
-    cplx y[PP];
+struct BandVals {
+    cplx* sm;
+    cplx* spill;
+    long long T;
+    int nsm;
+    __device__ __forceinline__ cplx load(int slot) const {
+        return slot < nsm ? sm[slot * HVB_BAND_THREADS] : spill[(long long)(slot - nsm) * T];
+    }
+    __device__ __forceinline__ void store(int slot, cplx v) const {
+        if (slot < nsm) sm[slot * HVB_BAND_THREADS] = v; else spill[(long long)(slot - nsm) * T] = v;
+    }
 };
 
-// pull the per-point values row r sums into L1 ahead of its assembly: the walker below consumes them
-// one dependent load at a time, which would otherwise cost one DRAM round trip per entry
-__device__ __forceinline__ void band_prefetch_row(const HvbDev& D, int r, const cplx* __restrict__ Vt, long long T) {
-    const int lo = __ldg(D.row_ptr + r), hi = __ldg(D.row_ptr + r + 1);
-    for (int e = lo; e < hi; ++e) {
-        const int vid = (__ldg(D.row_ent + e) >> 1) & 0x7FFFF;
-        if (vid >= D.nvc) asm volatile("prefetch.global.L1 [%0];" ::"l"(Vt + (long long)(vid - D.nvc) * T));
+// evaluate the value ops scheduled before row r (hvb_api.cu: build_band_schedule)
+__device__ __forceinline__ void band_run_schedule(const HvbDev& D, int r, double f, long long fi,
+                                                  const double* __restrict__ srow, const BandVals& vals) {
+    const int lo = __ldg(D.band_sched_ptr + r), hi = __ldg(D.band_sched_ptr + r + 1);
+    const double w = __dmul_rn(HVB_TWOPI, f);
+    for (int i = lo; i < hi; ++i) {
+        const int ref = __ldg(D.band_sched_op + i);
+        if (ref >= 0) {                                     // fast op (same arithmetic as eval_fast_ops)
+            const int code = __ldg(D.fop_code + ref);
+            double p = __ldg(D.fop_arg + ref);
+            if (code & 4) p = srow[(int)p];
+            const double tt = (code & 2) ? __dmul_rn(w, p) : p;
+            const double v = (code & 1) ? 1.0 / tt : tt;
+            const bool imag = (code & 2) != 0;
+            vals.store(__ldg(D.band_fslot + ref), cmk(imag ? 0.0 : v, imag ? ((code & 1) ? -v : v) : 0.0));
+        } else {
+            const int o = ~ref;
+            const int* __restrict__ op = D.ops + o * HVB_OP_WORDS;
+            const int out = __ldg(op + 1) - D.nvc;
+            cplx tmp[9];
+            eval_simple_op(D, op, f, fi, srow, tmp - out);
+            const int cnt = __ldg(op) == OP_TLINE ? 9 : 1;
+            for (int e = 0; e < cnt; ++e) {
+                const int sl = __ldg(D.band_oslot + o * 9 + e);
+                if (sl >= 0) vals.store(sl, tmp[e]);
+            }
+        }
     }
 }
 
-// assemble system row r into a window row whose first column is k0 (row entries are sorted by column)
-template <int B, int PP>
-__device__ __forceinline__ void band_assemble_row(const HvbDev& D, int r, int k0, const cplx* __restrict__ Vt, long long T,
-                                                  BandRow<B, PP>& row) {
+// Assemble system row r: matrix cells (columns k0 .. k0+2B) into registers a[], right-hand-side cells
+// into the shared-memory ring row yr[] (element i at yr[i*THREADS]).  D.band_ent is row_ent, sorted
+// by column, with per-point value ids replaced by nvc + slot.
+template <int B>
+__device__ __forceinline__ void band_assemble_row(const HvbDev& D, int r, int k0, const BandVals& vals,
+                                                  cplx (&a)[2 * B + 1], cplx* __restrict__ yr) {
     int e = __ldg(D.row_ptr + r);
     const int hi = __ldg(D.row_ptr + r + 1);
-    int word = e < hi ? __ldg(D.row_ent + e) : 0;
+    int word = e < hi ? __ldg(D.band_ent + e) : 0;
     int ecol = e < hi ? (int)(((unsigned)word >> 20) & 0x7FFu) : -1;
-    auto cell = [&](int col) {
-        cplx acc = cmk(0.0, 0.0);
-        while (ecol == col) {
-            const int vid = (word >> 1) & 0x7FFFF;
-            const cplx v = vid < D.nvc ? D.const_vals[vid] : Vt[(long long)(vid - D.nvc) * T];
-            if (word & 1) { acc.x -= v.x; acc.y -= v.y; } else { acc.x += v.x; acc.y += v.y; }
-            ++e;
-            word = e < hi ? __ldg(D.row_ent + e) : 0;
-            ecol = e < hi ? (int)(((unsigned)word >> 20) & 0x7FFu) : -1;
-        }
-        return acc;
+    auto value = [&]() {
+        const int vid = (word >> 1) & 0x7FFFF;
+        cplx v = vid < D.nvc ? D.const_vals[vid] : vals.load(vid - D.nvc);
+        if (word & 1) v = cneg(v);
+        ++e;
+        word = e < hi ? __ldg(D.band_ent + e) : 0;
+        ecol = e < hi ? (int)(((unsigned)word >> 20) & 0x7FFu) : -1;
+        return v;
     };
 #pragma unroll
-    for (int c = 0; c <= 2 * B; ++c) row.a[c] = cell(k0 + c < D.n ? k0 + c : -2);
-#pragma unroll
-    for (int i = 0; i < PP; ++i) row.y[i] = cell(i < D.P ? D.n + i : -2);
+    for (int c = 0; c <= 2 * B; ++c) {
+        const int col = k0 + c < D.n ? k0 + c : -2;
+        cplx acc = cmk(0.0, 0.0);
+        while (ecol == col) acc = cadd(acc, value());
+        a[c] = acc;
+    }
+    for (int i = 0; i < D.P; ++i) yr[i * HVB_BAND_THREADS] = cmk(0.0, 0.0);   // all of it: act(k) grows with k
+    while (e < hi) {                                        // what is left are right-hand-side cells (col >= n)
+        const int i = ecol - D.n;
+        const cplx v = value();
+        yr[i * HVB_BAND_THREADS] = cadd(yr[i * HVB_BAND_THREADS], v);
+    }
 }
 
-template <int B, int PP>
-__global__ void __launch_bounds__(HVB_BAND_THREADS) hvb_bandf_kernel(const HvbDev D) {
-    constexpr int WD = 2 * B + 1;
+template <int B>
+__global__ void __launch_bounds__(HVB_BAND_THREADS, B == 1 ? 5 : B == 2 ? 4 : B == 3 ? 3 : 2) hvb_bandf_kernel(const HvbDev D) {
+    constexpr int WD = 2 * B + 1, NR = B + 1, NX = 2 * B, NRING = NR > NX ? NR : NX;
     const int n = D.n, P = D.P;
     const long long T = (long long)gridDim.x * blockDim.x;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    // finished pivot rows are a sequential stream of records [inv(u_kk), u_k,k+1 .. u_k,k+2B, y_k0 .. y_k,P-1]:
-    // written front to back by the elimination, read back to front by the substitution
-    const int RS = WD + P;
-    cplx* __restrict__ Rt = D.W + t;                                   // element e of record k at Rt[(k*RS + e)*T]
-    cplx* __restrict__ Xs = Rt + (long long)n * RS * T;               // x(slot, r) of the rows the epilogue reads
-    cplx* __restrict__ Vt = Xs + (long long)D.band_nslots * P * T;    // values
+    cplx* __restrict__ Rt = D.W + t;                                   // record stream, element e at Rt[e*T]
+    cplx* __restrict__ Xs = Rt + (long long)D.band_rec_words * T;     // x(slot, r) of the rows the epilogue reads
+    extern __shared__ __align__(16) unsigned char hvb_band_smem[];
+    cplx* __restrict__ ring = reinterpret_cast<cplx*>(hvb_band_smem) + threadIdx.x;   // ring row i, column r: ring[(i*P + r)*THREADS]
+    const BandVals vals{ring + NRING * P * HVB_BAND_THREADS, Xs + (long long)D.band_nslots * P * T, T, D.band_nsm};
+    const int ring_row = P * HVB_BAND_THREADS;
     const long long total = D.nS * D.nF;
     unsigned bad = 0;
 
@@ -262,58 +297,43 @@ __global__ void __launch_bounds__(HVB_BAND_THREADS) hvb_bandf_kernel(const HvbDe
         const double f = __ldg(D.f + fi);
         const double* __restrict__ srow = D.samples + s * D.nR;
 
-        // ---- value program ----------------------------------------------------------------------
+        // ---- elimination ----------------------------------------------------------------------------
+        cplx A[NR][WD];
+        int yrow[NR];                                       // ring row holding the right-hand sides of window row i
+#pragma unroll
+        for (int i = 0; i < NR; ++i) yrow[i] = i;
         {
-            const double w = __dmul_rn(HVB_TWOPI, f);
-            for (int o = 0; o < D.nfast; ++o) {
-                const int code = __ldg(D.fop_code + o);
-                double p = __ldg(D.fop_arg + o);
-                if (code & 4) p = srow[(int)p];
-                const double tt = (code & 2) ? __dmul_rn(w, p) : p;
-                const double v = (code & 1) ? 1.0 / tt : tt;
-                const bool imag = (code & 2) != 0;
-                Vt[(long long)__ldg(D.fop_out + o) * T] = cmk(imag ? 0.0 : v, imag ? ((code & 1) ? -v : v) : 0.0);
-            }
-            for (int o = 0; o < D.nops; ++o) {
-                const int* __restrict__ op = D.ops + o * HVB_OP_WORDS;
-                const int out = __ldg(op + 1) - D.nvc;
-                cplx tmp[9];
-                eval_simple_op(D, op, f, fi, srow, tmp - out);
-                const int cnt = __ldg(op) == OP_TLINE ? 9 : 1;
-                for (int e = 0; e < cnt; ++e) Vt[(long long)(out + e) * T] = tmp[e];
-            }
-        }
-
-        // ---- elimination: window rows k .. k+B in registers --------------------------------------
-        BandRow<B, PP> R[B + 1];
 #pragma unroll
-        for (int i = 0; i < B; ++i) {
-            if (i < n) band_assemble_row<B, PP>(D, i, 0, Vt, T, R[i]);
-            else {
+            for (int i = 0; i < B; ++i) {
+                if (i < n) {
+                    band_run_schedule(D, i, f, fi, srow, vals);
+                    band_assemble_row<B>(D, i, 0, vals, A[i], ring + yrow[i] * ring_row);
+                } else {
 #pragma unroll
-                for (int c = 0; c < WD; ++c) R[i].a[c] = cmk(0.0, 0.0);
-#pragma unroll
-                for (int r = 0; r < PP; ++r) R[i].y[r] = cmk(0.0, 0.0);
+                    for (int c = 0; c < WD; ++c) A[i][c] = cmk(0.0, 0.0);
+                    for (int r = 0; r < P; ++r) ring[yrow[i] * ring_row + r * HVB_BAND_THREADS] = cmk(0.0, 0.0);
+                }
             }
         }
         double pmin = 1e300, pmax = 0.0;
         cplx* __restrict__ wp = Rt;
-        for (int r = B; r < B + HVB_BAND_PREFETCH && r < n; ++r) band_prefetch_row(D, r, Vt, T);
         for (int k = 0; k < n; ++k) {
-            if (k + B + HVB_BAND_PREFETCH < n) band_prefetch_row(D, k + B + HVB_BAND_PREFETCH, Vt, T);
-            if (k + B < n) band_assemble_row<B, PP>(D, k + B, k, Vt, T, R[B]);
-            else {
+            const int na = __ldg(D.band_act + k);
+            cplx* __restrict__ ynew = ring + yrow[B] * ring_row;
+            if (k + B < n) {
+                band_run_schedule(D, k + B, f, fi, srow, vals);
+                band_assemble_row<B>(D, k + B, k, vals, A[B], ynew);
+            } else {
 #pragma unroll
-                for (int c = 0; c < WD; ++c) R[B].a[c] = cmk(0.0, 0.0);
-#pragma unroll
-                for (int r = 0; r < PP; ++r) R[B].y[r] = cmk(0.0, 0.0);
+                for (int c = 0; c < WD; ++c) A[B][c] = cmk(0.0, 0.0);
+                for (int r = 0; r < P; ++r) ynew[r * HVB_BAND_THREADS] = cmk(0.0, 0.0);
             }
             int p = 0;
-            double best = fabs(R[0].a[0].x) + fabs(R[0].a[0].y);
+            double best = fabs(A[0][0].x) + fabs(A[0][0].y);
             if (!(best >= 0.0)) best = -1.0;                 // NaN never wins
 #pragma unroll
             for (int i = 1; i <= B; ++i) {
-                const double m = fabs(R[i].a[0].x) + fabs(R[i].a[0].y);
+                const double m = fabs(A[i][0].x) + fabs(A[i][0].y);
                 if (m > best) { best = m; p = i; }
             }
             pmin = fmin(pmin, best);
@@ -322,76 +342,85 @@ __global__ void __launch_bounds__(HVB_BAND_THREADS) hvb_bandf_kernel(const HvbDe
             for (int i = 1; i <= B; ++i) {
                 if (p == i) {
 #pragma unroll
-                    for (int c = 0; c < WD; ++c) { const cplx x = R[0].a[c]; R[0].a[c] = R[i].a[c]; R[i].a[c] = x; }
-#pragma unroll
-                    for (int r = 0; r < PP; ++r) { const cplx x = R[0].y[r]; R[0].y[r] = R[i].y[r]; R[i].y[r] = x; }
+                    for (int c = 0; c < WD; ++c) { const cplx x = A[0][c]; A[0][c] = A[i][c]; A[i][c] = x; }
+                    const int x = yrow[0]; yrow[0] = yrow[i]; yrow[i] = x;
                 }
             }
-            const cplx inv = crecip_fast(R[0].a[0]);
+            const cplx inv = crecip_fast(A[0][0]);
+            const cplx* __restrict__ y0 = ring + yrow[0] * ring_row;
             *wp = inv; wp += T;
 #pragma unroll
-            for (int c = 1; c < WD; ++c) { *wp = R[0].a[c]; wp += T; }
-#pragma unroll
-            for (int r = 0; r < PP; ++r) if (r < P) { *wp = R[0].y[r]; wp += T; }
-#pragma unroll
-            for (int i = 1; i <= B; ++i) {
-                const cplx l = cmul(R[i].a[0], inv);
-#pragma unroll
-                for (int c = 1; c < WD; ++c) cfnma(R[i].a[c], l, R[0].a[c]);
-#pragma unroll
-                for (int r = 0; r < PP; ++r) cfnma(R[i].y[r], l, R[0].y[r]);
-            }
-            // slide: row i becomes row i-1, column c becomes column c-1
+            for (int c = 1; c < WD; ++c) { *wp = A[0][c]; wp += T; }
+            for (int r = 0; r < na; ++r) { *wp = y0[r * HVB_BAND_THREADS]; wp += T; }
 #pragma unroll
             for (int i = 1; i <= B; ++i) {
+                const cplx l = cmul(A[i][0], inv);
 #pragma unroll
-                for (int c = 1; c < WD; ++c) R[i - 1].a[c - 1] = R[i].a[c];
-                R[i - 1].a[WD - 1] = cmk(0.0, 0.0);
-#pragma unroll
-                for (int r = 0; r < PP; ++r) R[i - 1].y[r] = R[i].y[r];
+                for (int c = 1; c < WD; ++c) cfnma(A[i][c], l, A[0][c]);
+                cplx* __restrict__ yi = ring + yrow[i] * ring_row;
+#pragma unroll 4
+                for (int r = 0; r < na; ++r) {
+                    cplx v = yi[r * HVB_BAND_THREADS];
+                    cfnma(v, l, y0[r * HVB_BAND_THREADS]);
+                    yi[r * HVB_BAND_THREADS] = v;
+                }
             }
+            // slide: row i becomes row i-1, column c becomes column c-1; the pivot row's ring row is recycled
+            const int freed = yrow[0];
+#pragma unroll
+            for (int i = 1; i <= B; ++i) {
+#pragma unroll
+                for (int c = 1; c < WD; ++c) A[i - 1][c - 1] = A[i][c];
+                A[i - 1][WD - 1] = cmk(0.0, 0.0);
+                yrow[i - 1] = yrow[i];
+            }
+            yrow[B] = freed;
         }
         if (!(pmin >= 2.2250738585072014e-308)) bad |= HVB_STATUS_ZERO_PIVOT_BIT;
         if (!(pmax <= 1.7976931348623157e308)) bad |= HVB_STATUS_NONFINITE_BIT;
 
-        // ---- back substitution: the last 2B solution rows slide through registers ------------------
+        // ---- back substitution: x_{k+1} .. x_{k+2B} in the shared-memory ring ------------------------
         {
-            cplx X[2 * B][PP];
+            for (int i = 0; i < NX * P; ++i) ring[i * HVB_BAND_THREADS] = cmk(0.0, 0.0);
+            int xrow[NX + 1];                               // xrow[j] = ring row of x_{k+j}; xrow[0] is the row x_k goes to
 #pragma unroll
-            for (int j = 0; j < 2 * B; ++j)
-#pragma unroll
-                for (int r = 0; r < PP; ++r) X[j][r] = cmk(0.0, 0.0);
-            const long long rec = (long long)RS * T;
-            const cplx* __restrict__ rp = Rt + (long long)(n - 1) * rec;
-            for (int d = 1; d <= HVB_BAND_PREFETCH_BACK && n - 1 - d >= D.band_min_row; ++d)
-                for (int e = 0; e < RS; ++e) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp - d * rec + e * T));
-            for (int k = n - 1; k >= D.band_min_row; --k, rp -= rec) {
-                if (k - HVB_BAND_PREFETCH_BACK - 1 >= D.band_min_row) {
-                    const cplx* __restrict__ pf = rp - (HVB_BAND_PREFETCH_BACK + 1) * rec;
-                    for (int e = 0; e < RS; ++e) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + e * T));
+            for (int j = 0; j <= NX; ++j) xrow[j] = j % NX;
+            const cplx* __restrict__ rp = wp;               // end of the stream
+            const cplx* __restrict__ pp = wp;               // prefetch cursor, band_pfb records ahead
+            int kp = n - 1;
+            for (int d = 0; d < D.band_pfb && kp >= D.band_min_row; ++d, --kp) {
+                const int rs = WD + __ldg(D.band_act + kp);
+                pp -= rs * T;
+                for (int e = 0; e < rs; ++e) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + e * T));
+            }
+            for (int k = n - 1; k >= D.band_min_row; --k) {
+                if (kp >= D.band_min_row) {
+                    const int rs = WD + __ldg(D.band_act + kp);
+                    pp -= rs * T;
+                    for (int e = 0; e < rs; ++e) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + e * T));
+                    --kp;
                 }
+                const int na = __ldg(D.band_act + k);
+                rp -= (WD + na) * T;
                 cplx u[WD];
 #pragma unroll
                 for (int c = 0; c < WD; ++c) u[c] = rp[c * T];
-                cplx x[PP];
-#pragma unroll
-                for (int r = 0; r < PP; ++r) {
-                    cplx acc = (r < P) ? rp[(WD + r) * T] : cmk(0.0, 0.0);
-#pragma unroll
-                    for (int j = 1; j <= 2 * B; ++j) cfnma(acc, u[j], X[j - 1][r]);
-                    x[r] = cmul(acc, u[0]);
-                }
                 const int slot = __ldg(D.band_slot_of_row + k);
-                if (slot >= 0) {
+                cplx* __restrict__ xo = ring + xrow[0] * ring_row;
+                cplx* __restrict__ xs = Xs + (long long)(slot < 0 ? 0 : slot) * P * T;
+#pragma unroll 2
+                for (int r = 0; r < P; ++r) {
+                    cplx acc = (r < na) ? rp[(WD + r) * T] : cmk(0.0, 0.0);
 #pragma unroll
-                    for (int r = 0; r < PP; ++r) if (r < P) Xs[((long long)slot * P + r) * T] = x[r];
+                    for (int j = 1; j <= NX; ++j) cfnma(acc, u[j], ring[xrow[j] * ring_row + r * HVB_BAND_THREADS]);
+                    acc = cmul(acc, u[0]);
+                    xo[r * HVB_BAND_THREADS] = acc;         // xrow[0] == xrow[NX]: x_{k+2B} was read just above
+                    if (slot >= 0) xs[r * T] = acc;
                 }
+                // x_k becomes x_{(k-1)+1}
 #pragma unroll
-                for (int j = 2 * B - 1; j >= 1; --j)
-#pragma unroll
-                    for (int r = 0; r < PP; ++r) X[j][r] = X[j - 1][r];
-#pragma unroll
-                for (int r = 0; r < PP; ++r) X[0][r] = x[r];
+                for (int j = NX; j >= 1; --j) xrow[j] = xrow[j - 1];
+                xrow[0] = xrow[NX];
             }
         }
 
@@ -423,16 +452,17 @@ __global__ void __launch_bounds__(HVB_BAND_THREADS) hvb_bandf_kernel(const HvbDe
     if (bad && D.status) atomicOr(D.status, (int)bad);
 }
 
-const void* hvb_bandf_kernel_ptr(int b, int pp) {
-#define HVB_BANDF(BB, PPV) if (b == BB && pp == PPV) return (const void*)hvb_bandf_kernel<BB, PPV>;
-    HVB_BANDF(1, 2) HVB_BANDF(1, 4) HVB_BANDF(1, 8) HVB_BANDF(1, 16)
-    HVB_BANDF(2, 2) HVB_BANDF(2, 4) HVB_BANDF(2, 8)
-#undef HVB_BANDF
+const void* hvb_bandf_kernel_ptr(int b) {
+    switch (b) {
+        case 1: return (const void*)hvb_bandf_kernel<1>;
+        case 2: return (const void*)hvb_bandf_kernel<2>;
+        case 3: return (const void*)hvb_bandf_kernel<3>;
+        case 4: return (const void*)hvb_bandf_kernel<4>;
+    }
     return nullptr;
 }
-size_t hvb_bandf_words_per_thread(int b, int n, int p, int nslots, int n_dyn) {
-    return (size_t)n * (size_t)(2 * b + 1 + p) + (size_t)nslots * p + (size_t)(n_dyn > 0 ? n_dyn : 1);
-}
+// shared-memory complex words per thread: the right-hand-side / solution ring (value slots come on top)
+int hvb_bandf_ring_words(int b, int p) { return (b + 1 > 2 * b ? b + 1 : 2 * b) * p; }
 
 const void* hvb_band_kernel_ptr(int b) {
     switch (b) {

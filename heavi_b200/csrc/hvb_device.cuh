@@ -57,6 +57,15 @@ struct HvbDev {
     cplx* W;                                // dense dump / block-kernel / band-kernel workspace
     const int* band_slot_of_row;            // kernel C (fused): solution rows the S epilogue reads -> slot
     int band_nslots, band_min_row;
+    int band_pfb;                           // pivot-row records prefetched (to L2) ahead of the back substitution
+    int band_nsm;                           // value slots held in shared memory (the rest spill to W)
+    const int* band_act;                    // [n] right-hand-side columns that can be non-zero in rows <= k+B
+    long long band_rec_words;               // words of one point's pivot-row record stream
+    const int* band_sched_ptr;              // [n+1] value ops to run before assembling row r
+    const int* band_sched_op;               // >= 0: fast op index, < 0: ~(simple op index)
+    const int* band_fslot;                  // [nfast] output slot
+    const int* band_oslot;                  // [nops][9] output slots (-1: unused output)
+    const int* band_ent;                    // row_ent with per-point value ids replaced by nvc + slot
     int* status;
 };
 
