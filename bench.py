@@ -353,6 +353,19 @@ def main():
         roof_hbm = {"bound": "hbm", "achieved": bytes_alg / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": bytes_alg / (k_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_solve": 8 + 16 * plan.P ** 2,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if mp else "fallback 6650 GB/s"}
+        if ki["kernel_class"] == 2:
+            # banded kernel: thread per point, pivot-row records stream through HBM (write once, read once);
+            # its flop count is O(n B (2B+P)), so the bound is memory, and the dense-LU flop figure is only
+            # reported as an equivalent
+            per_solve = 8 + 16 * (2 * ki["stream_words"] + plan.P ** 2)
+            gbs = per_solve * job_points(jobs[top]) / (k_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                    "traffic": ncu_traffic(args.workload), "kernel": "hvb_bandf_kernel<%d>" % ki["group"],
+                    "launch_ms": k_ms, "n_factored": plan.n, "solver_mode": plan.mode, "half_bandwidth": plan.band,
+                    "bytes_per_solve": per_solve, "solves_per_launch": job_points(jobs[top]),
+                    "dense_lu_equivalent_tflops": achieved,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if mp else "fallback 6650 GB/s",
+                    "regs": ki["regs"], "ctas_per_sm": ki["ctas_per_sm"], "smem_bytes": ki["smem_bytes"]}
         cpu = None
         if not args.no_cpu:
             v, ms, info = time_cpu(jobs, 2, 1)

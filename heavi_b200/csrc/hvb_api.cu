@@ -596,7 +596,9 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     // that the first copy starts early and the exposed head (first kernel) / tail stay short; tiles
     // are equal-sized so no short tile trails the pipeline.
     const char* env = getenv("HVB_CHUNK_MB");
-    const int64_t chunk_bytes = (int64_t)(env && atoi(env) > 0 ? atoi(env) : 16) << 20;
+    int64_t chunk_bytes = (int64_t)(env && atoi(env) > 0 ? atoi(env) : 16) << 20;
+    // the banded kernel runs one point per thread: a tile should fill the grid at least once
+    if (pl->kclass == 2 && !(env && atoi(env) > 0)) chunk_bytes = std::max<int64_t>(chunk_bytes, (int64_t)pl->max_grid * pl->threads * PP * 16);
     const int64_t total_bytes = nS * nF * PP * 16;
     int64_t ntiles = std::max<int64_t>((total_bytes + chunk_bytes - 1) / chunk_bytes, 1);
     if (ntiles == 1 && nS * nF >= 65536) ntiles = 2;      // small jobs: overlap copy 1 with kernel 2
@@ -775,7 +777,7 @@ extern "C" int hvb_plan_kernel_info(hvb_plan* pl, hvb_kernel_info* out) {
     out->ctas_per_sm = pl->ctas_per_sm;
     out->sm_count = pl->sm_count;
     out->rows_per_lane = pl->rows_per_lane;
-    out->reserved0 = 0;
+    out->stream_words = pl->kclass == 2 ? (int32_t)(pl->band_fused ? pl->band_rec_words : (long long)pl->work_words) : 0;
     out->launches = pl->launches;
     return HVB_OK;
 }

@@ -43,7 +43,7 @@ class RunArgs(C.Structure):
 
 class KernelInfo(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("kernel_class", "group", "pmax", "threads", "smem_bytes", "regs",
-                                         "ctas_per_sm", "sm_count", "rows_per_lane", "reserved0")] + [("launches", C.c_int64)]
+                                         "ctas_per_sm", "sm_count", "rows_per_lane", "stream_words")] + [("launches", C.c_int64)]
 
 
 EXPORTS = ("hvb_warp_shape", "hvb_plan_create", "hvb_plan_destroy", "hvb_run_host", "hvb_run_device",

@@ -143,8 +143,9 @@ int hvb_warp_shape(int32_t n, int32_t P, int32_t max_nport, int32_t* n_pad, int3
 
 /* Introspection for the benchmark / tests. */
 typedef struct hvb_kernel_info {
-    int32_t kernel_class;   /* 0 = warp kernel (n <= 32), 1 = block kernel                       */
-    int32_t group;          /* warp kernel: padded rows N;  block kernel: panel width NB         */
+    int32_t kernel_class;   /* 0 = warp kernel (n <= 32), 1 = dense block kernel, 2 = banded kernel */
+    int32_t group;          /* warp kernel: padded rows N;  block kernel: panel width NB;
+                               banded kernel: instantiated half bandwidth B                       */
     int32_t pmax;           /* warp kernel: padded RHS columns                                   */
     int32_t threads;        /* threads per CTA                                                   */
     int32_t smem_bytes;     /* dynamic shared memory per CTA                                     */
@@ -152,7 +153,8 @@ typedef struct hvb_kernel_info {
     int32_t ctas_per_sm;    /* occupancy                                                         */
     int32_t sm_count;
     int32_t rows_per_lane;  /* warp kernel: matrix rows held by one lane (1 or 2)                */
-    int32_t reserved0;
+    int32_t stream_words;   /* banded kernel: complex words of pivot-row records one point writes
+                               to global memory once and reads back once; 0 for the other classes */
     int64_t launches;       /* kernel launches issued by this plan so far                        */
 } hvb_kernel_info;
 int hvb_plan_kernel_info(hvb_plan* plan, hvb_kernel_info* out);
