@@ -598,7 +598,11 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     const char* env = getenv("HVB_CHUNK_MB");
     int64_t chunk_bytes = (int64_t)(env && atoi(env) > 0 ? atoi(env) : 16) << 20;
     // the banded kernel runs one point per thread: a tile should fill the grid at least once
-    if (pl->kclass == 2 && !(env && atoi(env) > 0)) chunk_bytes = std::max<int64_t>(chunk_bytes, (int64_t)pl->max_grid * pl->threads * PP * 16);
+    if (pl->kclass == 2 && !(env && atoi(env) > 0)) {
+        const char* tw = getenv("HVB_BAND_TILE_WAVES");
+        const double waves = tw && atof(tw) > 0 ? atof(tw) : 1.0;
+        chunk_bytes = std::max<int64_t>(chunk_bytes, (int64_t)(waves * pl->max_grid * pl->threads) * PP * 16);
+    }
     const int64_t total_bytes = nS * nF * PP * 16;
     int64_t ntiles = std::max<int64_t>((total_bytes + chunk_bytes - 1) / chunk_bytes, 1);
     if (ntiles == 1 && nS * nF >= 65536) ntiles = 2;      // small jobs: overlap copy 1 with kernel 2

@@ -233,11 +233,21 @@ __device__ __forceinline__ void band_run_schedule(const HvbDev& D, int r, double
             const int* __restrict__ op = D.ops + o * HVB_OP_WORDS;
             const int out = __ldg(op + 1) - D.nvc;
             cplx tmp[9];
-            eval_simple_op(D, op, f, fi, srow, tmp - out);
-            const int cnt = __ldg(op) == OP_TLINE ? 9 : 1;
-            for (int e = 0; e < cnt; ++e) {
-                const int sl = __ldg(D.band_oslot + o * 9 + e);
-                if (sl >= 0) vals.store(sl, tmp[e]);
+            const bool line = __ldg(op) == OP_TLINE;
+            if (line) {
+                const cplx Z0 = eval_param(D.pv, __ldg(op + 2), f, fi, srow);
+                const cplx beta = eval_param(D.pv, __ldg(op + 3), f, fi, srow);
+                eval_tline_fast(Z0, beta, D.pv.consts[__ldg(op + 4)].x, tmp);
+            } else {
+                eval_simple_op(D, op, f, fi, srow, tmp - out);
+            }
+            const int cnt = line ? 9 : 1;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) {
+                if (e < cnt) {
+                    const int sl = __ldg(D.band_oslot + o * 9 + e);
+                    if (sl >= 0) vals.store(sl, tmp[e]);
+                }
             }
         }
     }

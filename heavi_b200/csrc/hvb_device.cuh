@@ -135,19 +135,6 @@ __device__ __forceinline__ cplx crecip_fast(cplx z) {
     return cmk(z.x * r, -z.y * r);
 }
 
-// C99 csqrt (what numpy's npy_csqrt follows) for finite input
-__device__ __forceinline__ cplx csqrt_np(cplx z) {
-    if (z.y == 0.0 && z.x >= 0.0) return cmk(sqrt(z.x), z.y);
-    if (z.x == 0.0 && z.y == 0.0) return cmk(0.0, z.y);
-    const double h = hypot(z.x, z.y);
-    if (z.x >= 0.0) {
-        const double t = sqrt((z.x + h) * 0.5);
-        return cmk(t, z.y / (2.0 * t));
-    }
-    const double t = sqrt((-z.x + h) * 0.5);
-    return cmk(fabs(z.y) / (2.0 * t), copysign(t, z.y));
-}
-
 // ------------------------------------------------------------------------------------------------
 // B-spline trace evaluation: scipy's find_interval + _deBoor_D + dot, constant end fill
 // (src/heavi/lib/touchstone.py:253-260 -> scipy.interpolate.interp1d(kind='cubic'))
@@ -239,7 +226,7 @@ __device__ __forceinline__ cplx eval_param(const ParamView& D, int pi, double f,
         case PK_BETA: {
             // TWOPI * f / c0 * sqrt(er)   (network.py:627-631), left to right
             const double b0 = __dmul_rn(HVB_TWOPI, f) / HVB_C0;
-            const cplx s = csqrt_np(D.consts[pr.y]);
+            const cplx s = D.consts[pr.y];                  // sqrt(er), computed by the plan compiler
             return cmk(__dmul_rn(b0, s.x), s.y == 0.0 ? 0.0 : __dmul_rn(b0, s.y));
         }
     }
@@ -280,6 +267,36 @@ static __device__ __noinline__ void eval_tline(cplx Z0, cplx beta, double len, c
     o[5] = cneg(s1);
     o[6] = cneg(cadd(y11, y21));
     o[7] = cneg(cadd(y12, y22));
+    o[8] = cadd(s0, s1);
+}
+
+// Same algebra with ONE complex reciprocal (1/a12) in place of the four Smith divisions and with fused
+// multiplies: a few ulp away from the reference's values instead of bit-faithful.  Used by the banded
+// solve kernel, where a chain of lines makes this function the largest single cost; the assembly dump
+// and the other solve kernels keep eval_tline.
+__device__ __forceinline__ void eval_tline_fast(cplx Z0, cplx beta, double len, cplx* __restrict__ o) {
+    const double x = -beta.y * len, y = beta.x * len;
+    double sy, cy;
+    sincos(y, &sy, &cy);
+    cplx ch, sh;
+    if (x == 0.0) { ch = cmk(cy, 0.0); sh = cmk(0.0, sy); }
+    else {
+        const double chx = cosh(x), shx = sinh(x);
+        ch = cmk(chx * cy, shx * sy);
+        sh = cmk(shx * cy, chx * sy);
+    }
+    const cplx a12 = cmul(Z0, sh);
+    const cplx a21 = cmul(crecip_fast(Z0), sh);
+    const cplx r = crecip_fast(a12);
+    const cplx y11 = cmul(ch, r);
+    const cplx y12 = cneg(cmul(csub(cmul(ch, ch), cmul(a12, a21)), r));
+    const cplx y21 = cneg(r);
+    const cplx s0 = cadd(y11, y12), s1 = cadd(y21, y11);
+    o[0] = y11; o[1] = y12; o[2] = y21; o[3] = y11;
+    o[4] = cneg(s0);
+    o[5] = cneg(s1);
+    o[6] = cneg(cadd(y11, y21));
+    o[7] = cneg(cadd(y12, y11));
     o[8] = cadd(s0, s1);
 }
 

@@ -201,7 +201,12 @@ class _Builder:
                 col = len(self.sample_owners) - 1
             return self.pref({"id": PK_SAMPLE, "neg": PK_SAMPLE_NEG, "inv": PK_SAMPLE_INV}[op], col), d
         if tag == "beta":
-            return self.pref(PK_BETA, self.const(d[1])), d
+            # the device multiplies (2 pi f / c0) by sqrt(er): the root does not depend on f, so numpy
+            # takes it here, once, exactly as `np.sqrt(er(f))` does per element (network.py:627-631)
+            er = complex(d[1])
+            with np.errstate(invalid="ignore"):
+                root = np.sqrt(np.float64(er.real)) if er.imag == 0 else np.sqrt(np.complex128(er))
+            return self.pref(PK_BETA, self.const(complex(root))), d
         if tag == "spline":
             return self.pref(PK_SPLINE, self.add_spline(d[1])), d
         # generic callable: tabulated per run

@@ -58,9 +58,9 @@ class Interp:
         if kind == pl.PK_TABLE:
             return self.tables[idx]
         if kind == pl.PK_BETA:
-            er = self.consts[idx]
-            er = er.real if er.imag == 0 else er
-            return _TWOPI * f / _C0 * np.sqrt(er * one)
+            root = self.consts[idx]                      # sqrt(er), taken by the plan compiler
+            root = root.real if root.imag == 0 else root
+            return _TWOPI * f / _C0 * (root * one)
         if kind == pl.PK_SPLINE:
             t_off, nt, c_off, k = self.p.spl_trace[idx]
             t = self.p.spl_t[t_off:t_off + nt]
