@@ -624,7 +624,7 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     for (int b = 0; b < 2; ++b) CU(pl->S[b].ensure((size_t)Sc * PP * Fc * 16));
 
     const char* c2d = getenv("HVB_COPY2D");
-    const bool copy2d = c2d && c2d[0] == '1';
+    const bool copy2d = !(c2d && c2d[0] == '0');          // default; 0 = one plain copy per row (measured slower)
     int tile = 0;
     for (int64_t sb = 0; sb < nS; sb += Sc) {
         const int64_t ns = std::min(Sc, nS - sb);
@@ -644,8 +644,7 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
             if (rc) return rc;
             // rows of nf elements, one per (sample, j, i); destination pitch is the full nF
             char* dst = (char*)S_out + ((size_t)sb * PP * nF + (size_t)fb) * 16;
-            // contiguous destination -> one plain copy; a few long rows -> one plain copy per row
-            // (both reach the full PCIe rate); many short rows -> strided 2-D copy
+            // contiguous destination -> one plain copy; otherwise one strided 2-D copy
             const int64_t rows = ns * PP;
             if (nf == nF) {
                 CU(cudaMemcpyAsync(dst, D.S, (size_t)rows * nf * 16, cudaMemcpyDeviceToHost, st));

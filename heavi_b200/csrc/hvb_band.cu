@@ -401,31 +401,48 @@ __global__ void __launch_bounds__(HVB_BAND_THREADS, B == 1 ? 5 : B == 2 ? 4 : B 
             for (int d = 0; d < D.band_pfb && kp >= D.band_min_row; ++d, --kp) {
                 const int rs = WD + __ldg(D.band_act + kp);
                 pp -= rs * T;
-                for (int e = 0; e < rs; ++e) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + e * T));
+                const cplx* __restrict__ pe = pp;
+                for (int e = 0; e < rs; ++e, pe += T) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe));
             }
             for (int k = n - 1; k >= D.band_min_row; --k) {
                 if (kp >= D.band_min_row) {
                     const int rs = WD + __ldg(D.band_act + kp);
                     pp -= rs * T;
-                    for (int e = 0; e < rs; ++e) asm volatile("prefetch.global.L2 [%0];" ::"l"(pp + e * T));
+                    const cplx* __restrict__ pe = pp;
+                    for (int e = 0; e < rs; ++e, pe += T) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe));
                     --kp;
                 }
                 const int na = __ldg(D.band_act + k);
                 rp -= (WD + na) * T;
                 cplx u[WD];
+                const cplx* __restrict__ yp = rp;
 #pragma unroll
-                for (int c = 0; c < WD; ++c) u[c] = rp[c * T];
+                for (int c = 0; c < WD; ++c, yp += T) u[c] = *yp;
                 const int slot = __ldg(D.band_slot_of_row + k);
                 cplx* __restrict__ xo = ring + xrow[0] * ring_row;
-                cplx* __restrict__ xs = Xs + (long long)(slot < 0 ? 0 : slot) * P * T;
-#pragma unroll 2
-                for (int r = 0; r < P; ++r) {
-                    cplx acc = (r < na) ? rp[(WD + r) * T] : cmk(0.0, 0.0);
+                const cplx* xj[NX + 1];
 #pragma unroll
-                    for (int j = 1; j <= NX; ++j) cfnma(acc, u[j], ring[xrow[j] * ring_row + r * HVB_BAND_THREADS]);
-                    acc = cmul(acc, u[0]);
-                    xo[r * HVB_BAND_THREADS] = acc;         // xrow[0] == xrow[NX]: x_{k+2B} was read just above
-                    if (slot >= 0) xs[r * T] = acc;
+                for (int j = 1; j <= NX; ++j) xj[j] = ring + xrow[j] * ring_row;
+                cplx* __restrict__ xs = Xs + (long long)(slot < 0 ? 0 : slot) * P * T;
+                // four right-hand sides at a time: their record loads are issued together
+                for (int r0 = 0; r0 < P; r0 += 4) {
+                    cplx acc[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[i] = (r0 + i < na) ? *yp : cmk(0.0, 0.0);
+                        if (r0 + i < na) yp += T;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (r0 + i < P) {
+                            const int off = (r0 + i) * HVB_BAND_THREADS;
+#pragma unroll
+                            for (int j = 1; j <= NX; ++j) cfnma(acc[i], u[j], xj[j][off]);
+                            acc[i] = cmul(acc[i], u[0]);
+                            xo[off] = acc[i];                // xrow[0] == xrow[NX]: x_{k+2B} was read just above
+                            if (slot >= 0) { *xs = acc[i]; xs += T; }
+                        }
+                    }
                 }
                 // x_k becomes x_{(k-1)+1}
 #pragma unroll
