@@ -553,48 +553,13 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     const int64_t nF = a->nF, nS = a->nS;
     const int64_t PP = (int64_t)d.P * d.P;
     if (nF == 0 || PP == 0) { if (status_out) *status_out = 0; return HVB_OK; }
+    if ((d.n_consts && !a->consts) || (d.n_prefs && !a->prefs)) return fail(HVB_ERR_ARG, "consts/prefs missing");
     cudaStream_t s0 = pl->streams[0], s1 = pl->streams[1];
 
-    // inputs: ONE pinned staging block [status | consts | prefs | f | samples] and ONE async H2D on
-    // stream 0 (f and the sample matrix usually come from pageable numpy memory, where a direct
-    // cudaMemcpyAsync degrades to a synchronous staged copy, and every extra API call costs microseconds)
-    auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
-    const size_t off_consts = 16;
-    const size_t off_prefs = off_consts + up16((size_t)d.n_consts * 16);
-    const size_t off_f = off_prefs + up16((size_t)d.n_prefs * 8);
-    const size_t off_smp = off_f + up16((size_t)nF * 8);
-    const size_t in_bytes = off_smp + up16(d.n_samples_cols ? (size_t)nS * d.n_samples_cols * 8 : 0);
-    if ((d.n_consts && !a->consts) || (d.n_prefs && !a->prefs)) return fail(HVB_ERR_ARG, "consts/prefs missing");
-    if (pl->h_in_bytes < in_bytes) {
-        CU(cudaStreamSynchronize(s0));
-        if (pl->h_in) cudaFreeHost(pl->h_in);
-        pl->h_in = nullptr; pl->h_in_bytes = 0;
-        CU(cudaMallocHost(&pl->h_in, in_bytes + in_bytes / 4 + 4096));
-        pl->h_in_bytes = in_bytes + in_bytes / 4 + 4096;
-    }
-    CU(pl->inbuf.ensure(in_bytes));
-    CU(cudaEventSynchronize(pl->ev_ready));              // the previous run's H2D out of h_in has finished
-    {
-        char* h = (char*)pl->h_in;
-        memset(h, 0, 16);
-        if (d.n_consts) memcpy(h + off_consts, a->consts, (size_t)d.n_consts * 16);
-        if (d.n_prefs) memcpy(h + off_prefs, a->prefs, (size_t)d.n_prefs * 8);
-        memcpy(h + off_f, a->f, (size_t)nF * 8);
-        if (d.n_samples_cols) memcpy(h + off_smp, a->samples, (size_t)nS * d.n_samples_cols * 8);
-    }
-    CU(cudaMemcpyAsync(pl->inbuf.p, pl->h_in, in_bytes, cudaMemcpyHostToDevice, s0));
-    if (a->n_tables) {
-        CU(pl->tables.ensure((size_t)a->n_tables * nF * 16));
-        CU(cudaMemcpyAsync(pl->tables.p, a->tables, (size_t)a->n_tables * nF * 16, cudaMemcpyHostToDevice, s0));
-    }
-    CU(cudaEventRecord(pl->ev_ready, s0));
-    CU(cudaStreamWaitEvent(s1, pl->ev_ready, 0));
-    const char* dbase = (const char*)pl->inbuf.p;
-
-    // tiles: whole samples when several fit in a chunk, else frequency slabs of one sample
-    // Tile size: large enough for the copy to run at the full PCIe rate (>= a few MB), small enough
-    // that the first copy starts early and the exposed head (first kernel) / tail stay short; tiles
-    // are equal-sized so no short tile trails the pipeline.
+    // ---- tiles: whole samples when several fit in a chunk, else frequency slabs of one sample --------
+    // Tile size: large enough for the copy to run at the full PCIe rate (a few MB), small enough that
+    // the first copy starts early and the exposed head (first kernel) / tail stay short; tiles are
+    // equal-sized so no short tile trails the pipeline.
     const char* env = getenv("HVB_CHUNK_MB");
     int64_t chunk_bytes = (int64_t)(env && atoi(env) > 0 ? atoi(env) : 16) << 20;
     // the banded kernel runs one point per thread: a tile should fill the grid at least once
@@ -603,25 +568,58 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
         const double waves = tw && atof(tw) > 0 ? atof(tw) : 1.0;
         chunk_bytes = std::max<int64_t>(chunk_bytes, (int64_t)(waves * pl->max_grid * pl->threads) * PP * 16);
     }
+    const char* ms = getenv("HVB_MIN_SLAB");
+    const int64_t min_slab = ms && atoi(ms) > 0 ? atoi(ms) : 32768;   // points; a slab leaves as P*P segments of 16*slab bytes
     const int64_t total_bytes = nS * nF * PP * 16;
     int64_t ntiles = std::max<int64_t>((total_bytes + chunk_bytes - 1) / chunk_bytes, 1);
-    if (ntiles == 1 && nS * nF >= 65536) ntiles = 2;      // small jobs: overlap copy 1 with kernel 2
+    // small jobs: still cut them so that the copy of one tile overlaps the kernel of the next
+    if (ntiles < 4 && pl->kclass != 2) ntiles = std::max<int64_t>(ntiles, std::min<int64_t>(4, nS * nF / min_slab));
     int64_t Sc = nS, Fc = nF;
     if (nS >= ntiles) {
         Sc = (nS + ntiles - 1) / ntiles;                  // whole samples per tile
     } else {
         Sc = 1;                                           // frequency slabs of one sample
-        const int64_t per_sample = (ntiles + nS - 1) / nS;
-        Fc = std::max<int64_t>((nF + per_sample - 1) / per_sample, 1);
-        // a slab is copied out as P*P separate row segments: keep each segment around 1 MB or the
-        // copy engine spends its time on per-copy overhead (measured: 128 KB segments halve the rate)
-        if (Fc < 65536 && nF > Fc) {
-            const int64_t want = std::min<int64_t>(nF, 65536);
-            const int64_t slabs = std::max<int64_t>(nF / want, 1);
-            Fc = (nF + slabs - 1) / slabs;
-        }
+        int64_t slabs = (ntiles + nS - 1) / nS;
+        slabs = std::max<int64_t>(std::min<int64_t>(slabs, nF / min_slab), 1);
+        Fc = (nF + slabs - 1) / slabs;
     }
     for (int b = 0; b < 2; ++b) CU(pl->S[b].ensure((size_t)Sc * PP * Fc * 16));
+
+    // ---- inputs: ONE pinned staging block [status | consts | prefs | samples | f] -------------------
+    // (f and the sample matrix usually come from pageable numpy memory, where a direct cudaMemcpyAsync
+    // degrades to a synchronous staged copy, and every extra API call costs microseconds.)  A single
+    // sweep cut into frequency slabs uploads f slab by slab, each on its tile's stream, so the first
+    // kernel starts after the first slab instead of after the whole axis.
+    auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t off_consts = 16;
+    const size_t off_prefs = off_consts + up16((size_t)d.n_consts * 16);
+    const size_t off_smp = off_prefs + up16((size_t)d.n_prefs * 8);
+    const size_t off_f = off_smp + up16(d.n_samples_cols ? (size_t)nS * d.n_samples_cols * 8 : 0);
+    const size_t in_bytes = off_f + up16((size_t)nF * 8);
+    const bool slab_upload = nS == 1 && Fc < nF;
+    if (pl->h_in_bytes < in_bytes) {
+        CU(cudaStreamSynchronize(s0));
+        if (pl->h_in) cudaFreeHost(pl->h_in);
+        pl->h_in = nullptr; pl->h_in_bytes = 0;
+        CU(cudaMallocHost(&pl->h_in, in_bytes + in_bytes / 4 + 4096));
+        pl->h_in_bytes = in_bytes + in_bytes / 4 + 4096;
+    }
+    CU(pl->inbuf.ensure(in_bytes));
+    char* h = (char*)pl->h_in;                            // free: the previous call waited for all its copies
+    const int64_t f_first = slab_upload ? Fc : nF;
+    memset(h, 0, 16);
+    if (d.n_consts) memcpy(h + off_consts, a->consts, (size_t)d.n_consts * 16);
+    if (d.n_prefs) memcpy(h + off_prefs, a->prefs, (size_t)d.n_prefs * 8);
+    if (d.n_samples_cols) memcpy(h + off_smp, a->samples, (size_t)nS * d.n_samples_cols * 8);
+    memcpy(h + off_f, a->f, (size_t)f_first * 8);
+    CU(cudaMemcpyAsync(pl->inbuf.p, h, off_f + (size_t)f_first * 8, cudaMemcpyHostToDevice, s0));
+    if (a->n_tables) {
+        CU(pl->tables.ensure((size_t)a->n_tables * nF * 16));
+        CU(cudaMemcpyAsync(pl->tables.p, a->tables, (size_t)a->n_tables * nF * 16, cudaMemcpyHostToDevice, s0));
+    }
+    CU(cudaEventRecord(pl->ev_ready, s0));
+    CU(cudaStreamWaitEvent(s1, pl->ev_ready, 0));
+    char* dbase = (char*)pl->inbuf.p;
 
     const char* c2d = getenv("HVB_COPY2D");
     const bool copy2d = !(c2d && c2d[0] == '0');          // default; 0 = one plain copy per row (measured slower)
@@ -631,6 +629,11 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
         for (int64_t fb = 0; fb < nF; fb += Fc, ++tile) {
             const int64_t nf = std::min(Fc, nF - fb);
             cudaStream_t st = pl->streams[tile & 1];
+            if (slab_upload && fb > 0) {
+                memcpy(h + off_f + (size_t)fb * 8, a->f + fb, (size_t)nf * 8);
+                CU(cudaMemcpyAsync(dbase + off_f + (size_t)fb * 8, h + off_f + (size_t)fb * 8, (size_t)nf * 8,
+                                   cudaMemcpyHostToDevice, st));
+            }
             HvbDev D = make_dev(pl);
             D.nF = nf; D.nS = ns; D.ldS = nf; D.pv.table_ld = nF;
             D.pv.consts = (const cplx*)(dbase + off_consts);
@@ -662,6 +665,8 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     CU(cudaEventRecord(pl->ev_tail, s1));
     CU(cudaStreamWaitEvent(s0, pl->ev_tail, 0));
     CU(cudaMemcpyAsync(pl->h_status, pl->inbuf.p, 4, cudaMemcpyDeviceToHost, s0));
+    // host work that would otherwise follow the call, done while the GPU is busy
+    if (a->f32_out) for (int64_t i = 0; i < nF; ++i) a->f32_out[i] = (float)a->f[i];
     CU(cudaStreamSynchronize(s0));
     if (status_out) *status_out = *pl->h_status;
     return HVB_OK;

@@ -38,7 +38,8 @@ class PlanDesc(C.Structure):
 
 class RunArgs(C.Structure):
     _fields_ = [("consts", C.c_void_p), ("prefs", C.c_void_p), ("f", C.c_void_p), ("nF", C.c_int64),
-                ("samples", C.c_void_p), ("nS", C.c_int64), ("tables", C.c_void_p), ("n_tables", C.c_int32)]
+                ("samples", C.c_void_p), ("nS", C.c_int64), ("tables", C.c_void_p), ("n_tables", C.c_int32),
+                ("f32_out", C.c_void_p)]
 
 
 class KernelInfo(C.Structure):
@@ -196,7 +197,10 @@ class DevicePlanHandle:
         return {k: getattr(ki, k) for k, _ in KernelInfo._fields_}
 
     # ---- host buffers in, host buffer out ------------------------------------------------------
-    def run_host(self, f, consts, prefs, tables, samples, out: np.ndarray | None = None):
+    def run_host(self, f, consts, prefs, tables, samples, out: np.ndarray | None = None,
+                 f32_out: np.ndarray | None = None):
+        """`f32_out` (float32 [nF], optional) receives the frequencies rounded to float32, filled in by
+        the library while the GPU works (the reference's `Sparameters.f`)."""
         p = self.plan
         f = np.ascontiguousarray(f, dtype=np.float64)
         nF, nS = f.shape[0], samples.shape[0]
@@ -205,6 +209,10 @@ class DevicePlanHandle:
         tables = np.ascontiguousarray(tables, dtype=np.complex128)
         samples = np.ascontiguousarray(samples, dtype=np.float64)
         a = self._args(consts, prefs, _ptr(f), nF, _ptr(samples), nS, _ptr(tables), tables.shape[0])
+        if f32_out is not None:
+            if f32_out.dtype != np.float32 or f32_out.shape != (nF,) or not f32_out.flags.c_contiguous:
+                raise ValueError("f32_out must be a contiguous float32 array of nF elements")
+            a.f32_out = _ptr(f32_out)
         status = C.c_int32(0)
         _check(self.lib.hvb_run_host(self.handle, C.byref(a), out.ctypes.data_as(C.c_void_p), C.byref(status)))
         return out, status.value
@@ -282,10 +290,10 @@ class CompiledNetwork:
     def resolve(self, f, drivers=None, values=None):
         return pl.resolve_run(self.plan, f, drivers, values)
 
-    def run(self, f: np.ndarray, drivers=None, values=None, out=None) -> np.ndarray:
+    def run(self, f: np.ndarray, drivers=None, values=None, out=None, f32_out=None) -> np.ndarray:
         """S[nS,P,P,nF] complex128 on pinned host memory."""
         consts, prefs, tables, samples = self.resolve(f, drivers, values)
-        S, status = self.handle.run_host(f, consts, prefs, tables, samples, out)
+        S, status = self.handle.run_host(f, consts, prefs, tables, samples, out, f32_out)
         if status & HVB_STATUS_NONFINITE:
             # the reference's numba lstsq raises for NaN/Inf input (SURVEY.md section 5)
             raise np.linalg.LinAlgError("MNA matrix or S-parameters contain NaN/Inf (e.g. f = 0 with an inductor)")

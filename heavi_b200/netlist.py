@@ -216,12 +216,16 @@ class Network:
         """S-parameter sweep at `frequencies` -> Sparameters(S[P,P,nF] complex128, f float32)."""
         compiled = self._compiled()
         f64 = np.ascontiguousarray(frequencies, dtype=np.float64)
-        S = compiled.run(f64)                                     # [1,P,P,nF] on pinned host memory
+        # float32 copy of the frequency axis, the reference's quirk (network.py:407,421); float64 holds
+        # every float32-representable input exactly, so converting from f64 gives the same values.  The
+        # library fills it in while the GPU works.
+        f32 = np.empty(f64.shape, dtype=np.float32)
+        S = compiled.run(f64, f32_out=f32 if f64.ndim == 1 else None)   # [1,P,P,nF] on pinned host memory
+        if f64.ndim != 1:
+            f32 = f64.astype(np.float32)
         if reinitialize:
             self._initialized = False
-        # float32 copy of the frequency axis, the reference's quirk (network.py:407,421); float64 holds
-        # every float32-representable input exactly, so converting from f64 gives the same values
-        return Sparameters(S[0], f64.astype(np.float32))
+        return Sparameters(S[0], f32)
 
     def run_sp_batch(self, frequencies: np.ndarray, drivers, values: np.ndarray) -> np.ndarray:
         """Batched Monte-Carlo / sweep evaluation: `values[s, k]` is the value of `drivers[k]`

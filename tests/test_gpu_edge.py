@@ -230,3 +230,13 @@ def test_two_models_interleaved():
     for _ in range(3):
         assert np.max(np.abs(m1.run_sp(f)._S - oracle_S(m1, f))) < TOL
         assert np.max(np.abs(m2.run_sp(f)._S - oracle_S(m2, f))) < TOL
+
+
+def test_frequency_axis_float32_filled_by_the_library():
+    """`Sparameters.f` is float32 (network.py:407,421); the library converts it while the GPU works."""
+    m, _ = ladder(6, 2)
+    f = np.linspace(0.5e9, 4e9, 1001) + 0.123
+    S = m.run_sp(f)
+    assert S.f.dtype == np.float32 and np.array_equal(S.f, f.astype(np.float32))
+    S2 = m.run_sp(list(f[:7]))
+    assert np.array_equal(S2.f, f[:7].astype(np.float32))
