@@ -718,8 +718,8 @@ extern "C" int hvb_run_stats_host(hvb_plan* pl, const hvb_run_args* a, double* s
         long long a_nS = nS, a_rows = PP, a_nF = nf, a_ld = nf, a_ldo = nf;
         double* dout = (double*)pl->stats.p;
         void* args[] = {&dS, &a_nS, &a_rows, &a_nF, &a_ld, &dout, &a_ldo};
-        const long long blocks = std::min<long long>((PP * nf + 255) / 256, (long long)pl->sm_count * 8);
-        CU(cudaLaunchKernel(rk, dim3((unsigned)blocks), dim3(256), args, 0, st));
+        const long long blocks = std::min<long long>(PP * ((nf + 31) / 32), (long long)pl->sm_count * 8);
+        CU(cudaLaunchKernel(rk, dim3((unsigned)blocks), dim3(hvb_stats_threads()), args, 0, st));
         pl->launches++;
         CU(cudaMemcpy2DAsync((char*)stats_out + (size_t)fb * 8, (size_t)nF * 8, pl->stats.p, (size_t)nf * 8,
                              (size_t)nf * 8, (size_t)(6 * PP), cudaMemcpyDeviceToHost, st));

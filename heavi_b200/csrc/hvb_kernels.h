@@ -29,4 +29,5 @@ int hvb_bandf_ring_words(int b, int p);
 
 const void* hvb_dump_kernel_ptr();
 const void* hvb_stats_kernel_ptr();
+int hvb_stats_threads();
 const void* hvb_dfma_probe_ptr();
