@@ -152,3 +152,39 @@ def test_closed_form_epilogue_not_used_when_port_is_not_ground_referenced():
         distinct = len({int(r[1]) for r in tab.port_table}) == tab.P
         assert p.epi_simple == (1 if grounded and distinct else 0)
     assert pl.compile_plan(REG["c1_readme"]().stamp_table(), "full").epi_simple == 0
+
+
+def _half_bandwidth(p):
+    return max((abs(r - c) for r in range(p.n) for c in range(p.n)
+                if p.cell_ptr[r * p.ncols + c + 1] > p.cell_ptr[r * p.ncols + c]), default=0)
+
+
+@pytest.mark.parametrize("reach,K,nports,mode", [(1, 40, 2, "auto"), (2, 60, 3, "auto"), (4, 80, 3, "auto"),
+                                                  (2, 50, 3, "full"), (1, 33, 2, "full")])
+def test_band_ordering_is_a_symmetric_permutation(reach, K, nports, mode):
+    """The bandwidth-reducing row order (what the banded kernel needs) renumbers the unknowns and
+    changes nothing else: same S as the natural order, structure inside the reported band."""
+    import circuits
+    m, f = circuits.build_band_ladder(hv, K=K, reach=reach, nports=nports, seed=reach * 100 + K)
+    tab = m.stamp_table()
+    nat = pl.compile_plan(tab, mode, order="natural")
+    rcm = pl.compile_plan(tab, mode, order="rcm")
+    assert nat.band == -1 and rcm.band >= reach and rcm.band <= pl.BAND_MAX_HALF_WIDTH
+    assert _half_bandwidth(rcm) == rcm.band
+    if mode == "auto":
+        assert rcm.band == reach                       # the netlist's own chain order is already optimal
+    assert sorted(rcm.row_ent.tolist()) != [] and rcm.n == nat.n and len(rcm.row_ent) == len(nat.row_ent)
+    f = f[:6]
+    assert np.max(np.abs(pi.run_plan(rcm, f) - pi.run_plan(nat, f))) < 1e-12
+    auto = pl.compile_plan(tab, mode)                  # "auto" orders systems beyond the register kernels
+    assert (auto.band >= 0) == (auto.n_real >= pl.BAND_MIN_ROWS)
+
+
+def test_band_ordering_skips_dense_and_small_systems():
+    g = golden("c3_touchstone")
+    assert pl.compile_plan(REG["c3_touchstone"]().stamp_table()).band == -1      # N-port block, n = 24
+    assert pl.compile_plan(REG["c2_bandpass"]().stamp_table()).band == -1        # n = 7: register kernel
+    c5 = pl.compile_plan(REG["c5_ladder"]().stamp_table())
+    assert c5.band == 1 and c5.n_real == 191 and _half_bandwidth(c5) == 1
+    with pytest.raises(ValueError):
+        pl.compile_plan(REG["c5_ladder"]().stamp_table(), order="nearest")
