@@ -290,8 +290,45 @@ class CompiledNetwork:
     def resolve(self, f, drivers=None, values=None):
         return pl.resolve_run(self.plan, f, drivers, values)
 
+    def _tables_follow_drivers(self, f: np.ndarray, drivers, values) -> bool:
+        """True when a host-tabulated callable reads one of the batch drivers (e.g. a closure over
+        `Random` objects, lib/mc.py RandomTwoPort): such a table differs from sample to sample, which the
+        one-table-per-run layout cannot express.  Probed by evaluating every tabulated callable on a few
+        frequencies with the drivers set to two different rows of `values`."""
+        if not self.plan.table_params or values is None or len(values) < 2 or not len(drivers):
+            return False
+        fp = np.ascontiguousarray(f[:: max(1, len(f) // 3)][:4], dtype=np.float64)
+        saved = [d._value for d in drivers]
+        try:
+            rows = []
+            for row in (values[0], values[-1], values[len(values) // 2]):
+                for d, v in zip(drivers, row):
+                    d._value = float(v)
+                rows.append([np.array(fn(fp), dtype=np.complex128, copy=True) * np.ones(fp.shape) for (_, _, fn) in self.plan.table_params])
+        finally:
+            for d, v in zip(drivers, saved):
+                d._value = v
+        return any(not np.array_equal(a, b) for other in rows[1:] for a, b in zip(rows[0], other))
+
     def run(self, f: np.ndarray, drivers=None, values=None, out=None, f32_out=None) -> np.ndarray:
         """S[nS,P,P,nF] complex128 on pinned host memory."""
+        if drivers is not None and self._tables_follow_drivers(f, drivers, values):
+            # sample-dependent callables: one run per sample with the drivers set, like the reference's loop
+            values = np.asarray(values, dtype=np.float64)
+            nS = values.shape[0]
+            S = out if out is not None else pinned_empty((nS, self.plan.P, self.plan.P, len(f)))
+            saved = [d._value for d in drivers]
+            try:
+                for s in range(nS):
+                    for d, v in zip(drivers, values[s]):
+                        d._value = float(v)
+                    self.run(f, list(drivers), values[s:s + 1], out=S[s:s + 1])
+            finally:
+                for d, v in zip(drivers, saved):
+                    d._value = v
+            if f32_out is not None:
+                f32_out[:] = f
+            return S
         consts, prefs, tables, samples = self.resolve(f, drivers, values)
         S, status = self.handle.run_host(f, consts, prefs, tables, samples, out, f32_out)
         if status & HVB_STATUS_NONFINITE:
@@ -312,6 +349,12 @@ class CompiledNetwork:
     def run_stats(self, f: np.ndarray, drivers, values) -> np.ndarray:
         """Moments over the sample axis, reduced on the device: float64 [6, P, P, nF] in the order
         amplitude mean/std, power mean/std, rms mean/std (StatSparam, sparam.py:215-243)."""
+        if self._tables_follow_drivers(f, drivers, values):
+            S = self.run(f, drivers, values)                  # per-sample runs; moments taken on the host
+            a = np.abs(S)
+            pw = a ** 2
+            return np.stack([a.mean(axis=0), a.std(axis=0), pw.mean(axis=0), pw.std(axis=0),
+                             np.sqrt(pw).mean(axis=0), np.sqrt(pw).std(axis=0)])
         consts, prefs, tables, samples = self.resolve(f, drivers, values)
         out, status = self.handle.run_stats_host(f, consts, prefs, tables, samples)
         self._raise_for_status(status)

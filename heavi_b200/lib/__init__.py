@@ -1,2 +1,2 @@
-"""Part libraries (host-side netlist builders) and the optimiser: `smd`, `tl`, `libgen`, `touchstone`, `optim`."""
-from . import libgen, optim, smd, subcircuit, tl, touchstone  # noqa: F401
+"""Part libraries (host-side netlist builders) and the optimiser: `smd`, `tl`, `libgen`, `touchstone`, `emerge`, `mc`, `optim`."""
+from . import emerge, libgen, mc, optim, smd, subcircuit, tl, touchstone  # noqa: F401

@@ -72,8 +72,23 @@ def capture(name, net, f, y_points=3, extra=None):
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
 
 
+def mc_twoport(hv):
+    """lib/mc.py RandomTwoPort under the reference's own Monte-Carlo loop, np.random.seed(11), 6 trials."""
+    m, f, mc = circuits.build_random_twoport(hv)
+    np.random.seed(11)
+    draws, Ss = [], []
+    for _ in mc.iterate(6):
+        draws.append([r._value for r in mc._random_numbers])
+        Ss.append(m.run_sp(f)._S)
+    np.savez_compressed(os.path.join(GOLD, "mc_twoport.npz"), f=f, mc_draws=np.array(draws), mc_S=np.stack(Ss))
+    print("mc_twoport     %d trials, %d randoms, nF=%d" % (len(Ss), len(mc._random_numbers), len(f)), flush=True)
+
+
 def main():
     hv = load_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-mc-twoport":
+        os.makedirs(GOLD, exist_ok=True)
+        return mc_twoport(hv)
     os.makedirs(GOLD, exist_ok=True)
     if not os.path.exists(circuits.SYNTH8):
         circuits.write_synth8()
@@ -100,6 +115,8 @@ def main():
 
     m, f = circuits.build_c5(hv, nF=1_000_000)
     capture("c5_ladder", m, f[::66667][:12], y_points=1)
+
+    mc_twoport(hv)
 
     m, f = circuits.build_divider(hv)
     capture("ka_divider", m, f)

@@ -129,6 +129,24 @@ def build_c4(hv, nF: int = 2001):
     return m, hv.frange(1.8e9, 2.2e9, nF), mc
 
 
+def build_random_twoport(hv, nF: int = 41):
+    """Monte-Carlo cable model (lib/mc.py RandomTwoPort) between a port and a short matched line: its
+    S_ij are closures over `Random` objects, i.e. tabulated callables that change from trial to trial."""
+    import importlib
+    RandomTwoPort = importlib.import_module(hv.__name__ + ".lib.mc").RandomTwoPort
+    m = _model(hv)
+    mc = hv.MonteCarlo()
+    a = m.quick_port(50)
+    b = m.quick_port(50)
+    mid = m.node()
+    blk = RandomTwoPort(mc, 0.25, 50.0, VSWR=1.4, er=2.1, attenuation=0.8, phase_stability=4.0,
+                        amplitude_stability=0.3, Z0_error=3.0)
+    blk.connect(a, mid)
+    m.transmissionline(mid, b, 50.0, 2.9, 7e-3)
+    m.capacitor(mid, m.gnd, mc.gaussian(0.3e-12, 0.01e-12))
+    return m, np.linspace(1e9, 4e9, nF), mc
+
+
 # ---------------------------------------------------------------- config 5 (SURVEY App. D-5)
 def build_c5(hv, nF: int = 1_000_000, K: int = 190):
     rng = np.random.default_rng(2024)

@@ -196,3 +196,62 @@ def test_subcircuit_framework():
     assert t.first_node == 2 and not t._complete()
     t.partial_connect(2, b)
     assert len([x for x in m.components if x.kind == "resistor"]) == 5
+
+
+def test_emerge_model_equals_touchstone_block():
+    """EMergeModel((F, S)) is the in-memory counterpart of FileBasedNPort (lib/emerge.py:14-60): fed the
+    arrays a Touchstone file parses to, it must produce the same netlist, plan and S."""
+    import circuits
+    import plan_interp as pi
+    from heavi_b200 import plan as pl
+    from heavi_b200.lib.emerge import EMergeModel
+    ref_blk = hv.FileBasedNPort(circuits.SYNTH8)
+
+    def build(block):
+        m = hv.Model(suppress_loadbar=True)
+        inner = [m.node() for _ in range(8)]
+        for k, n in enumerate(inner):
+            sig = m.quick_port(50)
+            mid = m.node()
+            m.inductor(sig, mid, (1.0 + 0.25 * k) * 1e-9)
+            m.capacitor(mid, m.gnd, (0.5 + 0.1 * k) * 1e-12)
+            m.capacitor(mid, n, (2.0 + 0.3 * k) * 1e-12)
+        block.connect(*inner)
+        return m
+
+    m_file = build(hv.FileBasedNPort(circuits.SYNTH8))
+    m_mem = build(EMergeModel((ref_blk.Fdata, ref_blk.Sdata)))
+    ta, tb = m_file.stamp_table(), m_mem.stamp_table()
+    assert ta.kinds == tb.kinds and ta.ids == tb.ids
+    f = np.linspace(1e9, 6e9, 9)
+    Sa = pi.run_plan(pl.compile_plan(ta), f)
+    Sb = pi.run_plan(pl.compile_plan(tb), f)
+    assert np.array_equal(Sa, Sb)
+    blk = EMergeModel((ref_blk.Fdata, ref_blk.Sdata.copy()))
+    assert blk.n_ports == 8 and blk.refimp == 50
+    S0 = blk.Sdata.copy()
+    blk.renormalize(75.0).renormalize(50.0)
+    assert blk.refimp == 50.0 and np.max(np.abs(blk.Sdata - S0)) < 1e-12
+    with pytest.raises(ValueError):
+        EMergeModel((ref_blk.Fdata[:-1], ref_blk.Sdata))
+
+
+def test_random_twoport_draws_and_per_trial_plan_match_the_reference():
+    """lib/mc.py RandomTwoPort: the S_ij are closures over Random objects.  The pre-drawn batch must walk
+    np.random exactly like `mc.iterate`, and a per-trial evaluation must reproduce the reference's S."""
+    import os
+    import circuits
+    import plan_interp as pi
+    from heavi_b200 import plan as pl
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mc_twoport.npz"))
+    m, f, mc = circuits.build_random_twoport(hv)
+    np.random.seed(11)
+    draws = mc.draw(6)
+    assert np.array_equal(draws, g["mc_draws"])
+    plan = pl.compile_plan(m.stamp_table())
+    assert len(plan.table_params) == 4                           # the four S_ij closures are host-tabulated
+    for s in range(6):
+        for r, v in zip(mc._random_numbers, draws[s]):
+            r._value = float(v)
+        S = pi.run_plan(plan, f, mc._random_numbers, draws[s:s + 1])[0]
+        assert np.max(np.abs(S - g["mc_S"][s])) < 1e-11

@@ -240,3 +240,29 @@ def test_frequency_axis_float32_filled_by_the_library():
     assert S.f.dtype == np.float32 and np.array_equal(S.f, f.astype(np.float32))
     S2 = m.run_sp(list(f[:7]))
     assert np.array_equal(S2.f, f[:7].astype(np.float32))
+
+
+def test_monte_carlo_with_sample_dependent_callables_runs_per_trial():
+    """A closure over Random objects (lib/mc.py RandomTwoPort) changes its table from trial to trial: the
+    batched drivers must notice and reproduce the reference's serial loop, seed for seed."""
+    import circuits
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "mc_twoport.npz"))
+    m, f, mc = circuits.build_random_twoport(hv)
+    cn = m._compiled()
+    np.random.seed(11)
+    vals = mc.draw(6)
+    assert cn._tables_follow_drivers(f, mc._random_numbers, vals)
+    np.random.seed(11)
+    stat = m.run_mc(f, mc, 6)
+    S = np.stack(stat._Sdata) if isinstance(stat._Sdata, list) else np.asarray(stat._Sdata)
+    assert S.shape == g["mc_S"].shape and np.max(np.abs(S - g["mc_S"])) < 1e-11
+    np.random.seed(11)
+    mom = m.run_mc_stats(f, mc, 6)
+    for (j, i) in ((1, 1), (2, 1), (1, 2)):
+        ref = np.abs(g["mc_S"][:, j - 1, i - 1, :])
+        assert np.max(np.abs(mom.S(j, i).amplitude_mean - ref.mean(axis=0))) < 1e-11
+        assert np.max(np.abs(mom.S(j, i).amplitude_std - ref.std(axis=0))) < 1e-11
+    # plain Random-valued components (config 4) stay on the batched path
+    m4, f4, mc4 = circuits.build_c4(hv)
+    np.random.seed(7)
+    assert not m4._compiled()._tables_follow_drivers(f4, mc4._random_numbers, mc4.draw(3))
