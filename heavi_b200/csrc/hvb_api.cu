@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -543,6 +544,13 @@ extern "C" int hvb_run_device(hvb_plan* pl, const hvb_run_args* a, double* d_S, 
     return launch(pl, D, st);
 }
 
+// copy a frequency slab into the pinned staging block and, in the same pass over the caller's array,
+// round it to float32 for `Sparameters.f` (network.py:407,421) when the caller asked for that
+static void stage_f(double* __restrict__ dst, const double* __restrict__ src, float* __restrict__ f32, int64_t n) {
+    if (!f32) { memcpy(dst, src, (size_t)n * 8); return; }
+    for (int64_t i = 0; i < n; ++i) { const double v = src[i]; dst[i] = v; f32[i] = (float)v; }
+}
+
 extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, int32_t* status_out) {
     int rc = check_args(pl, a);
     if (rc) return rc;
@@ -555,6 +563,10 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     if (nF == 0 || PP == 0) { if (status_out) *status_out = 0; return HVB_OK; }
     if ((d.n_consts && !a->consts) || (d.n_prefs && !a->prefs)) return fail(HVB_ERR_ARG, "consts/prefs missing");
     cudaStream_t s0 = pl->streams[0], s1 = pl->streams[1];
+    static const bool trace = getenv("HVB_TRACE") != nullptr;
+    timespec tsp[8]; int ntp = 0;
+    auto mark = [&]() { if (trace && ntp < 8) clock_gettime(CLOCK_MONOTONIC, &tsp[ntp++]); };
+    mark();
 
     // ---- tiles: whole samples when several fit in a chunk, else frequency slabs of one sample --------
     // Tile size: large enough for the copy to run at the full PCIe rate (a few MB), small enough that
@@ -611,7 +623,7 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     if (d.n_consts) memcpy(h + off_consts, a->consts, (size_t)d.n_consts * 16);
     if (d.n_prefs) memcpy(h + off_prefs, a->prefs, (size_t)d.n_prefs * 8);
     if (d.n_samples_cols) memcpy(h + off_smp, a->samples, (size_t)nS * d.n_samples_cols * 8);
-    memcpy(h + off_f, a->f, (size_t)f_first * 8);
+    stage_f((double*)(h + off_f), a->f, a->f32_out, f_first);
     CU(cudaMemcpyAsync(pl->inbuf.p, h, off_f + (size_t)f_first * 8, cudaMemcpyHostToDevice, s0));
     if (a->n_tables) {
         CU(pl->tables.ensure((size_t)a->n_tables * nF * 16));
@@ -620,6 +632,7 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     CU(cudaEventRecord(pl->ev_ready, s0));
     CU(cudaStreamWaitEvent(s1, pl->ev_ready, 0));
     char* dbase = (char*)pl->inbuf.p;
+    mark();
 
     const char* c2d = getenv("HVB_COPY2D");
     const bool copy2d = !(c2d && c2d[0] == '0');          // default; 0 = one plain copy per row (measured slower)
@@ -630,7 +643,7 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
             const int64_t nf = std::min(Fc, nF - fb);
             cudaStream_t st = pl->streams[tile & 1];
             if (slab_upload && fb > 0) {
-                memcpy(h + off_f + (size_t)fb * 8, a->f + fb, (size_t)nf * 8);
+                stage_f((double*)(h + off_f) + fb, a->f + fb, a->f32_out ? a->f32_out + fb : nullptr, nf);
                 CU(cudaMemcpyAsync(dbase + off_f + (size_t)fb * 8, h + off_f + (size_t)fb * 8, (size_t)nf * 8,
                                    cudaMemcpyHostToDevice, st));
             }
@@ -665,9 +678,14 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     CU(cudaEventRecord(pl->ev_tail, s1));
     CU(cudaStreamWaitEvent(s0, pl->ev_tail, 0));
     CU(cudaMemcpyAsync(pl->h_status, pl->inbuf.p, 4, cudaMemcpyDeviceToHost, s0));
-    // host work that would otherwise follow the call, done while the GPU is busy
-    if (a->f32_out) for (int64_t i = 0; i < nF; ++i) a->f32_out[i] = (float)a->f[i];
+    mark();
+    mark();
     CU(cudaStreamSynchronize(s0));
+    mark();
+    if (trace) {
+        auto us = [&](int i) { return (tsp[i].tv_sec - tsp[0].tv_sec) * 1e6 + (tsp[i].tv_nsec - tsp[0].tv_nsec) * 1e-3; };
+        fprintf(stderr, "hvb_run_host: staged+H2D queued %.1f us, tiles queued %.1f, synced %.1f (tiles=%d)\n", us(1), us(2), us(4), tile);
+    }
     if (status_out) *status_out = *pl->h_status;
     return HVB_OK;
 }
