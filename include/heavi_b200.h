@@ -106,7 +106,12 @@ typedef struct hvb_run_args {
                                   works; NULL to skip.  Ignored by the other entry points.         */
 } hvb_run_args;
 
-/* Create / destroy.  `device` is a CUDA ordinal.  The plan copies everything in `desc`. */
+/* Create / destroy.  `device` is a CUDA ordinal.  The plan copies everything in `desc`.
+ * The library picks the kernel from the shape and structure of the system: register-resident dense
+ * Gauss-Jordan for n <= 32 (the host pads to a shape hvb_warp_shape returns), banded LU with one
+ * thread per point when the matrix block has a half bandwidth <= 8 in the row order the plan was
+ * compiled with (heavi_b200/plan.py applies a reverse Cuthill-McKee ordering to large netlists),
+ * blocked dense LU otherwise.  Results do not depend on the choice beyond rounding. */
 int  hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan** out);
 void hvb_plan_destroy(hvb_plan* plan);
 
