@@ -65,7 +65,7 @@ struct hvb_plan {
     int32_t* h_status = nullptr;                       // pinned status word
     cudaEvent_t ev_ready = nullptr, ev_tail = nullptr;
     // host pipeline buffers
-    DevBuf f, samples, tables, S[2], status, work[2], dump, stats, inbuf;
+    DevBuf f, samples, tables, S[2], status, work[2], dump, stats, inbuf, f32;
     cudaStream_t streams[2] = {nullptr, nullptr};
     cudaEvent_t upload_done = nullptr;
     // kernel choice
@@ -417,7 +417,7 @@ extern "C" void hvb_plan_destroy(hvb_plan* pl) {
     cudaSetDevice(pl->device);
     DevBuf* all[] = {&pl->const_vals, &pl->ops, &pl->coops, &pl->cell_ptr, &pl->cell_ent, &pl->row_ptr, &pl->row_ent, &pl->fop_code, &pl->fop_out, &pl->fop_arg, &pl->epi_por, &pl->epi_scale, &pl->port_rows, &pl->port_zpref,
                      &pl->spl_t, &pl->spl_c, &pl->spl_trace, &pl->spl_fill, &pl->spl_range, &pl->band_slots, &pl->band_sched_ptr, &pl->band_sched_op, &pl->band_fslot, &pl->band_oslot, &pl->band_ent, &pl->band_act, &pl->consts, &pl->prefs,
-                     &pl->f, &pl->samples, &pl->tables, &pl->S[0], &pl->S[1], &pl->status, &pl->work[0], &pl->work[1], &pl->dump, &pl->stats, &pl->inbuf};
+                     &pl->f, &pl->samples, &pl->tables, &pl->S[0], &pl->S[1], &pl->status, &pl->work[0], &pl->work[1], &pl->f32, &pl->dump, &pl->stats, &pl->inbuf};
     for (DevBuf* b : all) b->release();
     if (pl->h_stage) cudaFreeHost(pl->h_stage);
     if (pl->h_in) cudaFreeHost(pl->h_in);
@@ -544,13 +544,6 @@ extern "C" int hvb_run_device(hvb_plan* pl, const hvb_run_args* a, double* d_S, 
     return launch(pl, D, st);
 }
 
-// copy a frequency slab into the pinned staging block and, in the same pass over the caller's array,
-// round it to float32 for `Sparameters.f` (network.py:407,421) when the caller asked for that
-static void stage_f(double* __restrict__ dst, const double* __restrict__ src, float* __restrict__ f32, int64_t n) {
-    if (!f32) { memcpy(dst, src, (size_t)n * 8); return; }
-    for (int64_t i = 0; i < n; ++i) { const double v = src[i]; dst[i] = v; f32[i] = (float)v; }
-}
-
 extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, int32_t* status_out) {
     int rc = check_args(pl, a);
     if (rc) return rc;
@@ -617,13 +610,14 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
         pl->h_in_bytes = in_bytes + in_bytes / 4 + 4096;
     }
     CU(pl->inbuf.ensure(in_bytes));
+    if (a->f32_out) CU(pl->f32.ensure((size_t)nF * 4));
     char* h = (char*)pl->h_in;                            // free: the previous call waited for all its copies
     const int64_t f_first = slab_upload ? Fc : nF;
     memset(h, 0, 16);
     if (d.n_consts) memcpy(h + off_consts, a->consts, (size_t)d.n_consts * 16);
     if (d.n_prefs) memcpy(h + off_prefs, a->prefs, (size_t)d.n_prefs * 8);
     if (d.n_samples_cols) memcpy(h + off_smp, a->samples, (size_t)nS * d.n_samples_cols * 8);
-    stage_f((double*)(h + off_f), a->f, a->f32_out, f_first);
+    memcpy(h + off_f, a->f, (size_t)f_first * 8);
     CU(cudaMemcpyAsync(pl->inbuf.p, h, off_f + (size_t)f_first * 8, cudaMemcpyHostToDevice, s0));
     if (a->n_tables) {
         CU(pl->tables.ensure((size_t)a->n_tables * nF * 16));
@@ -643,7 +637,7 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
             const int64_t nf = std::min(Fc, nF - fb);
             cudaStream_t st = pl->streams[tile & 1];
             if (slab_upload && fb > 0) {
-                stage_f((double*)(h + off_f) + fb, a->f + fb, a->f32_out ? a->f32_out + fb : nullptr, nf);
+                memcpy(h + off_f + (size_t)fb * 8, a->f + fb, (size_t)nf * 8);
                 CU(cudaMemcpyAsync(dbase + off_f + (size_t)fb * 8, h + off_f + (size_t)fb * 8, (size_t)nf * 8,
                                    cudaMemcpyHostToDevice, st));
             }
@@ -656,8 +650,11 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
             D.pv.tables = a->n_tables ? (const cplx*)pl->tables.p + fb : nullptr;
             D.S = (cplx*)pl->S[tile & 1].p;
             D.status = (int*)pl->inbuf.p;
+            // the points of sample 0 also round their frequency to float32 (`Sparameters.f`, network.py:407,421)
+            D.f32 = (a->f32_out && sb == 0) ? (float*)pl->f32.p + fb : nullptr;
             rc = launch(pl, D, st, tile & 1);
             if (rc) return rc;
+            if (D.f32) CU(cudaMemcpyAsync(a->f32_out + fb, D.f32, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
             // rows of nf elements, one per (sample, j, i); destination pitch is the full nF
             char* dst = (char*)S_out + ((size_t)sb * PP * nF + (size_t)fb) * 16;
             // contiguous destination -> one plain copy; otherwise one strided 2-D copy

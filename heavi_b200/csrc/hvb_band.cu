@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(HVB_BAND_THREADS) hvb_band_kernel(const HvbDev
     for (long long q = t; q < total; q += T) {
         const long long s = q / D.nF, fi = q - s * D.nF;
         const double f = __ldg(D.f + fi);
+        if (D.f32 && s == 0) D.f32[fi] = (float)f;
         const double* __restrict__ srow = D.samples + s * D.nR;
 
         // ---- value program ----------------------------------------------------------------------
@@ -305,6 +306,7 @@ __global__ void __launch_bounds__(HVB_BAND_THREADS, B == 1 ? 5 : B == 2 ? 4 : B 
     for (long long q = t; q < total; q += T) {
         const long long s = q / D.nF, fi = q - s * D.nF;
         const double f = __ldg(D.f + fi);
+        if (D.f32 && s == 0) D.f32[fi] = (float)f;
         const double* __restrict__ srow = D.samples + s * D.nR;
 
         // ---- elimination ----------------------------------------------------------------------------

@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(HVB_BLOCK_THREADS, MINB) hvb_block_kernel(cons
     for (long long q = blockIdx.x; q < total; q += gridDim.x) {
         const long long s = q / D.nF, fi = q - s * D.nF;
         const double f = __ldg(D.f + fi);
+        if (D.f32 && s == 0 && tid == 0) D.f32[fi] = (float)f;
         const double* __restrict__ srow = D.samples + s * D.nR;
         unsigned bad = 0;
         if (tid == 0) sh_bad = 0;

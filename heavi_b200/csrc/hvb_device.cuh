@@ -54,6 +54,7 @@ struct HvbDev {
     const int* port_rows;
     const int* port_zpref;
     cplx* S;
+    float* f32;                             // optional: f rounded to float32, written by sample 0's points
     cplx* W;                                // dense dump / block-kernel / band-kernel workspace
     const int* band_slot_of_row;            // kernel C (fused): solution rows the S epilogue reads -> slot
     int band_nslots, band_min_row;

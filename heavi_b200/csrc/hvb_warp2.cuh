@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(HVB_WARP_THREADS, Warp2Cfg<N, P>::kMinBlocks) 
         const long long qq = active ? q : total - 1;
         const long long s = qq / D.nF, fi = qq - s * D.nF;
         const double f = __ldg(D.f + fi);
+        if (D.f32 && active && s == 0 && gl == 0) D.f32[fi] = (float)f;
         const double* __restrict__ srow = D.samples + s * D.nR;
         unsigned bad = 0;
 

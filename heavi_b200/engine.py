@@ -117,7 +117,8 @@ def pinned_empty(shape, dtype=np.complex128) -> np.ndarray:
     """numpy array on page-locked memory (torch's caching host allocator), so that the D2H of S runs
     at full PCIe rate and asynchronously."""
     import torch
-    tdt = {np.dtype(np.complex128): torch.complex128, np.dtype(np.float64): torch.float64}[np.dtype(dtype)]
+    tdt = {np.dtype(np.complex128): torch.complex128, np.dtype(np.float64): torch.float64,
+           np.dtype(np.float32): torch.float32}[np.dtype(dtype)]
     return torch.empty(tuple(int(x) for x in shape), dtype=tdt, pin_memory=True).numpy()
 
 

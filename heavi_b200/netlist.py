@@ -218,8 +218,9 @@ class Network:
         f64 = np.ascontiguousarray(frequencies, dtype=np.float64)
         # float32 copy of the frequency axis, the reference's quirk (network.py:407,421); float64 holds
         # every float32-representable input exactly, so converting from f64 gives the same values.  The
-        # library fills it in while the GPU works.
-        f32 = np.empty(f64.shape, dtype=np.float32)
+        # kernels produce it and it comes back with the tiles of S.
+        from .engine import pinned_empty
+        f32 = pinned_empty(f64.shape, np.float32) if f64.ndim == 1 else None
         S = compiled.run(f64, f32_out=f32 if f64.ndim == 1 else None)   # [1,P,P,nF] on pinned host memory
         if f64.ndim != 1:
             f32 = f64.astype(np.float32)

@@ -101,9 +101,10 @@ typedef struct hvb_run_args {
     int64_t        nS;
     const double*  tables;     /* [n_tables*nF] complex, row-major; NULL when n_tables == 0     */
     int32_t        n_tables;
-    float*         f32_out;    /* optional HOST [nF]: hvb_run_host also stores f rounded to float32 -- the
-                                  reference's `Sparameters.f` (network.py:407,421) -- while the GPU
-                                  works; NULL to skip.  Ignored by the other entry points.         */
+    float*         f32_out;    /* optional HOST [nF] (page-locked for full overlap): hvb_run_host also
+                                  returns f rounded to float32 -- the reference's `Sparameters.f`
+                                  (network.py:407,421) -- produced by the kernels and copied back tile
+                                  by tile; NULL to skip.  Ignored by the other entry points.       */
 } hvb_run_args;
 
 /* Create / destroy.  `device` is a CUDA ordinal.  The plan copies everything in `desc`.
