@@ -209,9 +209,10 @@ static bool band_kernel_ok(const hvb_plan* pl) {
     if (off && off[0] == '1') return false;
     const char* force = getenv("HVB_FORCE_BLOCK");          // tests: dense block kernel for any shape
     if (force && force[0] == '1') return false;
-    if (pl->band < 0 || d.n_coops != 0) return false;
+    if (pl->band < 0 || d.n_coops != 0 || d.kernel_hint == 1) return false;
     const int B = hvb_band_round_up(pl->band);
     if (B == 0) return false;
+    if (d.kernel_hint == 2) return B <= 4 && 2 * B + 1 <= d.n;   // the host measured / decided: any narrow band
     return 2 * (3 * B + 1) <= d.n;                       // a narrow band, not a small dense block
 }
 
@@ -234,7 +235,8 @@ static int select_kernel(hvb_plan* pl) {
     const void* wk = warp_kernel_ptr(d.n, PP);
     const char* force = getenv("HVB_FORCE_BLOCK");
     const size_t staged = (size_t)(d.n_const_vals + d.n_fast_ops) * 16 + (size_t)(2 * d.n + 1 + d.n_row_ent + 2 * d.n_fast_ops) * 4 + (size_t)d.P * d.P * 8 + 64;
-    if (wk && max_nport <= d.n && staged <= 24576 && !(force && force[0] == '1')) {
+    const bool band_first = d.kernel_hint == 2 && PP == d.P && band_kernel_ok(pl);
+    if (!band_first && wk && max_nport <= d.n && staged <= 24576 && !(force && force[0] == '1')) {
         const int N = d.n;
         const int G = N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32;
         pl->kclass = 0; pl->G = N; pl->PMAX = PP;

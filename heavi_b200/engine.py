@@ -29,7 +29,7 @@ _f64p = C.POINTER(C.c_double)
 class PlanDesc(C.Structure):
     _fields_ = [(k, C.c_int32) for k in (
         "n", "ncols", "P", "n_consts", "n_prefs", "n_const_vals", "n_dyn", "n_ops", "n_coops",
-        "n_samples_cols", "coop_scratch", "n_traces", "n_knots", "n_coefs", "n_row_ent", "n_fast_ops", "epi_simple", "reserved0")] + [
+        "n_samples_cols", "coop_scratch", "n_traces", "n_knots", "n_coefs", "n_row_ent", "n_fast_ops", "epi_simple", "kernel_hint")] + [
         ("const_vals", _f64p), ("ops", _i32p), ("coops", _i32p), ("cell_ptr", _i32p), ("cell_ent", _i32p),
         ("row_ptr", _i32p), ("row_ent", _i32p), ("fop_code", _i32p), ("fop_out", _i32p), ("fop_arg", _f64p),
         ("epi_port_of_row", _i32p), ("epi_scale", _f64p), ("port_rows", _i32p), ("port_zpref", _i32p), ("spl_t", _f64p), ("spl_c", _f64p),
@@ -131,7 +131,8 @@ def _ptr(a: np.ndarray):
 class DevicePlanHandle:
     """Owns one `hvb_plan*`."""
 
-    def __init__(self, plan: pl.DevicePlan, device: int | None = None):
+    def __init__(self, plan: pl.DevicePlan, device: int | None = None, kernel_hint: int = 0):
+        """`kernel_hint`: 0 library decides, 1 dense kernels only, 2 banded kernel when the structure allows."""
         self.lib = load_library()
         self.plan = plan
         self.device = current_device() if device is None else device
@@ -160,6 +161,7 @@ class DevicePlanHandle:
         d.row_ptr = arr("rp", plan.row_ptr, np.int32).ctypes.data_as(_i32p)
         d.row_ent = arr("re", plan.row_ent, np.int32).ctypes.data_as(_i32p)
         d.n_fast_ops, d.epi_simple = len(plan.fop_code), plan.epi_simple
+        d.kernel_hint = int(kernel_hint)
         d.fop_code = arr("fc", plan.fop_code, np.int32).ctypes.data_as(_i32p)
         d.fop_out = arr("fo", plan.fop_out, np.int32).ctypes.data_as(_i32p)
         d.fop_arg = arr("fa", plan.fop_arg, np.float64).ctypes.data_as(_f64p)
@@ -276,7 +278,15 @@ def measure_dfma_peak(device: int | None = None) -> float:
 
 
 class CompiledNetwork:
-    """A frozen `Network`: stamp table + device plan + the library handle."""
+    """A frozen `Network`: stamp table + device plan(s) + the library handle(s).
+
+    Narrow-banded systems that still fit the register kernels (9..32 unknowns) get two variants: the
+    dense register-kernel plan (`plan` / `handle`, the default) and a banded one (`band_plan` /
+    `band_handle`, built on first use).  The banded kernel runs one thread per point, so it wins on
+    large batches -- 2x at 10 unknowns, 7-9x at 24-32 (profiles/README.md) -- and loses on short sweeps
+    to the latency of a single point; `run` picks by the number of points of the call."""
+
+    BAND_MIN_POINTS = 49152          # about half a grid of the banded kernel (148 SMs x 5 CTAs x 128 threads)
 
     def __init__(self, net, mode: str | None = None, device: int | None = None):
         self.table = net.stamp_table()
@@ -286,12 +296,33 @@ class CompiledNetwork:
         if shape is not None and shape != (plan.n, plan.ncols - plan.n):
             plan = pl.compile_plan(self.table, plan.mode, pad_to=shape)
         self.plan = plan
-        self.handle = DevicePlanHandle(self.plan, device)
+        self.handle = DevicePlanHandle(self.plan, device, kernel_hint=1 if shape is not None else 0)
         self.rows_per_lane = self.handle.kernel_info()["rows_per_lane"]
         self._dump = None
+        self._band = None            # (plan, handle) | False once known not to exist
+        if shape is None or os.environ.get("HVB_NO_BAND") == "1" or plan.n_real < pl.BAND_SMALL_MIN_ROWS:
+            self._band = False
 
-    def resolve(self, f, drivers=None, values=None):
-        return pl.resolve_run(self.plan, f, drivers, values)
+    def _band_variant(self):
+        if self._band is None:
+            bplan = pl.compile_plan(self.table, self.plan.mode, order="rcm")
+            if bplan.band < 0 or bplan.band > 4:
+                self._band = False
+            else:
+                handle = DevicePlanHandle(bplan, self.handle.device, kernel_hint=2)
+                self._band = (bplan, handle) if handle.kernel_info()["kernel_class"] == 2 else False
+        return self._band
+
+    def variant(self, points: int):
+        """(plan, handle) that serves a call of `points` (sample, frequency) points."""
+        if self._band is not False and points >= self.BAND_MIN_POINTS:
+            band = self._band_variant()
+            if band:
+                return band
+        return self.plan, self.handle
+
+    def resolve(self, f, drivers=None, values=None, plan=None):
+        return pl.resolve_run(plan or self.plan, f, drivers, values)
 
     def _tables_follow_drivers(self, f: np.ndarray, drivers, values) -> bool:
         """True when a host-tabulated callable reads one of the batch drivers (e.g. a closure over
@@ -332,8 +363,9 @@ class CompiledNetwork:
             if f32_out is not None:
                 f32_out[:] = f
             return S
-        consts, prefs, tables, samples = self.resolve(f, drivers, values)
-        S, status = self.handle.run_host(f, consts, prefs, tables, samples, out, f32_out)
+        plan, handle = self.variant(len(f) * (1 if values is None else len(values)))
+        consts, prefs, tables, samples = self.resolve(f, drivers, values, plan)
+        S, status = handle.run_host(f, consts, prefs, tables, samples, out, f32_out)
         if status & HVB_STATUS_NONFINITE:
             # the reference's numba lstsq raises for NaN/Inf input
             raise np.linalg.LinAlgError("MNA matrix or S-parameters contain NaN/Inf (e.g. f = 0 with an inductor)")
@@ -358,8 +390,9 @@ class CompiledNetwork:
             pw = a ** 2
             return np.stack([a.mean(axis=0), a.std(axis=0), pw.mean(axis=0), pw.std(axis=0),
                              np.sqrt(pw).mean(axis=0), np.sqrt(pw).std(axis=0)])
-        consts, prefs, tables, samples = self.resolve(f, drivers, values)
-        out, status = self.handle.run_stats_host(f, consts, prefs, tables, samples)
+        plan, handle = self.variant(len(f) * len(values))
+        consts, prefs, tables, samples = self.resolve(f, drivers, values, plan)
+        out, status = handle.run_stats_host(f, consts, prefs, tables, samples)
         self._raise_for_status(status)
         return out
 

@@ -354,10 +354,11 @@ def norton_legal(table: StampTable) -> bool:
 
 
 BAND_MIN_ROWS = 33        # systems the register-resident kernels cannot hold
+BAND_SMALL_MIN_ROWS = 9   # from here on the banded kernel beats the register kernels on large batches
 BAND_MAX_HALF_WIDTH = 8   # widest band the banded kernel is instantiated for
 
 
-def _band_order(table: StampTable, rowmap: np.ndarray, mode: str):
+def _band_order(table: StampTable, rowmap: np.ndarray, mode: str, small: bool = False):
     """Reverse Cuthill-McKee ordering of the system rows (a symmetric permutation of the unknowns,
     which leaves S unchanged).  Returns (new rowmap, half bandwidth) or None when the structure
     is not narrow-banded.  Chains -- ladders, cascaded lines, filters -- come out tri-/penta-diagonal."""
@@ -385,7 +386,9 @@ def _band_order(table: StampTable, rowmap: np.ndarray, mode: str):
     natural = int(np.abs(coo.row - coo.col).max())
     if natural <= band:                                 # the netlist was already written as a chain
         pos, band = np.arange(n, dtype=np.int64), natural
-    if band > BAND_MAX_HALF_WIDTH or 2 * (3 * band + 1) > n:
+    # a narrow band, not a small dense block; `small` (order="rcm" asked for explicitly) only needs the band
+    # to be narrower than the matrix
+    if band > BAND_MAX_HALF_WIDTH or (2 * band + 1 > n if small else 2 * (3 * band + 1) > n):
         return None
     new = rowmap.copy()
     live = rowmap >= 0
@@ -428,7 +431,7 @@ def compile_plan(table: StampTable, mode: str = "auto", pad_to: tuple[int, int] 
     band = -1
     if mode != "dump" and pad_to is None and (order == "rcm" or (order == "auto" and n_real >= BAND_MIN_ROWS)):
         if not any(k in ("nport_s", "nport_y") for k in table.kinds):
-            res = _band_order(table, rowmap, mode)
+            res = _band_order(table, rowmap, mode, small=(order == "rcm"))
             if res is not None:
                 rowmap, band = res
     n, n_rhs = n_real, (0 if mode == "dump" else P)

@@ -66,7 +66,10 @@ typedef struct hvb_plan_desc {
     int32_t n_row_ent;     /* entries of the per-row lists                                      */
     int32_t n_fast_ops;    /* value ops with a real-constant / plain-sample argument            */
     int32_t epi_simple;    /* 1: closed-form epilogue S_ji = (2 V_sig_j - d_ij) sqrt(Zi/Zj)     */
-    int32_t reserved0;     /* keeps the pointer block 8-byte aligned                            */
+    int32_t kernel_hint;   /* 0 = library decides (banded kernel from 33 unknowns on when the
+                              structure allows), 1 = dense kernels only, 2 = banded kernel whenever
+                              the structure allows (what the host asks for on large batches of
+                              narrow-banded systems with 9..32 unknowns)                        */
     const double*  const_vals; /* [n_const_vals] complex                                        */
     const int32_t* ops;        /* [n_ops*8]                                                     */
     const int32_t* coops;      /* [n_coops*8]                                                   */

@@ -139,3 +139,42 @@ def test_two_pipeline_slots_do_not_share_a_workspace(band):
         os.environ.pop("HVB_CHUNK_MB")
     idx = np.unique(np.concatenate([np.arange(0, 140_000, 1511), np.arange(65_400, 65_700), np.arange(69_900, 70_100)]))
     assert np.array_equal(S[..., idx], cn.run(f[idx])[0])
+
+
+def test_mid_size_banded_system_switches_kernel_with_the_batch_size():
+    """9..32 unknowns, narrow band: short sweeps stay on the register kernel (lowest latency), large
+    batches go to the banded kernel (one thread per point: 2-9x the throughput); same S either way."""
+    import heavi_b200 as hv
+    from heavi_b200.engine import CompiledNetwork
+    m, _ = circuits.build_band_ladder(hv, K=19, reach=1, nports=2, seed=21)
+    cn = CompiledNetwork(m)
+    assert cn.plan.n_real == 20 and cn.handle.kernel_info()["kernel_class"] == 0
+    f_small = np.linspace(0.5e9, 6e9, 501)
+    S_small = cn.run(f_small)[0]
+    assert cn._band is None                                   # banded variant not even built yet
+    f_big = np.linspace(0.5e9, 6e9, CompiledNetwork.BAND_MIN_POINTS + 17)
+    S_big = cn.run(f_big)[0]
+    assert cn._band and cn._band[1].kernel_info()["kernel_class"] == 2 and cn._band[0].band == 1
+    # the same frequencies through both kernels
+    idx = np.linspace(0, len(f_big) - 1, 301).astype(int)
+    S_dense = cn.handle.run_host(f_big[idx], *cn.resolve(f_big[idx]))[0][0]
+    assert _close(S_big[..., idx], S_dense)
+    from oracle import mna_oracle as orc
+    So = orc.run_sp(m.records(), m.n_nodes, len(m.sources), f_small, method="lu_batched")
+    assert _close(S_small, So)
+    # Monte-Carlo batches count samples x frequencies
+    mc = hv.MonteCarlo()
+    m2 = hv.Model(suppress_loadbar=True)
+    chain = [m2.node() for _ in range(12)]
+    m2.new_port(50, chain[0]); m2.new_port(50, chain[11])
+    for k in range(11):
+        m2.inductor(chain[k], chain[k + 1], mc.gaussian(2e-9, 1e-10))
+        m2.capacitor(chain[k + 1], m2.gnd, mc.gaussian(1e-12, 5e-14))
+    f = np.linspace(1e9, 3e9, 257)
+    np.random.seed(3)
+    vals = mc.draw(200)                                         # 51 400 points
+    cn2 = m2._compiled()
+    Sb = cn2.run(f, mc._random_numbers, vals)
+    assert cn2._band and Sb.shape == (200, 2, 2, 257)
+    Sd = cn2.handle.run_host(f, *cn2.resolve(f, mc._random_numbers, vals[:5]))[0]
+    assert _close(Sb[:5], Sd)
