@@ -466,8 +466,11 @@ static HvbDev make_dev(const hvb_plan* pl) {
     D.band_slot_of_row = (const int*)pl->band_slots.p;
     D.band_nslots = pl->band_nslots; D.band_min_row = pl->band_min_row;
     {
+        // records of small systems stay in the L2 (every thread rewrites the same words point after point):
+        // prefetching them only costs issue slots
         const char* b = getenv("HVB_BAND_PFB");
-        D.band_pfb = b ? atoi(b) : 2;
+        const size_t footprint = (size_t)pl->band_rec_words * sizeof(cplx) * (size_t)pl->max_grid * pl->threads;
+        D.band_pfb = b ? atoi(b) : (footprint > ((size_t)48 << 20) ? 2 : 0);
     }
     D.band_nsm = pl->band_nsm;
     D.band_sched_ptr = (const int*)pl->band_sched_ptr.p;

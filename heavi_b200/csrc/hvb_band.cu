@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(HVB_BAND_THREADS, B == 1 ? 5 : B == 2 ? 4 : B 
                 for (int e = 0; e < rs; ++e, pe += T) asm volatile("prefetch.global.L2 [%0];" ::"l"(pe));
             }
             for (int k = n - 1; k >= D.band_min_row; --k) {
-                if (kp >= D.band_min_row) {
+                if (D.band_pfb > 0 && kp >= D.band_min_row) {
                     const int rs = WD + __ldg(D.band_act + kp);
                     pp -= rs * T;
                     const cplx* __restrict__ pe = pp;
