@@ -344,8 +344,11 @@ class CompiledNetwork:
                 d._value = v
         return any(not np.array_equal(a, b) for other in rows[1:] for a, b in zip(rows[0], other))
 
-    def run(self, f: np.ndarray, drivers=None, values=None, out=None, f32_out=None) -> np.ndarray:
-        """S[nS,P,P,nF] complex128 on pinned host memory."""
+    def run(self, f: np.ndarray, drivers=None, values=None, out=None, f32_out=None,
+            batch_points: int | None = None) -> np.ndarray:
+        """S[nS,P,P,nF] complex128 on pinned host memory.  `batch_points`: size of the whole job when this
+        call is one shard of it, so that every shard picks the same kernel variant (and the result does
+        not depend on how the job was cut)."""
         if drivers is not None and self._tables_follow_drivers(f, drivers, values):
             # sample-dependent callables: one run per sample with the drivers set, like the reference's loop
             values = np.asarray(values, dtype=np.float64)
@@ -363,7 +366,8 @@ class CompiledNetwork:
             if f32_out is not None:
                 f32_out[:] = f
             return S
-        plan, handle = self.variant(len(f) * (1 if values is None else len(values)))
+        points = len(f) * (1 if values is None else len(values))
+        plan, handle = self.variant(points if batch_points is None else batch_points)
         consts, prefs, tables, samples = self.resolve(f, drivers, values, plan)
         S, status = handle.run_host(f, consts, prefs, tables, samples, out, f32_out)
         if status & HVB_STATUS_NONFINITE:

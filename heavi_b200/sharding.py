@@ -100,7 +100,8 @@ def run_sp_distributed(net, frequencies, drivers=None, values=None, group=None, 
     nS = 1 if values is None else int(np.asarray(values).shape[0])
 
     def compute(fb, vb):
-        return compiled.run(fb, drivers=drivers, values=vb)
+        # every rank picks the kernel variant from the size of the WHOLE job: bit-identical for any world size
+        return compiled.run(fb, drivers=drivers, values=vb, batch_points=nS * f.shape[0])
 
     sh, blk = run_sharded(compute, f, values, world, rank)
     return gather_to_root(blk, sh, nS, f.shape[0], group=group, dst=dst)

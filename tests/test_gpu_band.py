@@ -178,3 +178,18 @@ def test_mid_size_banded_system_switches_kernel_with_the_batch_size():
     assert cn2._band and Sb.shape == (200, 2, 2, 257)
     Sd = cn2.handle.run_host(f, *cn2.resolve(f, mc._random_numbers, vals[:5]))[0]
     assert _close(Sb[:5], Sd)
+
+
+def test_sharded_run_of_a_mid_size_banded_system_is_bit_identical():
+    """Each shard of a distributed run is told the size of the whole job, so all of them use the kernel
+    variant the single-GPU run uses and the pieces concatenate to exactly the same S."""
+    import heavi_b200 as hv
+    from heavi_b200 import sharding as sh
+    m, _ = circuits.build_band_ladder(hv, K=15, reach=1, nports=2, seed=4)
+    cn = m._compiled()
+    f = np.linspace(0.5e9, 6e9, cn.BAND_MIN_POINTS + 1000)
+    whole = cn.run(f)[0].copy()
+    assert cn._band                                            # the whole job is large enough for the banded kernel
+    for world in (2, 8):                                       # each shard alone would be below the threshold
+        parts = [sh.run_sharded(lambda fb, vb: cn.run(fb, batch_points=len(f)).copy(), f, None, world, r) for r in range(world)]
+        assert np.array_equal(np.concatenate([p[1] for p in parts], axis=3)[0], whole)
