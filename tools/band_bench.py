@@ -11,6 +11,8 @@ reach, K, nports, pts = (int(x) for x in sys.argv[1:5])
 m, _ = circuits.build_band_ladder(hv, K=K, reach=reach, nports=nports, seed=3)
 f = np.linspace(0.5e9, 6e9, pts)
 cn = CompiledNetwork(m)
+if os.environ.get("HVB_BAND_VARIANT") == "1" and cn._band is not False and cn._band_variant():
+    cn.plan, cn.handle = cn._band_variant()          # time the banded variant of a 9..32-unknown system
 consts, prefs, tables, samples = cn.resolve(f)
 dev = torch.device("cuda", 0)
 d_f = torch.from_numpy(f).to(dev); d_smp = torch.from_numpy(samples).to(dev)
@@ -22,6 +24,6 @@ for _ in range(4):
     a.record(); cn.handle.run_device(d_f, consts, prefs, None, d_smp, d_S, d_st); b.record(); torch.cuda.synchronize()
     ms.append(a.elapsed_time(b))
 ki = cn.handle.kernel_info()
-print("reach %d n=%d band=%d P=%d V=%s fused=%s: class %d B=%d thr=%d regs=%d ctas=%d smem=%d -> %.3f ms, %.3e solves/s" % (
-    reach, cn.plan.n, cn.plan.band, cn.plan.P, os.environ.get("HVB_BAND_V"), os.environ.get("HVB_BAND_FUSED"), ki["kernel_class"], ki["group"], ki["threads"], ki["regs"],
+print("reach %d n=%d band=%d P=%d fused=%s: class %d B=%d thr=%d regs=%d ctas=%d smem=%d -> %.3f ms, %.3e solves/s" % (
+    reach, cn.plan.n, cn.plan.band, cn.plan.P, os.environ.get("HVB_BAND_FUSED"), ki["kernel_class"], ki["group"], ki["threads"], ki["regs"],
     ki["ctas_per_sm"], ki["smem_bytes"], min(ms), pts / (min(ms) * 1e-3)))
