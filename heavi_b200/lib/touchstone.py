@@ -64,6 +64,28 @@ class SplineTrace:
                 int(spl.k))
 
 
+def renormalize_s(sdata: np.ndarray, z_old: float, z_new: float) -> np.ndarray:
+    """S[nf, P, P] referenced to `z_old` -> referenced to `z_new` (both real, equal on all ports):
+    S' = A^-1 (S - R)(I - R S)^-1 A with A = sqrt(z_new / z_old) / (z_new + z_old) I and
+    R = (z_new - z_old)/(z_new + z_old) I, the transform of touchstone.py:233-251."""
+    P = sdata.shape[1]
+    eye = np.eye(P, P)
+    A = eye * np.sqrt(z_new / z_old) * (1 / (z_new + z_old))
+    R = eye * ((z_new - z_old) / (z_new + z_old))
+    iA = np.linalg.pinv(A)
+    out = np.empty_like(sdata)
+    for k in range(sdata.shape[0]):
+        S = sdata[k, :, :]
+        out[k, :, :] = iA @ (S - R) @ np.linalg.pinv(eye - R @ S) @ A
+    return out
+
+
+def spline_traces(fdata: np.ndarray, sdata: np.ndarray, kind: str):
+    """P x P nested list of `SplineTrace`s, one per S_ij(f)."""
+    P = sdata.shape[1]
+    return [[SplineTrace(fdata, sdata[:, i, j], kind) for j in range(P)] for i in range(P)]
+
+
 class FileBasedNPort(SubCircuit):
     """N-port defined by a Touchstone file.  `connect(n1, ..., nP)` stamps it."""
 
@@ -151,20 +173,11 @@ class FileBasedNPort(SubCircuit):
 
     def renormalize(self, new_impedance: float) -> "FileBasedNPort":
         """Re-reference the S data to a new real impedance (touchstone.py:233-251)."""
-        z_old, z_new = self.refimp, new_impedance
-        P = self.n_ports
-        A = np.eye(P, P) * np.sqrt(z_new / z_old) * (1 / (z_new + z_old))
-        R = np.eye(P, P) * ((z_new - z_old) / (z_new + z_old))
-        iA = np.linalg.pinv(A)
-        E = np.eye(P, P)
-        for k in range(self.n_frequencies):
-            S = self.Sdata[k, :, :]
-            self.Sdata[k, :, :] = iA @ (S - R) @ np.linalg.pinv(E - R @ S) @ A
+        self.Sdata = renormalize_s(self.Sdata, self.refimp, new_impedance)
         self.refimp = new_impedance
         return self
 
     def __on_connect__(self):
-        traces = [[SplineTrace(self.Fdata, self.Sdata[:, i, j], self.interp_type) for j in range(self.n_ports)]
-                  for i in range(self.n_ports)]
-        self.network.n_port_S(self.network.gnd, [self.nodes[i] for i in range(1, self.n_ports + 1)],
-                              traces, self.refimp)
+        terminals = [self.nodes[i] for i in range(1, self.n_ports + 1)]
+        self.network.n_port_S(self.network.gnd, terminals, spline_traces(self.Fdata, self.Sdata, self.interp_type),
+                              self.refimp)
