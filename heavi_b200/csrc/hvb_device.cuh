@@ -212,6 +212,31 @@ static __device__ __noinline__ cplx spline_eval(const double* __restrict__ spl_t
 }
 
 // ------------------------------------------------------------------------------------------------
+// Surface-mount part with package parasitics (heavi_b200/lib/smd.py, reference lib/smd.py:103-294),
+// numpy's operation order: w = 2 pi f, zs = a + j w b, zc = 1 / (j w c), then
+//   kind 0 resistor   zs * zc / (zs + zc)
+//   kind 1 inductor   1 / (1 / zs + 1 / zc)
+//   kind 2 capacitor  zs + zc
+// and Function.__call__'s nan_to_num (NaN -> 0).
+// ------------------------------------------------------------------------------------------------
+static __device__ __noinline__ cplx eval_smd(const cplx* __restrict__ k, double f) {
+    const int kind = (int)k[0].x;
+    const double w = __dmul_rn(HVB_TWOPI, f);
+    const cplx one = cmk(1.0, 0.0);
+    const cplx zs = cmk(k[1].x, __dmul_rn(w, k[2].x));
+    const cplx zc = cdiv_np(one, cmk(0.0, __dmul_rn(w, k[3].x)));
+    cplx z;
+    if (kind == 0) z = cdiv_np(cmul_np(zs, zc), cmk(__dadd_rn(zs.x, zc.x), __dadd_rn(zs.y, zc.y)));
+    else if (kind == 1) {
+        const cplx y1 = cdiv_np(one, zs), y2 = cdiv_np(one, zc);
+        z = cdiv_np(one, cmk(__dadd_rn(y1.x, y2.x), __dadd_rn(y1.y, y2.y)));
+    } else z = cmk(__dadd_rn(zs.x, zc.x), __dadd_rn(zs.y, zc.y));
+    if (z.x != z.x) z.x = 0.0;
+    if (z.y != z.y) z.y = 0.0;
+    return z;
+}
+
+// ------------------------------------------------------------------------------------------------
 // parameter reference -> complex value at (f, sample row, frequency index)
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ cplx eval_param(const ParamView& D, int pi, double f, long long fi,
@@ -224,6 +249,7 @@ __device__ __forceinline__ cplx eval_param(const ParamView& D, int pi, double f,
         case PK_SAMPLE_INV: return cmk(1.0 / srow[pr.y], 0.0);
         case PK_TABLE: return D.tables[(long long)pr.y * D.table_ld + fi];
         case PK_SPLINE: return spline_eval(D.spl_t, D.spl_c, D.spl_trace, D.spl_fill, D.spl_range, pr.y, f);
+        case PK_SMD: return eval_smd(D.consts + pr.y, f);
         case PK_BETA: {
             // TWOPI * f / c0 * sqrt(er)   (network.py:627-631), left to right
             const double b0 = __dmul_rn(HVB_TWOPI, f) / HVB_C0;

@@ -10,6 +10,7 @@
 #define PK_SAMPLE_INV 3
 #define PK_TABLE 4
 #define PK_SPLINE 5
+#define PK_SMD 7         /* SMD part with parasitics: consts[idx..idx+3] = kind, a, b, c (params.py SMDImpedance) */
 #define PK_BETA 6        /* (2 pi f / c0) * consts[idx], consts[idx] = sqrt(er) taken by the plan compiler */
 
 /* simple value ops (8 int32 words: code, out, p0, p1, p2, p3, aux0, aux1) */

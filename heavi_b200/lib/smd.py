@@ -8,6 +8,7 @@ from __future__ import annotations
 import math
 from enum import Enum
 
+from ..params import SMDImpedance
 from .libgen import TwoNodeSubCircuit
 
 
@@ -70,7 +71,8 @@ class SMDResistor(_SMDPart):
             Zl = 1j * w * self.inductance
             Zc = 1 / (1j * w * self.capacitance)
             return (Zr + Zl) * Zc / (Zr + Zl + Zc)
-        self._stamp(z_parasitic, self.resistance, inductance=self.inductance, capacitance=self.capacitance)
+        z = SMDImpedance(0, self.resistance, self.inductance, self.capacitance, z_parasitic)
+        self._stamp(z, self.resistance, inductance=self.inductance, capacitance=self.capacitance)
 
 
 class SMDInductor(_SMDPart):
@@ -91,7 +93,8 @@ class SMDInductor(_SMDPart):
             z_series = self.esr + 1j * w * self.inductance
             z_parallel_cap = 1 / (1j * w * self.parallel_capacitance)
             return 1 / (1 / (z_series) + 1 / (z_parallel_cap))
-        self._stamp(z_parasitic, self.inductance, esr=self.esr, parallel_capacitance=self.parallel_capacitance)
+        z = SMDImpedance(1, self.esr, self.inductance, self.parallel_capacitance, z_parasitic)
+        self._stamp(z, self.inductance, esr=self.esr, parallel_capacitance=self.parallel_capacitance)
 
 
 class SMDCapacitor(_SMDPart):
@@ -112,4 +115,5 @@ class SMDCapacitor(_SMDPart):
             z_series = self.esr + 1j * w * self.esl
             z_c = 1 / (1j * w * self.capacitance)
             return z_series + z_c
-        self._stamp(z_parasitic, self.capacitance, esr=self.esr, esl=self.esl)
+        z = SMDImpedance(2, self.esr, self.esl, self.capacitance, z_parasitic)
+        self._stamp(z, self.capacitance, esr=self.esr, esl=self.esl)

@@ -177,6 +177,26 @@ class PhaseConstant(Function):
         return ("table", self)
 
 
+class SMDImpedance(Function):
+    """Z(f) of a surface-mount part with its package parasitics (lib/smd.py:103-294 in the reference).
+    Still a plain callable of f -- `function` is the part's own formula -- but it also tells the plan
+    compiler which closed form it is, so the device evaluates it per point instead of the host
+    tabulating it per run:
+        kind 0 (resistor)   (a + j w b) * Zc / (a + j w b + Zc),  Zc = 1 / (j w c)     a = R, b = L, c = C
+        kind 1 (inductor)   1 / (1 / (a + j w b) + 1 / (1 / (j w c)))                  a = ESR, b = L, c = Cpar
+        kind 2 (capacitor)  a + j w b + 1 / (j w c)                                    a = ESR, b = ESL, c = C
+    with w = 2 pi f."""
+
+    def __init__(self, kind: int, a: float, b: float, c: float, function: Callable):
+        super().__init__(function)
+        self.kind, self.abc = int(kind), (float(a), float(b), float(c))
+
+    def describe(self):
+        if np.isinf(self._inf):
+            return ("smd", self.kind, self.abc)
+        return ("table", self)
+
+
 class _Drawn(SimParam):
     """Shared part of Random and Param: a scalar `_value` that a driver mutates between runs."""
 

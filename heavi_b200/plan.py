@@ -32,7 +32,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 # ---- constants shared with csrc/plan_format.h (keep in sync) -------------------------------------
-PK_CONST, PK_SAMPLE, PK_SAMPLE_NEG, PK_SAMPLE_INV, PK_TABLE, PK_SPLINE, PK_BETA = range(7)
+PK_CONST, PK_SAMPLE, PK_SAMPLE_NEG, PK_SAMPLE_INV, PK_TABLE, PK_SPLINE, PK_BETA, PK_SMD = range(8)
 OP_COPY, OP_RECIP, OP_CAP, OP_IND, OP_TLINE = range(5)
 COOP_NPORT_S, COOP_NPORT_Y = 0, 1
 OP_WORDS = 8          # int32 words per simple op
@@ -209,6 +209,12 @@ class _Builder:
             return self.pref(PK_BETA, self.const(complex(root))), d
         if tag == "spline":
             return self.pref(PK_SPLINE, self.add_spline(d[1])), d
+        if tag == "smd":
+            # closed form of a surface-mount part: four consecutive constants [kind, a, b, c]
+            first = self.const(float(d[1]))
+            for v in d[2]:
+                self.const(float(v))
+            return self.pref(PK_SMD, first), d
         # generic callable: tabulated per run
         fn = d[1]
         slot = self.const(0.0)

@@ -61,6 +61,13 @@ class Interp:
             root = self.consts[idx]                      # sqrt(er), taken by the plan compiler
             root = root.real if root.imag == 0 else root
             return _TWOPI * f / _C0 * (root * one)
+        if kind == pl.PK_SMD:
+            sub, a, b, c = (self.consts[idx + i].real for i in range(4))
+            w = 2 * 3.141592653589793 * f
+            zs = a + 1j * w * b
+            zc = 1 / (1j * w * c)
+            z = (zs * zc / (zs + zc)) if sub == 0 else (1 / (1 / zs + 1 / zc)) if sub == 1 else (zs + zc)
+            return np.nan_to_num(z, posinf=np.inf, neginf=-np.inf)
         if kind == pl.PK_SPLINE:
             t_off, nt, c_off, k = self.p.spl_trace[idx]
             t = self.p.spl_t[t_off:t_off + nt]

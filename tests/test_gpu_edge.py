@@ -266,3 +266,18 @@ def test_monte_carlo_with_sample_dependent_callables_runs_per_trial():
     m4, f4, mc4 = circuits.build_c4(hv)
     np.random.seed(7)
     assert not m4._compiled()._tables_follow_drivers(f4, mc4._random_numbers, mc4.draw(3))
+
+
+def test_smd_parts_are_evaluated_on_the_device():
+    """Surface-mount models (resistor, inductor, capacitor with package parasitics) are closed forms on the
+    device: assembled stamps within a few ulp of the host's numpy evaluation, S equal to the oracle."""
+    from test_plan import _smd_model
+    from helpers import max_ulps
+    m = _smd_model()
+    cn = m._compiled()
+    assert len(cn.plan.table_params) == 0
+    f = np.linspace(0.3e9, 7e9, 57)
+    Y = cn.assemble(f)
+    Yo = orc.assemble(m.records(), m.n_nodes + len(m.sources), f)
+    assert np.array_equal(Y != 0, Yo != 0) and max_ulps(Y, Yo) <= 4.0
+    assert np.max(np.abs(m.run_sp(f)._S - oracle_S(m, f))) < TOL

@@ -188,3 +188,40 @@ def test_band_ordering_skips_dense_and_small_systems():
     assert c5.band == 1 and c5.n_real == 191 and _half_bandwidth(c5) == 1
     with pytest.raises(ValueError):
         pl.compile_plan(REG["c5_ladder"]().stamp_table(), order="nearest")
+
+
+def _smd_model():
+    """All three surface-mount models in one two-port network."""
+    from heavi_b200.lib import smd
+    m = hv.Model(suppress_loadbar=True)
+    a, b = m.quick_port(50), m.quick_port(75)
+    n1, n2 = m.node(), m.node()
+    smd.SMDInductor(3.3e-9, smd.SMDInductorSize.L0402).connect(a, n1)
+    smd.SMDCapacitor(1.8e-12, smd.SMDCapacitorSize.C0603).connect(n1, m.gnd)
+    smd.SMDResistor(22.0, smd.SMDResistorSize.R0402).connect(n1, n2)
+    smd.SMDCapacitor(4.7e-12, smd.SMDCapacitorSize.C0402).connect(n2, b)
+    smd.SMDInductor(10e-9, smd.SMDInductorSize.L0603).connect(b, m.gnd)
+    return m
+
+
+def test_smd_closed_forms_are_compiled_not_tabulated():
+    """lib/smd.py parts describe themselves as closed forms (PK_SMD): nothing is tabulated on the host, and
+    the interpreter's / device's formula reproduces the part's own callable bit for bit."""
+    from oracle import mna_oracle as orc
+    m = _smd_model()
+    tab = m.stamp_table()
+    f = np.linspace(0.3e9, 7e9, 23)
+    for mode in ("dump", "full", "norton"):
+        p = pl.compile_plan(tab, mode)
+        assert len(p.table_params) == 0 and sum(int(k) == pl.PK_SMD for k, _ in p.prefs) == 5
+    W = pi.dump_plan(pl.compile_plan(tab, "dump"), f)
+    Y = orc.assemble(m.records(), m.n_nodes + len(m.sources), f)
+    assert np.array_equal(W, Y)                                   # same numpy arithmetic, same bits
+    S = pi.run_plan(pl.compile_plan(tab), f)[0]
+    So = orc.run_sp(m.records(), m.n_nodes, len(m.sources), f, method="lu_batched")
+    assert np.max(np.abs(S - So)) < 1e-13
+    # a finite `inf` clamp is not part of the closed form: such a parameter falls back to a table
+    from heavi_b200.params import SMDImpedance
+    z = SMDImpedance(2, 0.1, 0.5e-9, 1e-12, lambda fr: 0.1 + 1j * fr)
+    z._inf = 1e30
+    assert z.describe()[0] == "table"
