@@ -250,6 +250,7 @@ __device__ __forceinline__ cplx eval_param(const ParamView& D, int pi, double f,
         case PK_TABLE: return D.tables[(long long)pr.y * D.table_ld + fi];
         case PK_SPLINE: return spline_eval(D.spl_t, D.spl_c, D.spl_trace, D.spl_fill, D.spl_range, pr.y, f);
         case PK_SMD: return eval_smd(D.consts + pr.y, f);
+        case PK_BETA_MUL: return cmk(__dmul_rn(__dmul_rn(HVB_TWOPI, f), D.consts[pr.y].x) / HVB_C0, 0.0);
         case PK_BETA: {
             // TWOPI * f / c0 * sqrt(er)   (network.py:627-631), left to right
             const double b0 = __dmul_rn(HVB_TWOPI, f) / HVB_C0;

@@ -10,6 +10,7 @@
 #define PK_SAMPLE_INV 3
 #define PK_TABLE 4
 #define PK_SPLINE 5
+#define PK_BETA_MUL 8    /* ((2 pi f) * consts[idx]) / c0, consts[idx] = sqrt(er): lib/tl.py's order (params.py LinePhase) */
 #define PK_SMD 7         /* SMD part with parasitics: consts[idx..idx+3] = kind, a, b, c (params.py SMDImpedance) */
 #define PK_BETA 6        /* (2 pi f / c0) * consts[idx], consts[idx] = sqrt(er) taken by the plan compiler */
 

@@ -11,6 +11,7 @@ import math
 import numpy as np
 
 from ..filters import impedance_transformer_cheb
+from ..params import LinePhase, PhaseConstant, enforce_simparam
 from .libgen import FourNodeSubCircuit, ThreeNodeSubCircuit, TwoNodeSubCircuit
 
 _C0 = 299792458
@@ -35,12 +36,8 @@ class _ArmTable:
         self.Z0, self.fc, self.er = Z0, fc, er
 
     def __on_connect__(self):
-        er = self.er
-        unit = _quarter_wave(self.fc, er)
-
-        def beta(f):
-            return 2 * np.pi * f * np.sqrt(er) / (_C0)
-
+        unit = _quarter_wave(self.fc, self.er)
+        beta = LinePhase(self.er)                 # one object for all arms: evaluated once, closed form on the device
         net = self.network
         for a, b, quarters, mul, div in self.ARMS:
             net.TL(self.node(a), self.node(b), beta, quarters * unit, self.Z0 * mul / div)
@@ -102,5 +99,6 @@ class Transformer(TwoNodeSubCircuit):
         length = _quarter_wave(self.fc, self.er)
         inner = [self.network.node() for _ in range(self.N_sections - 1)]
         stops = [self.node(1), *inner, self.node(2)]
+        beta = PhaseConstant(enforce_simparam(self.er))          # 2 pi f / c0 * sqrt(er), the reference's order here
         for left, right, z0 in zip(stops, stops[1:], sections):
-            self.network.TL(left, right, lambda f: 2 * np.pi * f / _C0 * np.sqrt(self.er), length, float(z0))
+            self.network.TL(left, right, beta, length, float(z0))

@@ -177,6 +177,23 @@ class PhaseConstant(Function):
         return ("table", self)
 
 
+class LinePhase(Function):
+    """beta(f) = 2 pi f sqrt(er) / c0 in the operation order of the reference's coupler library
+    (lib/tl.py: `2*np.pi*f*np.sqrt(er)/(299792458)`, i.e. ((2 pi f) sqrt(er)) / c0 -- not the order of
+    `Network.transmissionline`, see PhaseConstant).  Callable like any Function; a real, positive `er`
+    is also a closed form for the device."""
+
+    def __init__(self, er: float):
+        self.er = er
+        super().__init__(lambda f: 2 * np.pi * f * np.sqrt(er) / (_C0))
+
+    def describe(self):
+        er = self.er
+        if isinstance(er, (int, float, np.integer, np.floating)) and er > 0 and np.isinf(self._inf):
+            return ("beta_mul", float(np.sqrt(er)))
+        return ("table", self)
+
+
 class SMDImpedance(Function):
     """Z(f) of a surface-mount part with its package parasitics (lib/smd.py:103-294 in the reference).
     Still a plain callable of f -- `function` is the part's own formula -- but it also tells the plan

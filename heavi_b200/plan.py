@@ -32,7 +32,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 # ---- constants shared with csrc/plan_format.h (keep in sync) -------------------------------------
-PK_CONST, PK_SAMPLE, PK_SAMPLE_NEG, PK_SAMPLE_INV, PK_TABLE, PK_SPLINE, PK_BETA, PK_SMD = range(8)
+PK_CONST, PK_SAMPLE, PK_SAMPLE_NEG, PK_SAMPLE_INV, PK_TABLE, PK_SPLINE, PK_BETA, PK_SMD, PK_BETA_MUL = range(9)
 OP_COPY, OP_RECIP, OP_CAP, OP_IND, OP_TLINE = range(5)
 COOP_NPORT_S, COOP_NPORT_Y = 0, 1
 OP_WORDS = 8          # int32 words per simple op
@@ -209,6 +209,8 @@ class _Builder:
             return self.pref(PK_BETA, self.const(complex(root))), d
         if tag == "spline":
             return self.pref(PK_SPLINE, self.add_spline(d[1])), d
+        if tag == "beta_mul":
+            return self.pref(PK_BETA_MUL, self.const(float(d[1]))), d
         if tag == "smd":
             # closed form of a surface-mount part: four consecutive constants [kind, a, b, c]
             first = self.const(float(d[1]))
@@ -613,16 +615,26 @@ def resolve_run(plan: DevicePlan, f: np.ndarray, drivers=None, values=None):
     consts = plan.consts.copy()
     prefs = plan.prefs.copy()
     rows = []
+    seen = {}                                  # a callable shared by several components is evaluated (and uploaded) once
     for (pi, slot, fn) in plan.table_params:
-        v = np.asarray(fn(f))
-        if v.ndim == 0 or v.size == 1 and f.size != 1:
-            consts[slot] = complex(v.reshape(-1)[0])
+        # `Function` wrappers of one user callable (each component wraps its own) count as the same table
+        inner = getattr(fn, "_func", None)
+        key = (id(inner), getattr(fn, "_inf", None)) if inner is not None and type(fn).__name__ == "Function" else id(fn)
+        if key not in seen:
+            v = np.asarray(fn(f))
+            if v.ndim == 0 or v.size == 1 and f.size != 1:
+                seen[key] = (None, complex(v.reshape(-1)[0]))
+            else:
+                if v.shape != f.shape:
+                    v = np.broadcast_to(v, f.shape)
+                seen[key] = (len(rows), None)
+                rows.append(np.ascontiguousarray(v, dtype=np.complex128))
+        row, scalar = seen[key]
+        if row is None:
+            consts[slot] = scalar
             prefs[pi] = (PK_CONST, slot)
         else:
-            if v.shape != f.shape:
-                v = np.broadcast_to(v, f.shape)
-            prefs[pi] = (PK_TABLE, len(rows))
-            rows.append(np.ascontiguousarray(v, dtype=np.complex128))
+            prefs[pi] = (PK_TABLE, row)
     tables = np.stack(rows) if rows else np.zeros((0, f.shape[0]), dtype=np.complex128)
 
     nR = len(plan.sample_owners)

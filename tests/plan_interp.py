@@ -61,6 +61,8 @@ class Interp:
             root = self.consts[idx]                      # sqrt(er), taken by the plan compiler
             root = root.real if root.imag == 0 else root
             return _TWOPI * f / _C0 * (root * one)
+        if kind == pl.PK_BETA_MUL:
+            return 2 * np.pi * f * self.consts[idx].real / _C0
         if kind == pl.PK_SMD:
             sub, a, b, c = (self.consts[idx + i].real for i in range(4))
             w = 2 * 3.141592653589793 * f

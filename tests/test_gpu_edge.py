@@ -281,3 +281,17 @@ def test_smd_parts_are_evaluated_on_the_device():
     Yo = orc.assemble(m.records(), m.n_nodes + len(m.sources), f)
     assert np.array_equal(Y != 0, Yo != 0) and max_ulps(Y, Yo) <= 4.0
     assert np.max(np.abs(m.run_sp(f)._S - oracle_S(m, f))) < TOL
+
+
+def test_coupler_library_on_the_device():
+    """Wilkinson / branch-line / rat-race / Chebyshev transformer (lib/tl.py): phase constants evaluated on
+    the device in the library's own operation order."""
+    from test_plan import _coupler_model
+    m = _coupler_model()
+    cn = m._compiled()
+    assert len(cn.plan.table_params) == 0
+    f = np.linspace(1.2e9, 3.6e9, 41)
+    Y = cn.assemble(f)
+    Yo = orc.assemble(m.records(), m.n_nodes + len(m.sources), f)
+    assert np.array_equal(Y != 0, Yo != 0) and np.max(np.abs(Y - Yo)) <= 1e-13 * np.max(np.abs(Yo))
+    assert np.max(np.abs(m.run_sp(f)._S - oracle_S(m, f))) < TOL

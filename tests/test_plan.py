@@ -225,3 +225,61 @@ def test_smd_closed_forms_are_compiled_not_tabulated():
     z = SMDImpedance(2, 0.1, 0.5e-9, 1e-12, lambda fr: 0.1 + 1j * fr)
     z._inf = 1e30
     assert z.describe()[0] == "table"
+
+
+def _coupler_model():
+    """Every part of lib/tl.py in one four-port network."""
+    from heavi_b200.lib import tl
+    m = hv.Model(suppress_loadbar=True)
+    p = [m.quick_port(50) for _ in range(4)]
+    a, b, c, d = (m.node() for _ in range(4))
+    tl.Wilkinson(50.0, 2.4e9, er=2.9).connect(p[0], a, b)
+    tl.BranchlineCoupler(50.0, 2.4e9, er=3.4).connect(a, p[1], c, d)
+    tl.RatraceCoupler(50.0, 2.4e9).connect(b, c, p[2], d)
+    tl.Transformer(50.0, 92.0, 2.4e9, N_sections=3, ripple=0.1, er=2.2).connect(d, p[3])
+    m.resistor(c, m.gnd, 180.0)
+    return m
+
+
+def test_coupler_library_compiles_to_closed_forms():
+    """lib/tl.py parts: their phase constants are closed forms (LinePhase / PhaseConstant), nothing is
+    tabulated, and the compiled stamps equal the host evaluation of the same callables."""
+    from oracle import mna_oracle as orc
+    m = _coupler_model()
+    tab = m.stamp_table()
+    f = np.linspace(1.2e9, 3.6e9, 17)
+    p = pl.compile_plan(tab, "dump")
+    assert len(p.table_params) == 0
+    kinds = [int(k) for k, _ in p.prefs]
+    assert kinds.count(pl.PK_BETA_MUL) >= 10 and kinds.count(pl.PK_BETA) == 3
+    W = pi.dump_plan(p, f)
+    Y = orc.assemble(m.records(), m.n_nodes + len(m.sources), f)
+    assert np.array_equal(W != 0, Y != 0)
+    assert np.max(np.abs(W - Y)) <= 1e-13 * np.max(np.abs(Y))
+    S = pi.run_plan(pl.compile_plan(tab), f)[0]
+    So = orc.run_sp(m.records(), m.n_nodes, len(m.sources), f, method="lu_batched")
+    assert np.max(np.abs(S - So)) < 1e-12
+
+
+def test_shared_callable_is_tabulated_once():
+    """One callable handed to several components is evaluated -- and uploaded -- once per run."""
+    calls = []
+
+    def z(f):
+        calls.append(np.size(f))
+        return 30.0 + 1e-9 * f
+
+    m = hv.Model(suppress_loadbar=True)
+    a, b = m.quick_port(50), m.quick_port(50)
+    mid = m.node()
+    m.impedance(a, mid, z)
+    m.impedance(mid, b, z)
+    m.impedance(mid, m.gnd, lambda f: 200.0 - 1j * 1e-8 * f)
+    p = pl.compile_plan(m.stamp_table())
+    assert len(p.table_params) == 3
+    f = np.linspace(1e9, 2e9, 11)
+    calls.clear()
+    consts, prefs, tables, samples = pl.resolve_run(p, f)
+    assert len(calls) == 1 and tables.shape == (2, 11)
+    rows = [int(prefs[pi][1]) for (pi, _, _) in p.table_params]
+    assert rows[0] == rows[1] != rows[2]
