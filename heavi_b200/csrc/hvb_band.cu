@@ -19,6 +19,9 @@
 #include "hvb_kernels.h"
 
 #define HVB_BAND_THREADS 128
+#ifndef HVB_BANDF_MINB1
+#define HVB_BANDF_MINB1 5
+#endif
 
 struct BandView {
     cplx* __restrict__ base;      // W + t
@@ -289,7 +292,7 @@ __device__ __forceinline__ void band_assemble_row(const HvbDev& D, int r, int k0
 }
 
 template <int B>
-__global__ void __launch_bounds__(HVB_BAND_THREADS, B == 1 ? 5 : B == 2 ? 4 : B == 3 ? 3 : 2) hvb_bandf_kernel(const HvbDev D) {
+__global__ void __launch_bounds__(HVB_BAND_THREADS, B == 1 ? HVB_BANDF_MINB1 : B == 2 ? 4 : B == 3 ? 3 : 2) hvb_bandf_kernel(const HvbDev D) {
     constexpr int WD = 2 * B + 1, NR = B + 1, NX = 2 * B, NRING = NR > NX ? NR : NX;
     const int n = D.n, P = D.P;
     const long long T = (long long)gridDim.x * blockDim.x;
