@@ -659,7 +659,6 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
             D.f32 = (a->f32_out && sb == 0) ? (float*)pl->f32.p + fb : nullptr;
             rc = launch(pl, D, st, tile & 1);
             if (rc) return rc;
-            if (D.f32) CU(cudaMemcpyAsync(a->f32_out + fb, D.f32, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
             // rows of nf elements, one per (sample, j, i); destination pitch is the full nF
             char* dst = (char*)S_out + ((size_t)sb * PP * nF + (size_t)fb) * 16;
             // contiguous destination -> one plain copy; otherwise one strided 2-D copy
@@ -680,6 +679,7 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     CU(cudaEventRecord(pl->ev_tail, s1));
     CU(cudaStreamWaitEvent(s0, pl->ev_tail, 0));
     CU(cudaMemcpyAsync(pl->h_status, pl->inbuf.p, 4, cudaMemcpyDeviceToHost, s0));
+    if (a->f32_out) CU(cudaMemcpyAsync(a->f32_out, pl->f32.p, (size_t)nF * 4, cudaMemcpyDeviceToHost, s0));   // one copy for the whole axis
     mark();
     mark();
     CU(cudaStreamSynchronize(s0));
