@@ -579,7 +579,9 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
         chunk_bytes = std::max<int64_t>(chunk_bytes, (int64_t)(waves * pl->max_grid * pl->threads) * PP * 16);
     }
     const char* ms = getenv("HVB_MIN_SLAB");
-    const int64_t min_slab = ms && atoi(ms) > 0 ? atoi(ms) : 32768;   // points; a slab leaves as P*P segments of 16*slab bytes
+    // points per slab at least (a slab leaves as P*P segments of 16*slab bytes).  Measured: a 100 k-point
+    // two-port sweep is fastest as two slabs, a 1 M-point eight-port sweep with ~30 (shorter exposed tail)
+    const int64_t min_slab = ms && atoi(ms) > 0 ? atoi(ms) : (nS * nF < 200000 ? 49152 : 32768);
     const int64_t total_bytes = nS * nF * PP * 16;
     int64_t ntiles = std::max<int64_t>((total_bytes + chunk_bytes - 1) / chunk_bytes, 1);
     // small jobs: still cut them so that the copy of one tile overlaps the kernel of the next
