@@ -17,6 +17,10 @@ parity is pinned by these files: each holds, for one circuit built by `tests/cir
   f32          the float32 frequency axis run_sp returns
 
 It also prints how far the numpy oracle (oracle/mna_oracle.py) is from the reference on each.
+
+`mc_twoport.npz` is different in kind: the reference's own Monte-Carlo loop (`for i in mc.iterate(6)`,
+np.random.seed(11)) over a netlist with lib/mc.py's RandomTwoPort -- per-trial draws and per-trial S.
+`python oracle/make_golden.py --only-mc-twoport` regenerates just that file.
 """
 from __future__ import annotations
 
