@@ -75,6 +75,7 @@ struct hvb_plan {
     int band = -1;                                     // structural half bandwidth of the matrix block
     size_t work_words = 0;                             // kernel C: workspace words per thread
     int band_nslots = 0, band_min_row = 0, band_fused = 0;
+    bool band_twoports_only = false;                   // every N-port block of the plan has two ports
     int band_value_slots = 0, band_nsm = 0;            // value slots the schedule needs / held in shared memory
     std::vector<int> rhs_minrow;                       // first row with an entry in each right-hand-side column
     long long band_rec_words = 0;
@@ -145,7 +146,17 @@ static cudaError_t build_band_schedule(hvb_plan* pl, const hvb_plan_desc& d) {
         for (int e = 0; e < cnt; ++e) if (last[out + e] >= 0) fr = std::min(fr, first[out + e]);
         if (fr < n) by_row[fr].push_back({~o, out, cnt});
     }
-    std::vector<int> slot(ndyn, -1), sched_ptr(n + 1, 0), sched_op, fslot(std::max(d.n_fast_ops, 1), 0), oslot((size_t)std::max(d.n_ops, 1) * 9, -1);
+    // two-port blocks ride in the same schedule, numbered after the simple ops: (Pn+1)^2 = 9 outputs each
+    pl->band_twoports_only = true;
+    for (int o = 0; o < d.n_coops; ++o) {
+        const int32_t* op = d.coops + (size_t)o * HVB_COOP_WORDS;
+        if (op[2] != 2) { pl->band_twoports_only = false; continue; }
+        const int out = op[1] - nvc;
+        int fr = n;
+        for (int e = 0; e < 9; ++e) if (last[out + e] >= 0) fr = std::min(fr, first[out + e]);
+        if (fr < n) by_row[fr].push_back({~(d.n_ops + o), out, 9});
+    }
+    std::vector<int> slot(ndyn, -1), sched_ptr(n + 1, 0), sched_op, fslot(std::max(d.n_fast_ops, 1), 0), oslot((size_t)std::max(d.n_ops + d.n_coops, 1) * 9, -1);
     std::vector<std::vector<int>> expire(n + 1);
     std::vector<int> free_slots;                           // min-heap
     int nslots = 0;
@@ -209,7 +220,19 @@ static bool band_kernel_ok(const hvb_plan* pl) {
     if (off && off[0] == '1') return false;
     const char* force = getenv("HVB_FORCE_BLOCK");          // tests: dense block kernel for any shape
     if (force && force[0] == '1') return false;
-    if (pl->band < 0 || d.n_coops != 0 || d.kernel_hint == 1) return false;
+    if (pl->band < 0 || d.kernel_hint == 1) return false;
+    if (d.n_coops != 0) {
+        // N-port blocks: only two-ports (evaluated per thread), and only the fused kernel knows how
+        if (!pl->band_twoports_only || d.ncols - d.n != d.P) return false;
+        const int Bc = hvb_band_round_up(pl->band);
+        int smem_sm = 0;
+        if (Bc < 1 || Bc > 4 || cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, pl->device) != cudaSuccess) return false;
+        const int want_ctas = Bc == 1 ? 5 : Bc == 2 ? 4 : Bc == 3 ? 3 : 2;
+        const size_t per_cta = (size_t)smem_sm / want_ctas - 1024;
+        if ((size_t)(hvb_bandf_ring_words(Bc, d.P) + 1) * hvb_band_threads() * sizeof(cplx) > per_cta) return false;
+        const char* nf = getenv("HVB_BAND_FUSED");
+        if (nf && nf[0] == '0') return false;
+    }
     const int B = hvb_band_round_up(pl->band);
     if (B == 0) return false;
     if (d.kernel_hint == 2) return B <= 4 && 2 * B + 1 <= d.n;   // the host measured / decided: any narrow band
@@ -259,7 +282,7 @@ static int select_kernel(hvb_plan* pl) {
         pl->smem = 0;
         pl->work_words = hvb_band_words_per_thread(pl->NB, d.n, PP, d.n_dyn);
         const char* nf = getenv("HVB_BAND_FUSED");
-        const void* fk = (PP == d.P && !(nf && nf[0] == '0')) ? hvb_bandf_kernel_ptr(pl->NB) : nullptr;
+        const void* fk = (PP == d.P && !(nf && nf[0] == '0')) ? hvb_bandf_kernel_ptr(pl->NB, d.n_coops > 0) : nullptr;
         if (fk) {
             // shared memory per thread: the right-hand-side ring + as many value slots as fit next to it
             const int want_ctas = pl->NB == 1 ? 5 : pl->NB == 2 ? 4 : pl->NB == 3 ? 3 : 2;
@@ -397,7 +420,7 @@ extern "C" int hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan**
         pl->band_nslots = std::max(ns, 1);
         pl->band_min_row = ns ? minrow : d.n;
         if (upload(pl->band_slots, slot.data(), slot.size() * 4) != cudaSuccess ||
-            (d.n_coops == 0 && build_band_schedule(pl, d) != cudaSuccess)) {
+            build_band_schedule(pl, d) != cudaSuccess) {
             hvb_plan_destroy(pl);
             return fail(HVB_ERR_CUDA, "plan upload failed");
         }

@@ -217,9 +217,79 @@ struct BandVals {
     }
 };
 
+// Two-port S or Y block evaluated by ONE thread (base/nport.py:28-39; the lane-cooperative version is
+// coop_nport in hvb_warp.cuh): S -> Y = (1/Z0)(I - S)(I + S)^-1 as a solve of (I+S)^T X^T = (I-S)^T with
+// partial pivoting, then the indefinite 3x3 block with the reference node's row / column (-row sums,
+// -column sums, +total).  o[r*3 + c]; returns status bits.
+// (out of line and fed a ParamView copy: only netlists with such blocks pay for it)
+static __device__ __noinline__ unsigned band_eval_twoport(const ParamView pv, const int* __restrict__ op, double f, long long fi,
+                                                          const double* __restrict__ srow, cplx* __restrict__ o) {
+    const int code = __ldg(op), first = __ldg(op + 3);
+    unsigned bad = 0;
+    cplx y[2][2];                                           // y[i][j]
+    if (code == COOP_NPORT_Y) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) y[i][j] = eval_param(pv, first + i * 2 + j, f, fi, srow);
+    } else {
+        cplx w[2][4];                                       // rows of [(I+S)^T | (I-S)^T]
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const cplx s = eval_param(pv, first + i * 2 + j, f, fi, srow);
+                const double d = (i == j) ? 1.0 : 0.0;
+                w[j][i] = cmk(d + s.x, s.y);
+                w[j][2 + i] = cmk(d - s.x, -s.y);
+            }
+        // column 0: pivot row p, the other row q
+        const bool swap = fabs(w[1][0].x) + fabs(w[1][0].y) > fabs(w[0][0].x) + fabs(w[0][0].y);
+        if (swap) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { const cplx t = w[0][c]; w[0][c] = w[1][c]; w[1][c] = t; }
+        }
+        const double m0 = fabs(w[0][0].x) + fabs(w[0][0].y);
+        const cplx inv0 = crecip_fast(w[0][0]);
+        const cplx l = cmul(w[1][0], inv0);
+#pragma unroll
+        for (int c = 1; c < 4; ++c) cfnma(w[1][c], l, w[0][c]);
+        const double m1 = fabs(w[1][1].x) + fabs(w[1][1].y);
+        if (!(m0 >= 2.2250738585072014e-308) || !(m1 >= 2.2250738585072014e-308)) bad |= HVB_STATUS_ZERO_PIVOT_BIT;
+        const cplx inv1 = crecip_fast(w[1][1]);
+        // back substitution: X^T rows, X^T[k][c] = X[c][k]
+        cplx xt[2][2];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            xt[1][c] = cmul(w[1][2 + c], inv1);
+            cplx t = w[0][2 + c];
+            cfnma(t, w[0][1], xt[1][c]);
+            xt[0][c] = cmul(t, inv0);
+        }
+        const cplx iz = crecip_np(pv.consts[__ldg(op + 4)]);     // 1/Z0 (nport.py:32)
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) y[c][k] = (iz.y == 0.0) ? cscale(xt[k][c], iz.x) : cmul(iz, xt[k][c]);
+    }
+    cplx tot = cmk(0.0, 0.0);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const cplx rs = cadd(y[i][0], y[i][1]), cs = cadd(y[0][i], y[1][i]);
+        o[i * 3 + 0] = y[i][0]; o[i * 3 + 1] = y[i][1];
+        o[i * 3 + 2] = cneg(rs);
+        o[2 * 3 + i] = cneg(cs);
+        tot = cadd(tot, rs);
+    }
+    o[8] = tot;
+    return bad;
+}
+
 // evaluate the value ops scheduled before row r (hvb_api.cu: build_band_schedule)
-__device__ __forceinline__ void band_run_schedule(const HvbDev& D, int r, double f, long long fi,
-                                                  const double* __restrict__ srow, const BandVals& vals) {
+template <bool TWOPORT>
+__device__ __forceinline__ unsigned band_run_schedule(const HvbDev& D, int r, double f, long long fi,
+                                                      const double* __restrict__ srow, const BandVals& vals) {
+    unsigned bad = 0;
     const int lo = __ldg(D.band_sched_ptr + r), hi = __ldg(D.band_sched_ptr + r + 1);
     const double w = __dmul_rn(HVB_TWOPI, f);
     for (int i = lo; i < hi; ++i) {
@@ -233,10 +303,19 @@ __device__ __forceinline__ void band_run_schedule(const HvbDev& D, int r, double
             const bool imag = (code & 2) != 0;
             vals.store(__ldg(D.band_fslot + ref), cmk(imag ? 0.0 : v, imag ? ((code & 1) ? -v : v) : 0.0));
         } else {
-            const int o = ~ref;
+            const int o = ~ref;                             // simple op, or nops + index of a two-port block
+            cplx tmp[9];
+            if (TWOPORT && o >= D.nops) {
+                bad |= band_eval_twoport(D.pv, D.coops + (o - D.nops) * HVB_COOP_WORDS, f, fi, srow, tmp);
+#pragma unroll
+                for (int e = 0; e < 9; ++e) {
+                    const int sl = __ldg(D.band_oslot + o * 9 + e);
+                    if (sl >= 0) vals.store(sl, tmp[e]);
+                }
+                continue;
+            }
             const int* __restrict__ op = D.ops + o * HVB_OP_WORDS;
             const int out = __ldg(op + 1) - D.nvc;
-            cplx tmp[9];
             const bool line = __ldg(op) == OP_TLINE;
             if (line) {
                 const cplx Z0 = eval_param(D.pv, __ldg(op + 2), f, fi, srow);
@@ -255,6 +334,7 @@ __device__ __forceinline__ void band_run_schedule(const HvbDev& D, int r, double
             }
         }
     }
+    return bad;
 }
 
 // Assemble system row r: matrix cells (columns k0 .. k0+2B) into registers a[], right-hand-side cells
@@ -291,7 +371,9 @@ __device__ __forceinline__ void band_assemble_row(const HvbDev& D, int r, int k0
     }
 }
 
-template <int B>
+// TWOPORT: the plan holds two-port S / Y blocks (evaluated per thread); kept out of the common instantiation
+// because the extra call path costs the hot loop registers (c5: 17 -> 23 ms when it was unconditional)
+template <int B, bool TWOPORT>
 __global__ void __launch_bounds__(HVB_BAND_THREADS, B == 1 ? HVB_BANDF_MINB1 : B == 2 ? 4 : B == 3 ? 3 : 2) hvb_bandf_kernel(const HvbDev D) {
     constexpr int WD = 2 * B + 1, NR = B + 1, NX = 2 * B, NRING = NR > NX ? NR : NX;
     const int n = D.n, P = D.P;
@@ -321,7 +403,7 @@ __global__ void __launch_bounds__(HVB_BAND_THREADS, B == 1 ? HVB_BANDF_MINB1 : B
 #pragma unroll
             for (int i = 0; i < B; ++i) {
                 if (i < n) {
-                    band_run_schedule(D, i, f, fi, srow, vals);
+                    bad |= band_run_schedule<TWOPORT>(D, i, f, fi, srow, vals);
                     band_assemble_row<B>(D, i, 0, vals, A[i], ring + yrow[i] * ring_row);
                 } else {
 #pragma unroll
@@ -336,7 +418,7 @@ __global__ void __launch_bounds__(HVB_BAND_THREADS, B == 1 ? HVB_BANDF_MINB1 : B
             const int na = __ldg(D.band_act + k);
             cplx* __restrict__ ynew = ring + yrow[B] * ring_row;
             if (k + B < n) {
-                band_run_schedule(D, k + B, f, fi, srow, vals);
+                bad |= band_run_schedule<TWOPORT>(D, k + B, f, fi, srow, vals);
                 band_assemble_row<B>(D, k + B, k, vals, A[B], ynew);
             } else {
 #pragma unroll
@@ -484,12 +566,12 @@ __global__ void __launch_bounds__(HVB_BAND_THREADS, B == 1 ? HVB_BANDF_MINB1 : B
     if (bad && D.status) atomicOr(D.status, (int)bad);
 }
 
-const void* hvb_bandf_kernel_ptr(int b) {
+const void* hvb_bandf_kernel_ptr(int b, int twoport) {
     switch (b) {
-        case 1: return (const void*)hvb_bandf_kernel<1>;
-        case 2: return (const void*)hvb_bandf_kernel<2>;
-        case 3: return (const void*)hvb_bandf_kernel<3>;
-        case 4: return (const void*)hvb_bandf_kernel<4>;
+        case 1: return twoport ? (const void*)hvb_bandf_kernel<1, true> : (const void*)hvb_bandf_kernel<1, false>;
+        case 2: return twoport ? (const void*)hvb_bandf_kernel<2, true> : (const void*)hvb_bandf_kernel<2, false>;
+        case 3: return twoport ? (const void*)hvb_bandf_kernel<3, true> : (const void*)hvb_bandf_kernel<3, false>;
+        case 4: return twoport ? (const void*)hvb_bandf_kernel<4, true> : (const void*)hvb_bandf_kernel<4, false>;
     }
     return nullptr;
 }

@@ -24,7 +24,7 @@ const void* hvb_band_kernel_ptr(int b);
 int hvb_band_threads();
 int hvb_band_round_up(int b);
 size_t hvb_band_words_per_thread(int b, int n, int pp, int n_dyn);
-const void* hvb_bandf_kernel_ptr(int b);
+const void* hvb_bandf_kernel_ptr(int b, int twoport);
 int hvb_bandf_ring_words(int b, int p);
 
 const void* hvb_dump_kernel_ptr();

@@ -438,7 +438,8 @@ def compile_plan(table: StampTable, mode: str = "auto", pad_to: tuple[int, int] 
         raise ValueError(order)
     band = -1
     if mode != "dump" and pad_to is None and (order == "rcm" or (order == "auto" and n_real >= BAND_MIN_ROWS)):
-        if not any(k in ("nport_s", "nport_y") for k in table.kinds):
+        # N-port blocks: the banded kernel evaluates two-ports per thread; larger blocks need the lane-cooperative path
+        if all(len(ids) == 3 for k, ids in zip(table.kinds, table.ids) if k in ("nport_s", "nport_y")):
             res = _band_order(table, rowmap, mode, small=(order == "rcm"))
             if res is not None:
                 rowmap, band = res

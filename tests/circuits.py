@@ -294,3 +294,30 @@ def build_random(hv, seed: int):
             m.resistor(a, a, float(rng.uniform(20, 200)))
     f = np.sort(rng.uniform(0.3e9, 8e9, size=int(rng.integers(3, 9))))
     return m, f
+
+
+def build_twoport_cascade(hv, sections: int = 6, nF: int = 33, seed: int = 0):
+    """Cascade of measured-style two-port S blocks (in-memory EMerge data), lines and shunt capacitors
+    between two ports: chain-like, so narrow-banded, with an N-port (two-port) value op per section."""
+    import importlib
+    EMergeModel = importlib.import_module(hv.__name__ + ".lib.emerge").EMergeModel
+    rng = np.random.default_rng(500 + seed)
+    F = np.linspace(0.2e9, 8e9, 41)
+    m = _model(hv)
+    a, b = m.quick_port(50), m.quick_port(50)
+    at = a
+    for k in range(sections):
+        # a slightly lossy, slightly mismatched line section as S data
+        th = 2 * np.pi * F * (0.6e-10 + 0.2e-10 * rng.random())
+        g = 0.05 + 0.1 * rng.random()
+        t = (1 - g ** 2) ** 0.5 * 10 ** (-0.02) * np.exp(-1j * th)
+        S = np.empty((len(F), 2, 2), dtype=complex)
+        S[:, 0, 0] = g * np.exp(1j * 0.3 * k); S[:, 1, 1] = -g * np.exp(-1j * 0.2 * k)
+        S[:, 0, 1] = t; S[:, 1, 0] = t
+        n1, n2 = m.node(), m.node()
+        m.transmissionline(at, n1, 50.0 + 5 * k, 2.2, 3e-3)
+        EMergeModel((F, S)).connect(n1, n2)
+        m.capacitor(n2, m.gnd, (0.1 + 0.05 * k) * 1e-12)
+        at = n2
+    m.inductor(at, b, 0.8e-9)
+    return m, np.linspace(0.5e9, 6e9, nF)

@@ -193,3 +193,28 @@ def test_sharded_run_of_a_mid_size_banded_system_is_bit_identical():
     for world in (2, 8):                                       # each shard alone would be below the threshold
         parts = [sh.run_sharded(lambda fb, vb: cn.run(fb, batch_points=len(f)).copy(), f, None, world, r) for r in range(world)]
         assert np.array_equal(np.concatenate([p[1] for p in parts], axis=3)[0], whole)
+
+
+def test_cascade_of_two_port_blocks_runs_on_the_banded_kernel():
+    """Two-port S blocks are evaluated per thread inside the banded kernel (larger N-port blocks keep the
+    lane-cooperative register kernels): same S as the dense path and as the oracle."""
+    import heavi_b200 as hv
+    from heavi_b200.engine import CompiledNetwork
+    from oracle import mna_oracle as orc
+    m, f = circuits.build_twoport_cascade(hv, sections=6)
+    cn = CompiledNetwork(m)
+    assert cn.plan.n_real >= 12 and cn.handle.kernel_info()["kernel_class"] == 0 and len(cn.plan.coops) == 6
+    band = cn._band_variant()
+    assert band and band[1].kernel_info()["kernel_class"] == 2 and band[0].band <= 2
+    Sb = band[1].run_host(f, *cn.resolve(f, plan=band[0]))[0][0]
+    Sd = cn.run(f)[0]
+    assert _close(Sb, Sd)
+    So = orc.run_sp(m.records(), m.n_nodes, len(m.sources), f, method="lu_batched")
+    assert _close(Sb, So)
+    # a long cascade (beyond the register kernels) takes the banded kernel by default
+    m2, f2 = circuits.build_twoport_cascade(hv, sections=20, seed=3)
+    cn2 = CompiledNetwork(m2)
+    assert cn2.plan.n_real > 32 and cn2.handle.kernel_info()["kernel_class"] == 2
+    S2 = cn2.run(f2)[0]
+    So2 = orc.run_sp(m2.records(), m2.n_nodes, len(m2.sources), f2, method="lu_batched")
+    assert _close(S2, So2)
