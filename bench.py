@@ -360,7 +360,7 @@ def main():
             per_solve = 8 + 16 * (2 * ki["stream_words"] + plan.P ** 2)
             gbs = per_solve * job_points(jobs[top]) / (k_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                    "traffic": ncu_traffic(args.workload), "kernel": "hvb_bandf_kernel<%d>" % ki["group"],
+                    "traffic": ncu_traffic(args.workload), "kernel": "hvb_bandf_kernel<%d,false>" % ki["group"],
                     "launch_ms": k_ms, "n_factored": plan.n, "solver_mode": plan.mode, "half_bandwidth": plan.band,
                     "bytes_per_solve": per_solve, "solves_per_launch": job_points(jobs[top]),
                     "dense_lu_equivalent_tflops": achieved,
