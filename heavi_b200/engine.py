@@ -288,6 +288,13 @@ class CompiledNetwork:
 
     BAND_MIN_POINTS = 49152          # about half a grid of the banded kernel (148 SMs x 5 CTAs x 128 threads)
 
+    @classmethod
+    def band_min_points(cls, n: int) -> int:
+        """Batch size from which the banded variant is used for an n-unknown system: (latency of one point
+        in the banded kernel) x (throughput of the register kernel), measured -- 42 k points at n = 10,
+        34 k at 16, 13 k at 24, 11 k at 32 (profiles/README.md)."""
+        return cls.BAND_MIN_POINTS if n <= 12 else cls.BAND_MIN_POINTS * 2 // 3 if n <= 20 else cls.BAND_MIN_POINTS // 3
+
     def __init__(self, net, mode: str | None = None, device: int | None = None):
         self.table = net.stamp_table()
         mode = mode or os.environ.get("HVB_MODE", "auto")
@@ -315,7 +322,7 @@ class CompiledNetwork:
 
     def variant(self, points: int):
         """(plan, handle) that serves a call of `points` (sample, frequency) points."""
-        if self._band is not False and points >= self.BAND_MIN_POINTS:
+        if self._band is not False and points >= self.band_min_points(self.plan.n_real):
             band = self._band_variant()
             if band:
                 return band

@@ -152,7 +152,7 @@ def test_mid_size_banded_system_switches_kernel_with_the_batch_size():
     f_small = np.linspace(0.5e9, 6e9, 501)
     S_small = cn.run(f_small)[0]
     assert cn._band is None                                   # banded variant not even built yet
-    f_big = np.linspace(0.5e9, 6e9, CompiledNetwork.BAND_MIN_POINTS + 17)
+    f_big = np.linspace(0.5e9, 6e9, CompiledNetwork.band_min_points(20) + 17)
     S_big = cn.run(f_big)[0]
     assert cn._band and cn._band[1].kernel_info()["kernel_class"] == 2 and cn._band[0].band == 1
     # the same frequencies through both kernels
@@ -172,7 +172,7 @@ def test_mid_size_banded_system_switches_kernel_with_the_batch_size():
         m2.capacitor(chain[k + 1], m2.gnd, mc.gaussian(1e-12, 5e-14))
     f = np.linspace(1e9, 3e9, 257)
     np.random.seed(3)
-    vals = mc.draw(200)                                         # 51 400 points
+    vals = mc.draw(200)                                         # 51 400 points >= band_min_points(11)
     cn2 = m2._compiled()
     Sb = cn2.run(f, mc._random_numbers, vals)
     assert cn2._band and Sb.shape == (200, 2, 2, 257)
@@ -187,7 +187,7 @@ def test_sharded_run_of_a_mid_size_banded_system_is_bit_identical():
     from heavi_b200 import sharding as sh
     m, _ = circuits.build_band_ladder(hv, K=15, reach=1, nports=2, seed=4)
     cn = m._compiled()
-    f = np.linspace(0.5e9, 6e9, cn.BAND_MIN_POINTS + 1000)
+    f = np.linspace(0.5e9, 6e9, cn.band_min_points(cn.plan.n_real) + 1000)
     whole = cn.run(f)[0].copy()
     assert cn._band                                            # the whole job is large enough for the banded kernel
     for world in (2, 8):                                       # each shard alone would be below the threshold
