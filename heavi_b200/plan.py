@@ -515,27 +515,28 @@ def compile_plan(table: StampTable, mode: str = "auto", pad_to: tuple[int, int] 
     def final(vid):
         return vid - _DYN + nvc if vid >= _DYN else vid
 
-    cell_ptr = np.zeros(n * ncols + 1, dtype=np.int32)
-    ent = []
-    for r in range(n):
-        for c in range(ncols):
-            lst = cells.get((r, c), ())
-            for vid, neg in lst:
-                ent.append((final(vid) << 1) | neg)
-            cell_ptr[r * ncols + c + 1] = len(ent)
-    # per-row lists: the same entries, sorted by column, with the column and an end-of-cell flag packed in
+    # cells sorted by (row, column): one pass builds the cell CSR and the per-row lists (the matrix is ~1 %
+    # dense for large netlists, so nothing here loops over the n x ncols grid)
+    items = sorted(cells.items())
+    counts = np.zeros(n * ncols, dtype=np.int64)
+    ent, rent = [], []
     row_ptr = np.zeros(n + 1, dtype=np.int32)
-    rent = []
-    for r in range(n):
-        for c in range(ncols):
-            lst = cells.get((r, c), ())
-            for k, (vid, neg) in enumerate(lst):
-                v = final(vid)
-                if v >= (1 << 19) or c >= (1 << 11):
-                    raise ValueError("plan too large for the packed row-entry format")
-                word = (neg & 1) | (v << 1) | (c << 20) | ((1 << 31) if k == len(lst) - 1 else 0)
-                rent.append(word - (1 << 32) if word >= (1 << 31) else word)
-        row_ptr[r + 1] = len(rent)
+    for (r, c), lst in items:
+        counts[r * ncols + c] = len(lst)
+        if c >= (1 << 11):
+            raise ValueError("plan too large for the packed row-entry format")
+        for k, (vid, neg) in enumerate(lst):
+            v = final(vid)
+            if v >= (1 << 19):
+                raise ValueError("plan too large for the packed row-entry format")
+            ent.append((v << 1) | neg)
+            # per-row lists: the same entries with the column and an end-of-cell flag packed in
+            word = (neg & 1) | (v << 1) | (c << 20) | ((1 << 31) if k == len(lst) - 1 else 0)
+            rent.append(word - (1 << 32) if word >= (1 << 31) else word)
+        row_ptr[r + 1] += len(lst)
+    row_ptr = np.cumsum(row_ptr).astype(np.int32)
+    cell_ptr = np.zeros(n * ncols + 1, dtype=np.int32)
+    np.cumsum(counts, out=cell_ptr[1:])
     ops = np.array(b.ops, dtype=np.int32).reshape(len(b.ops), OP_WORDS)
     coops = np.array(b.coops, dtype=np.int32).reshape(len(b.coops), COOP_WORDS)
     if len(ops):
