@@ -385,6 +385,37 @@ class CompiledNetwork:
                           "minimum-norm solution there, the LU solver cannot", RuntimeWarning)
         return S
 
+    def run_resident(self, f, drivers=None, values=None, out=None, check: bool = True):
+        """Like `run`, but the result stays in HBM: returns a torch CUDA tensor S[nS,P,P,nF] (complex128).
+        `f` may be a numpy array or a float64 CUDA tensor; nothing crosses PCIe except f, the sample matrix
+        and, with `check`, the 4-byte status word.  For post-processing on the GPU (cost functions of an
+        optimiser, statistics, plotting decimation) the 64 B per solve of a two-port never leave the device."""
+        import torch
+        dev = torch.device("cuda", self.handle.device)
+        if isinstance(f, torch.Tensor):
+            d_f = f.to(device=dev, dtype=torch.float64).contiguous()
+            f_host = d_f.cpu().numpy() if self.plan.table_params else None
+        else:
+            f_host = np.ascontiguousarray(f, dtype=np.float64)
+            d_f = torch.from_numpy(f_host).to(dev)
+        nF = int(d_f.shape[0])
+        if drivers is not None and self._tables_follow_drivers(f_host if f_host is not None else d_f.cpu().numpy(), drivers, values):
+            raise NotImplementedError("sample-dependent callables need the per-trial host path (CompiledNetwork.run)")
+        nS = 1 if values is None else len(values)
+        plan, handle = self.variant(nF * nS)
+        if plan.table_params and f_host is None:
+            f_host = d_f.cpu().numpy()
+        consts, prefs, tables, samples = pl.resolve_run(plan, f_host if f_host is not None else np.zeros(nF), drivers, values)
+        d_tab = torch.from_numpy(tables).to(dev) if tables.shape[0] else None
+        d_smp = torch.from_numpy(np.ascontiguousarray(samples)).to(dev)
+        if out is None:
+            out = torch.empty((nS, plan.P, plan.P, nF), dtype=torch.complex128, device=dev)
+        d_status = torch.zeros(1, dtype=torch.int32, device=dev)
+        handle.run_device(d_f, consts, prefs, d_tab, d_smp, out, d_status)
+        if check:
+            self._raise_for_status(int(d_status.item()))
+        return out
+
     def _raise_for_status(self, status: int):
         if status & HVB_STATUS_NONFINITE:
             raise np.linalg.LinAlgError("MNA matrix or S-parameters contain NaN/Inf (e.g. f = 0 with an inductor)")

@@ -236,6 +236,12 @@ class Network:
         f64 = np.ascontiguousarray(np.asarray(frequencies, dtype=np.float64))
         return compiled.run(f64, drivers=list(drivers), values=np.asarray(values, dtype=np.float64))
 
+    def run_sp_resident(self, frequencies, drivers=None, values=None):
+        """`run_sp` / `run_sp_batch` whose result stays on the GPU: torch CUDA tensor S[nS,P,P,nF]
+        (complex128, nS = 1 for a plain sweep).  Use it when the consumer of S is GPU code."""
+        return self._compiled().run_resident(frequencies, None if drivers is None else list(drivers),
+                                             None if values is None else np.asarray(values, dtype=np.float64))
+
     def run_mc(self, frequencies: np.ndarray, mc, N: int) -> StatSparameters:
         """`for i in mc.iterate(N): mc.submit_S(run_sp(f))` (numeric.py:498-507) as one batch.
         Draws are made on the host in the reference's order, so results are seed-compatible."""

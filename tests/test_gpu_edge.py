@@ -295,3 +295,29 @@ def test_coupler_library_on_the_device():
     Yo = orc.assemble(m.records(), m.n_nodes + len(m.sources), f)
     assert np.array_equal(Y != 0, Yo != 0) and np.max(np.abs(Y - Yo)) <= 1e-13 * np.max(np.abs(Yo))
     assert np.max(np.abs(m.run_sp(f)._S - oracle_S(m, f))) < TOL
+
+
+def test_resident_results_match_the_host_path():
+    """run_sp_resident leaves S in HBM (torch CUDA tensor); same values as run_sp / run_sp_batch."""
+    import torch
+    import circuits
+    m, _ = ladder(9, 3, seed=2)
+    f = np.linspace(0.4e9, 5e9, 777)
+    S_dev = m.run_sp_resident(f)
+    assert S_dev.is_cuda and S_dev.dtype == torch.complex128 and tuple(S_dev.shape) == (1, 3, 3, 777)
+    assert np.array_equal(S_dev.cpu().numpy()[0], m.run_sp(f)._S)
+    S_dev2 = m.run_sp_resident(torch.from_numpy(f).cuda())               # frequencies already on the device
+    assert torch.equal(S_dev, S_dev2)
+    m4, f4, mc = circuits.build_c4(hv, nF=201)
+    np.random.seed(3)
+    vals = mc.draw(16)
+    Sb = m4.run_sp_resident(f4, mc._random_numbers, vals)
+    assert np.array_equal(Sb.cpu().numpy(), m4.run_sp_batch(f4, mc._random_numbers, vals))
+    # a derived quantity computed where the data lives: worst-case |S21| in dB over the samples
+    worst = (20 * torch.log10(Sb[:, 1, 0, :].abs())).amin(dim=0)
+    assert worst.shape == (201,) and bool(torch.isfinite(worst).all())
+    m0 = hv.Model(suppress_loadbar=True)
+    a, b = m0.quick_port(50), m0.quick_port(50)
+    m0.inductor(a, b, 1e-9)
+    with pytest.raises(np.linalg.LinAlgError):
+        m0.run_sp_resident(np.array([0.0, 1e9]))
