@@ -266,7 +266,8 @@ static int select_kernel(hvb_plan* pl) {
         pl->kernel = wk;
         pl->lanes = G; pl->rows_per_lane = 1;
         const char* r1 = getenv("HVB_WARP_R");
-        const void* wk2 = (d.n_coops == 0 && !(r1 && atoi(r1) == 1)) ? hvb_warp2_kernel_ptr(N, PP) : nullptr;
+        // two rows per lane: the cooperative N-port op needs one lane per block row, so blocks up to the group size
+        const void* wk2 = (max_nport <= hvb_warp2_group(N) && !(r1 && atoi(r1) == 1)) ? hvb_warp2_kernel_ptr(N, PP) : nullptr;
         if (wk2) { pl->kernel = wk2; pl->lanes = hvb_warp2_group(N); pl->rows_per_lane = 2; }
         pl->threads = hvb_warp_threads();
         pl->region_b = std::max(d.coop_scratch, N * (N + PP));

@@ -73,7 +73,11 @@ __global__ void __launch_bounds__(HVB_WARP_THREADS, Warp2Cfg<N, P>::kMinBlocks) 
         const double* __restrict__ srow = D.samples + s * D.nR;
         unsigned bad = 0;
 
-        // ---- 1. value program (no cooperative ops in plans routed here) ------------------------
+        // ---- 1. value program (N-port blocks: only those with at most G ports are routed here) ----
+        if (D.ncoops > 0) {
+            CoopCtx ctx{D.pv, D.nvc, f, fi, srow, regA, regB};
+            for (int o = 0; o < D.ncoops; ++o) bad |= coop_nport<G>(&ctx, D.coops + o * HVB_COOP_WORDS, gl);
+        }
         eval_fast_ops(fcodeS, foutS, fargS, nfast, f, srow, regA, gl, G);
         for (int o = gl; o < D.nops; o += G) eval_simple_op(D, D.ops + o * HVB_OP_WORDS, f, fi, srow, regA);
         __syncwarp();
