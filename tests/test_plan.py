@@ -283,3 +283,18 @@ def test_shared_callable_is_tabulated_once():
     assert len(calls) == 1 and tables.shape == (2, 11)
     rows = [int(prefs[pi][1]) for (pi, _, _) in p.table_params]
     assert rows[0] == rows[1] != rows[2]
+
+
+def test_band_ordering_with_two_port_blocks():
+    """Two-port S blocks keep a cascade narrow-banded: the ordered plan is allowed (larger N-port blocks are
+    not), keeps its cooperative ops, and solves to the same S as the natural order."""
+    import circuits
+    m, f = circuits.build_twoport_cascade(hv, sections=5, nF=7)
+    tab = m.stamp_table()
+    nat = pl.compile_plan(tab, order="natural")
+    rcm = pl.compile_plan(tab, order="rcm")
+    assert nat.band == -1 and 1 <= rcm.band <= 2 and len(rcm.coops) == len(nat.coops) == 5
+    assert all(int(c[2]) == 2 for c in rcm.coops)
+    assert np.max(np.abs(pi.run_plan(rcm, f) - pi.run_plan(nat, f))) < 1e-12
+    # the 8-port Touchstone block of config 3 is never reordered
+    assert pl.compile_plan(REG["c3_touchstone"]().stamp_table(), order="rcm").band == -1
