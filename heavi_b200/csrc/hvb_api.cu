@@ -14,8 +14,14 @@
 
 #include "../../include/heavi_b200.h"
 #include "hvb_device.cuh"
+#include "hvb_gen.h"
+#include "hvb_jit.h"
 #include "hvb_kernels.h"
 #include "hvb_warp_shapes.h"
+
+#include <map>
+#include <memory>
+#include <mutex>
 
 static thread_local std::string g_err;
 
@@ -53,6 +59,16 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
 };
 
+// kernel D: one NVRTC-compiled kernel per (plan, parameter-reference layout)
+struct GenKernel {
+    HvbJitKernel k;
+    DevBuf rows, itab, dtab;
+    bool rolled = false, scratch_acc = false;
+    int ctas_per_sm = 0, n_cases = 0;
+    long long flops = 0;
+    std::vector<int32_t> prefs;                        // the layout the value formulas were specialised on
+};
+
 struct hvb_plan {
     int device = 0;
     hvb_plan_desc d{};
@@ -82,6 +98,15 @@ struct hvb_plan {
     const void* kernel = nullptr;
     int max_grid = 0;
     int64_t launches = 0;
+    // kernel D (generated): host copy of the plan the generator reads, compiled variants, the active one
+    GenPlan gen;
+    std::vector<GenKernel*> gen_variants;
+    GenKernel* gk = nullptr;
+    // tunables read once, at plan creation (environment)
+    int64_t env_chunk_mb = 0, env_min_slab = 0, env_stats_mb = 0;
+    double env_tile_waves = 0.0;
+    bool env_copy2d = true;
+    int env_band_pfb = -1;
 };
 
 static cudaError_t upload(DevBuf& b, const void* src, size_t bytes) {
@@ -239,6 +264,63 @@ static bool band_kernel_ok(const hvb_plan* pl) {
     return 2 * (3 * B + 1) <= d.n;                       // a narrow band, not a small dense block
 }
 
+static bool gen_kernel_ok(const hvb_plan* pl) {
+    const char* off = getenv("HVB_NO_GEN");
+    if (off && off[0] == '1') return false;
+    const char* force = getenv("HVB_FORCE_BLOCK");
+    if (force && force[0] == '1') return false;
+    if (pl->d.kernel_hint == 1) return false;
+    return hvb_gen_supported(pl->gen, nullptr);
+}
+
+// ---- kernel D: generate + compile (cached per process by source text) + load ------------------------
+static std::mutex g_cubin_mu;
+static std::map<std::string, std::shared_ptr<std::vector<char>>> g_cubins;
+
+static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs) {
+    const size_t np = (size_t)pl->d.n_prefs * 2;
+    if (pl->gk && pl->gk->prefs.size() == np && (np == 0 || memcmp(pl->gk->prefs.data(), prefs, np * 4) == 0)) return HVB_OK;
+    for (GenKernel* v : pl->gen_variants)
+        if (v->prefs.size() == np && (np == 0 || memcmp(v->prefs.data(), prefs, np * 4) == 0)) { pl->gk = v; return HVB_OK; }
+    GenResult res;
+    std::string err;
+    const char* md = getenv("HVB_GEN_MODE");
+    if (hvb_gen_source(pl->gen, prefs, md ? atoi(md) : 0, hvb_gen_prelude(), &res, &err) != 0)
+        return fail(HVB_ERR_UNSUPPORTED, "kernel generator: %s", err.c_str());
+    std::shared_ptr<std::vector<char>> cubin;
+    {
+        std::lock_guard<std::mutex> lk(g_cubin_mu);
+        auto it = g_cubins.find(res.src);
+        if (it != g_cubins.end()) cubin = it->second;
+    }
+    if (!cubin) {
+        cubin = std::make_shared<std::vector<char>>();
+        std::string log;
+        if (hvb_jit_compile(res.src, cubin.get(), &log, &err) != 0) return fail(HVB_ERR_CUDA, "NVRTC: %.900s", err.c_str());
+        std::lock_guard<std::mutex> lk(g_cubin_mu);
+        g_cubins[res.src] = cubin;
+    }
+    std::unique_ptr<GenKernel> gk(new GenKernel());
+    if (hvb_jit_load(*cubin, res.kernel_name.c_str(), &gk->k, &err) != 0) return fail(HVB_ERR_CUDA, "%s", err.c_str());
+    gk->rolled = res.rolled; gk->scratch_acc = res.scratch_acc; gk->n_cases = res.n_cases; gk->flops = res.flops_per_solve;
+    gk->prefs.assign(prefs, prefs + np);
+    if (res.rolled) {
+        CU(upload(gk->rows, res.rows.data(), res.rows.size() * 4));
+        CU(upload(gk->itab, res.itab.data(), res.itab.size() * 4));
+        CU(upload(gk->dtab, res.dtab.data(), res.dtab.size() * 8));
+    }
+    int occ = 0;
+    if (hvb_jit_occupancy(gk->k, pl->threads, 0, &occ, &err) != 0) return fail(HVB_ERR_CUDA, "%s", err.c_str());
+    if (occ < 1) return fail(HVB_ERR_UNSUPPORTED, "generated kernel does not fit on an SM (%d registers)", gk->k.regs);
+    gk->ctas_per_sm = occ;
+    pl->regs = gk->k.regs;
+    pl->ctas_per_sm = occ;
+    pl->max_grid = occ * pl->sm_count;
+    pl->gk = gk.get();
+    pl->gen_variants.push_back(gk.release());
+    return HVB_OK;
+}
+
 static int select_kernel(hvb_plan* pl) {
     const hvb_plan_desc& d = pl->d;
     cudaDeviceProp prop;
@@ -259,6 +341,16 @@ static int select_kernel(hvb_plan* pl) {
     const char* force = getenv("HVB_FORCE_BLOCK");
     const size_t staged = (size_t)(d.n_const_vals + d.n_fast_ops) * 16 + (size_t)(2 * d.n + 1 + d.n_row_ent + 2 * d.n_fast_ops) * 4 + (size_t)d.P * d.P * 8 + 64;
     const bool band_first = d.kernel_hint == 2 && PP == d.P && band_kernel_ok(pl);
+    if (gen_kernel_ok(pl)) {
+        // kernel D: the netlist is a chain (tridiagonal in the plan's row order) -> a kernel generated for
+        // exactly this netlist, one thread per point, compiled at the first run (hvb_gen.cpp, hvb_jit.cpp)
+        pl->kclass = 3;
+        pl->NB = 1;
+        pl->threads = 128;
+        pl->smem = 0;
+        pl->max_grid = pl->sm_count * 4;               // refined once the kernel exists
+        return HVB_OK;
+    }
     if (!band_first && wk && max_nport <= d.n && staged <= 24576 && !(force && force[0] == '1')) {
         const int N = d.n;
         const int G = N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32;
@@ -426,6 +518,16 @@ extern "C" int hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan**
             return fail(HVB_ERR_CUDA, "plan upload failed");
         }
     }
+    pl->gen.from_desc(d);
+    {   // environment tunables are read here, once, not on the per-call path
+        const char* e;
+        if ((e = getenv("HVB_CHUNK_MB")) && atoi(e) > 0) pl->env_chunk_mb = atoi(e);
+        if ((e = getenv("HVB_MIN_SLAB")) && atoi(e) > 0) pl->env_min_slab = atoi(e);
+        if ((e = getenv("HVB_STATS_MB")) && atoi(e) > 0) pl->env_stats_mb = atoi(e);
+        if ((e = getenv("HVB_BAND_TILE_WAVES")) && atof(e) > 0) pl->env_tile_waves = atof(e);
+        if ((e = getenv("HVB_COPY2D")) && e[0] == '0') pl->env_copy2d = false;
+        if ((e = getenv("HVB_BAND_PFB"))) pl->env_band_pfb = atoi(e);
+    }
     // the descriptor's host pointers are not kept
     pl->d.const_vals = nullptr; pl->d.ops = nullptr; pl->d.coops = nullptr; pl->d.cell_ptr = nullptr; pl->d.cell_ent = nullptr; pl->d.row_ptr = nullptr; pl->d.row_ent = nullptr; pl->d.fop_code = nullptr; pl->d.fop_out = nullptr; pl->d.fop_arg = nullptr; pl->d.epi_port_of_row = nullptr; pl->d.epi_scale = nullptr;
     pl->d.port_rows = nullptr; pl->d.port_zpref = nullptr; pl->d.spl_t = nullptr; pl->d.spl_c = nullptr; pl->d.spl_trace = nullptr;
@@ -445,6 +547,12 @@ extern "C" void hvb_plan_destroy(hvb_plan* pl) {
                      &pl->spl_t, &pl->spl_c, &pl->spl_trace, &pl->spl_fill, &pl->spl_range, &pl->band_slots, &pl->band_sched_ptr, &pl->band_sched_op, &pl->band_fslot, &pl->band_oslot, &pl->band_ent, &pl->band_act, &pl->consts, &pl->prefs,
                      &pl->f, &pl->samples, &pl->tables, &pl->S[0], &pl->S[1], &pl->status, &pl->work[0], &pl->work[1], &pl->f32, &pl->dump, &pl->stats, &pl->inbuf};
     for (DevBuf* b : all) b->release();
+    for (GenKernel* v : pl->gen_variants) {
+        v->rows.release(); v->itab.release(); v->dtab.release();
+        hvb_jit_unload(&v->k);
+        delete v;
+    }
+    pl->gen_variants.clear();
     if (pl->h_stage) cudaFreeHost(pl->h_stage);
     if (pl->h_in) cudaFreeHost(pl->h_in);
     if (pl->h_status) cudaFreeHost(pl->h_status);
@@ -492,9 +600,8 @@ static HvbDev make_dev(const hvb_plan* pl) {
     {
         // records of small systems stay in the L2 (every thread rewrites the same words point after point):
         // prefetching them only costs issue slots
-        const char* b = getenv("HVB_BAND_PFB");
         const size_t footprint = (size_t)pl->band_rec_words * sizeof(cplx) * (size_t)pl->max_grid * pl->threads;
-        D.band_pfb = b ? atoi(b) : (footprint > ((size_t)48 << 20) ? 2 : 0);
+        D.band_pfb = pl->env_band_pfb >= 0 ? pl->env_band_pfb : (footprint > ((size_t)48 << 20) ? 2 : 0);
     }
     D.band_nsm = pl->band_nsm;
     D.band_sched_ptr = (const int*)pl->band_sched_ptr.p;
@@ -504,6 +611,11 @@ static HvbDev make_dev(const hvb_plan* pl) {
     D.band_ent = (const int*)pl->band_ent.p;
     D.band_act = (const int*)pl->band_act.p;
     D.band_rec_words = pl->band_rec_words;
+    if (pl->gk) {
+        D.gen_rows = (const int*)pl->gk->rows.p;
+        D.gen_itab = (const int*)pl->gk->itab.p;
+        D.gen_dtab = (const double*)pl->gk->dtab.p;
+    }
     return D;
 }
 
@@ -530,7 +642,7 @@ static int launch(hvb_plan* pl, HvbDev& D, cudaStream_t st, int slot = 0) {
     if (pl->kclass == 0) {
         const int spb = (pl->threads / 32) * (32 / pl->lanes);
         blocks = (total + spb - 1) / spb;
-    } else if (pl->kclass == 2) {
+    } else if (pl->kclass == 2 || pl->kclass == 3) {
         blocks = (total + pl->threads - 1) / pl->threads;
     } else {
         blocks = total;
@@ -545,6 +657,13 @@ static int launch(hvb_plan* pl, HvbDev& D, cudaStream_t st, int slot = 0) {
         D.W = (cplx*)pl->work[slot].p;
     }
     void* args[] = {&D};
+    if (pl->kclass == 3) {
+        if (!pl->gk) return fail(HVB_ERR_ARG, "generated kernel missing (internal)");
+        std::string err;
+        if (hvb_jit_launch(pl->gk->k, (unsigned)grid, (unsigned)pl->threads, 0, st, args, &err) != 0) return fail(HVB_ERR_CUDA, "%s", err.c_str());
+        pl->launches++;
+        return HVB_OK;
+    }
     CU(cudaLaunchKernel(pl->kernel, dim3(grid), dim3(pl->threads), args, pl->smem, st));
     pl->launches++;
     return HVB_OK;
@@ -561,9 +680,10 @@ static int check_args(const hvb_plan* pl, const hvb_run_args* a) {
 extern "C" int hvb_run_device(hvb_plan* pl, const hvb_run_args* a, double* d_S, int64_t ldS, int32_t* d_status, void* stream) {
     int rc = check_args(pl, a);
     if (rc) return rc;
-    if (pl->d.ncols <= pl->d.n || !pl->kernel) return fail(HVB_ERR_ARG, "plan has no right-hand sides (dump plan)");
+    if (pl->d.ncols <= pl->d.n || (!pl->kernel && pl->kclass != 3)) return fail(HVB_ERR_ARG, "plan has no right-hand sides (dump plan)");
     CU(cudaSetDevice(pl->device));
     cudaStream_t st = (cudaStream_t)stream;
+    if (pl->kclass == 3 && (rc = ensure_gen_kernel(pl, a->prefs)) != HVB_OK) return rc;
     rc = push_params(pl, a, st);
     if (rc) return rc;
     HvbDev D = make_dev(pl);
@@ -578,12 +698,13 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     if (rc) return rc;
     if (!S_out) return fail(HVB_ERR_ARG, "S_out is NULL");
     const hvb_plan_desc& d = pl->d;
-    if (d.ncols <= d.n || !pl->kernel) return fail(HVB_ERR_ARG, "plan has no right-hand sides (dump plan)");
+    if (d.ncols <= d.n || (!pl->kernel && pl->kclass != 3)) return fail(HVB_ERR_ARG, "plan has no right-hand sides (dump plan)");
     CU(cudaSetDevice(pl->device));
     const int64_t nF = a->nF, nS = a->nS;
     const int64_t PP = (int64_t)d.P * d.P;
     if (nF == 0 || PP == 0) { if (status_out) *status_out = 0; return HVB_OK; }
     if ((d.n_consts && !a->consts) || (d.n_prefs && !a->prefs)) return fail(HVB_ERR_ARG, "consts/prefs missing");
+    if (pl->kclass == 3 && (rc = ensure_gen_kernel(pl, a->prefs)) != HVB_OK) return rc;
     cudaStream_t s0 = pl->streams[0], s1 = pl->streams[1];
     static const bool trace = getenv("HVB_TRACE") != nullptr;
     timespec tsp[8]; int ntp = 0;
@@ -594,22 +715,19 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     // Tile size: large enough for the copy to run at the full PCIe rate (a few MB), small enough that
     // the first copy starts early and the exposed head (first kernel) / tail stay short; tiles are
     // equal-sized so no short tile trails the pipeline.
-    const char* env = getenv("HVB_CHUNK_MB");
-    int64_t chunk_bytes = (int64_t)(env && atoi(env) > 0 ? atoi(env) : 16) << 20;
-    // the banded kernel runs one point per thread: a tile should fill the grid at least once
-    if (pl->kclass == 2 && !(env && atoi(env) > 0)) {
-        const char* tw = getenv("HVB_BAND_TILE_WAVES");
-        const double waves = tw && atof(tw) > 0 ? atof(tw) : 1.0;
+    int64_t chunk_bytes = (pl->env_chunk_mb > 0 ? pl->env_chunk_mb : 16) << 20;
+    // the thread-per-point kernels: a tile should fill the grid at least once
+    if ((pl->kclass == 2 || pl->kclass == 3) && pl->env_chunk_mb <= 0) {
+        const double waves = pl->env_tile_waves > 0 ? pl->env_tile_waves : 1.0;
         chunk_bytes = std::max<int64_t>(chunk_bytes, (int64_t)(waves * pl->max_grid * pl->threads) * PP * 16);
     }
-    const char* ms = getenv("HVB_MIN_SLAB");
     // points per slab at least (a slab leaves as P*P segments of 16*slab bytes).  Measured: a 100 k-point
     // two-port sweep is fastest as two slabs, a 1 M-point eight-port sweep with ~30 (shorter exposed tail)
-    const int64_t min_slab = ms && atoi(ms) > 0 ? atoi(ms) : (nS * nF < 200000 ? 49152 : 32768);
+    const int64_t min_slab = pl->env_min_slab > 0 ? pl->env_min_slab : (nS * nF < 200000 ? 49152 : 32768);
     const int64_t total_bytes = nS * nF * PP * 16;
     int64_t ntiles = std::max<int64_t>((total_bytes + chunk_bytes - 1) / chunk_bytes, 1);
     // small jobs: still cut them so that the copy of one tile overlaps the kernel of the next
-    if (ntiles < 4 && pl->kclass != 2) ntiles = std::max<int64_t>(ntiles, std::min<int64_t>(4, nS * nF / min_slab));
+    if (ntiles < 4 && pl->kclass != 2 && pl->kclass != 3) ntiles = std::max<int64_t>(ntiles, std::min<int64_t>(4, nS * nF / min_slab));
     int64_t Sc = nS, Fc = nF;
     if (nS >= ntiles) {
         Sc = (nS + ntiles - 1) / ntiles;                  // whole samples per tile
@@ -659,8 +777,7 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     char* dbase = (char*)pl->inbuf.p;
     mark();
 
-    const char* c2d = getenv("HVB_COPY2D");
-    const bool copy2d = !(c2d && c2d[0] == '0');          // default; 0 = one plain copy per row (measured slower)
+    const bool copy2d = pl->env_copy2d;                   // default; HVB_COPY2D=0 = one plain copy per row (measured slower)
     int tile = 0;
     for (int64_t sb = 0; sb < nS; sb += Sc) {
         const int64_t ns = std::min(Sc, nS - sb);
@@ -723,11 +840,13 @@ extern "C" int hvb_run_stats_host(hvb_plan* pl, const hvb_run_args* a, double* s
     if (rc) return rc;
     if (!stats_out) return fail(HVB_ERR_ARG, "stats_out is NULL");
     const hvb_plan_desc& d = pl->d;
-    if (d.ncols <= d.n || !pl->kernel) return fail(HVB_ERR_ARG, "plan has no right-hand sides (dump plan)");
+    if (d.ncols <= d.n || (!pl->kernel && pl->kclass != 3)) return fail(HVB_ERR_ARG, "plan has no right-hand sides (dump plan)");
     CU(cudaSetDevice(pl->device));
     const int64_t nF = a->nF, nS = a->nS;
     const int64_t PP = (int64_t)d.P * d.P;
     if (nF == 0 || PP == 0) { if (status_out) *status_out = 0; return HVB_OK; }
+    if ((d.n_consts && !a->consts) || (d.n_prefs && !a->prefs)) return fail(HVB_ERR_ARG, "consts/prefs missing");
+    if (pl->kclass == 3 && (rc = ensure_gen_kernel(pl, a->prefs)) != HVB_OK) return rc;
     cudaStream_t st = pl->streams[0];
     CU(pl->f.ensure((size_t)nF * 8));
     CU(cudaMemcpyAsync(pl->f.p, a->f, (size_t)nF * 8, cudaMemcpyHostToDevice, st));
@@ -743,8 +862,7 @@ extern "C" int hvb_run_stats_host(hvb_plan* pl, const hvb_run_args* a, double* s
     rc = push_params(pl, a, st);
     if (rc) return rc;
     // frequency slabs: all samples of a slab stay resident in HBM until they are reduced
-    const char* env = getenv("HVB_STATS_MB");
-    const int64_t budget = (int64_t)(env && atoi(env) > 0 ? atoi(env) : 4096) << 20;
+    const int64_t budget = (pl->env_stats_mb > 0 ? pl->env_stats_mb : 4096) << 20;
     const int64_t Fc = std::max<int64_t>(std::min<int64_t>(nF, budget / (nS * PP * 16)), 1);
     CU(pl->S[0].ensure((size_t)nS * PP * Fc * 16));
     CU(pl->stats.ensure((size_t)6 * PP * Fc * 8));
@@ -833,6 +951,52 @@ extern "C" int hvb_plan_kernel_info(hvb_plan* pl, hvb_kernel_info* out) {
     out->rows_per_lane = pl->rows_per_lane;
     out->stream_words = pl->kclass == 2 ? (int32_t)(pl->band_fused ? pl->band_rec_words : (long long)pl->work_words) : 0;
     out->launches = pl->launches;
+    out->gen_rolled = pl->gk ? (pl->gk->rolled ? 1 : 0) : -1;
+    out->gen_cases = pl->gk ? pl->gk->n_cases : 0;
+    out->local_bytes = pl->gk ? pl->gk->k.local_bytes : 0;
+    out->gen_scratch_acc = pl->gk ? (pl->gk->scratch_acc ? 1 : 0) : 0;
+    out->gen_flops_per_solve = pl->gk ? pl->gk->flops : 0;
+    return HVB_OK;
+}
+
+// ---- kernel D, host-only introspection (no CUDA call): generated source and an NVRTC compile check ----
+extern "C" int hvb_codegen_source(const hvb_plan_desc* desc, const int32_t* prefs, int32_t mode, char* src_out, int64_t src_cap,
+                                  int32_t* rows_out, int32_t* itab_out, double* dtab_out, hvb_codegen_info* info) {
+    if (!desc || !info) return fail(HVB_ERR_ARG, "null argument");
+    memset(info, 0, sizeof(*info));
+    GenPlan g;
+    g.from_desc(*desc);
+    std::string why;
+    if (!hvb_gen_supported(g, &why)) {
+        snprintf(info->reason, sizeof(info->reason), "%s", why.c_str());
+        return HVB_OK;
+    }
+    if (desc->n_prefs && !prefs) return fail(HVB_ERR_ARG, "prefs missing");
+    GenResult res;
+    if (hvb_gen_source(g, prefs, mode, hvb_gen_prelude(), &res, &why) != 0) return fail(HVB_ERR_UNSUPPORTED, "kernel generator: %s", why.c_str());
+    info->supported = 1;
+    info->rolled = res.rolled; info->n_cases = res.n_cases; info->scratch_acc = res.scratch_acc;
+    info->src_len = (int64_t)res.src.size();
+    info->n_rows = (int64_t)res.rows.size(); info->n_itab = (int64_t)res.itab.size(); info->n_dtab = (int64_t)res.dtab.size();
+    info->flops_per_solve = res.flops_per_solve;
+    if (src_out) {
+        if (src_cap < (int64_t)res.src.size() + 1) return fail(HVB_ERR_ARG, "source buffer too small");
+        memcpy(src_out, res.src.c_str(), res.src.size() + 1);
+    }
+    if (rows_out) memcpy(rows_out, res.rows.data(), res.rows.size() * 4);
+    if (itab_out) memcpy(itab_out, res.itab.data(), res.itab.size() * 4);
+    if (dtab_out) memcpy(dtab_out, res.dtab.data(), res.dtab.size() * 8);
+    return HVB_OK;
+}
+
+extern "C" int hvb_codegen_compile(const char* src, char* log_out, int64_t log_cap, int64_t* cubin_bytes) {
+    if (!src) return fail(HVB_ERR_ARG, "null argument");
+    std::vector<char> cubin;
+    std::string log, err;
+    const int rc = hvb_jit_compile(src, &cubin, &log, &err);
+    if (log_out && log_cap > 0) snprintf(log_out, (size_t)log_cap, "%s", rc ? err.c_str() : log.c_str());
+    if (cubin_bytes) *cubin_bytes = (int64_t)cubin.size();
+    if (rc) return fail(HVB_ERR_CUDA, "NVRTC: %.900s", err.c_str());
     return HVB_OK;
 }
 

@@ -68,6 +68,9 @@ struct HvbDev {
     const int* band_oslot;                  // [nops][9] output slots (-1: unused output)
     const int* band_ent;                    // row_ent with per-point value ids replaced by nvc + slot
     int* status;
+    const int* gen_rows;                    // kernel D, rolled form: [n-1][4] assembly case, step case, itab base, dtab base
+    const int* gen_itab;                    //   per-row integer constants (sample columns, parameter indices)
+    const double* gen_dtab;                 //   per-row real constants (component values, plan-time stamp values)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -123,7 +126,11 @@ __device__ __forceinline__ cplx crecip_np(cplx z) {
 // Not correctly rounded (<= ~1 ulp), which is irrelevant against kappa*eps of the solve.
 __device__ __forceinline__ double rcp_fast(double x) {
     double r;
+#ifdef HVB_HOST_SIM                         // tests/host_sim: the generated kernels compiled for the CPU
+    r = 1.0 / x;
+#else
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#endif
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);

@@ -1,0 +1,505 @@
+// hvb_gen.cpp -- kernel D source generator (see hvb_gen.h).
+//
+// Algorithm the generated kernel runs, one THREAD per (sample, frequency) point:
+//
+//   The plan compiler's bandwidth-reducing order makes ladders, filters and cascaded lines
+//   tridiagonal.  Row-oriented elimination with partial pivoting (the zgttrf recurrence: the pivot of
+//   column k is the larger of row k and row k+1, U gets a second super-diagonal) walks the chain once,
+//   front to back, holding two rows in registers.  What the S epilogue needs are the voltages of the
+//   P port nodes only (solvers/spfn.py:159-176), x_o = e_o^T U^-1 y.  Instead of storing every pivot
+//   row for a back substitution, each port row o carries w_o = e_o^T U^-1 forward (a forward
+//   substitution against the columns of U: w_o[k] = (d_ok - w_o[k-1] U[k-1][k] - w_o[k-2] U[k-2][k]) / U[k][k])
+//   and accumulates x_o += w_o[k] y_k on the fly, so nothing but S ever reaches HBM.
+//
+//   Right-hand sides: a port's Norton source enters at its own row.  Once a column's entry row has
+//   passed, its entries in the two live rows are (c_j, 0); one elimination step multiplies every such
+//   column by the same factor (-m without a row exchange, 1 with), so all "old" columns stay
+//   proportional: c_j = gamma_j * z with one scalar z per point.  Per step the kernel updates z and
+//   T_o += w_o[k] * zeta_k; only when a new port joins (P times per point) it folds
+//   acc[o][j] += gamma_j * T_o.  Work per row is O(active ports), not O(ports^2).
+//
+// Same pivots as a dense LU with partial pivoting of the same row order (the rest of column k is
+// structurally zero), same stamp formulas and summation order as the reference's closures
+// (base/*.py); transmission lines use the single-reciprocal form (eval_tline_fast).
+#include "hvb_gen.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+#include "plan_format.h"
+
+#ifndef HVB_GEN_UNROLL_MAX
+#define HVB_GEN_UNROLL_MAX 40
+#endif
+#define HVB_GEN_MAX_PORTS 16
+#define HVB_GEN_REG_ACC_PORTS 4
+
+void GenPlan::from_desc(const hvb_plan_desc& d) {
+    n = d.n; ncols = d.ncols; P = d.P; nvc = d.n_const_vals; ndyn = d.n_dyn; nops = d.n_ops; nfast = d.n_fast_ops;
+    ncoops = d.n_coops; epi_simple = d.epi_simple; nprefs = d.n_prefs;
+    const_vals.assign(d.const_vals, d.const_vals + 2 * (size_t)nvc);
+    ops.assign(d.ops, d.ops + (size_t)nops * HVB_OP_WORDS);
+    row_ptr.assign(d.row_ptr, d.row_ptr + n + 1);
+    row_ent.assign(d.row_ent, d.row_ent + d.n_row_ent);
+    fop_code.assign(d.fop_code, d.fop_code + nfast);
+    fop_out.assign(d.fop_out, d.fop_out + nfast);
+    fop_arg.assign(d.fop_arg, d.fop_arg + nfast);
+    port_rows.assign(d.port_rows, d.port_rows + 3 * (size_t)P);
+    epi_port_of_row.assign(d.epi_port_of_row, d.epi_port_of_row + n);
+    epi_scale.assign(d.epi_scale, d.epi_scale + (size_t)std::max(P * P, 1));
+}
+
+namespace {
+
+struct Entry { int col, vid; bool neg; };
+struct Prod { int kind = -1, idx = 0, sub = 0; };      // kind 0: fast op, 1: simple op (sub = output element)
+
+struct Analysis {
+    std::vector<std::vector<Entry>> rows;
+    std::vector<int> tap_row, tap_port, tap_of_row;
+    std::vector<Prod> prod;
+    std::vector<int> fop_first, fop_last, op_first, op_last;
+    std::string why;
+    bool ok = false;
+};
+
+std::string fmt(const char* f, ...) __attribute__((format(printf, 1, 2)));
+std::string fmt(const char* f, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, f);
+    vsnprintf(buf, sizeof(buf), f, ap);
+    va_end(ap);
+    return buf;
+}
+
+Analysis analyse(const GenPlan& g) {
+    Analysis a;
+    const int n = g.n, P = g.P;
+    auto no = [&](const std::string& w) { a.why = w; return a; };
+    if (!g.epi_simple) return no("S epilogue is not the closed form (ports not ground-referenced with constant real Z0, or not a Norton plan)");
+    if (g.ncoops) return no("plan holds N-port blocks");
+    if (g.ncols - n != P || P < 1) return no("plan is padded or has no ports");
+    if (P > HVB_GEN_MAX_PORTS) return no("too many ports");
+    if (n < 2) return no("fewer than two unknowns");
+    a.rows.resize(n);
+    for (int r = 0; r < n; ++r)
+        for (int e = g.row_ptr[r]; e < g.row_ptr[r + 1]; ++e) {
+            const uint32_t w = (uint32_t)g.row_ent[e];
+            Entry en{(int)((w >> 20) & 0x7FFu), (int)((w >> 1) & 0x7FFFFu), (w & 1u) != 0};
+            if (en.col < n && std::abs(en.col - r) > 1) return no("matrix is not tridiagonal in the plan's row order");
+            a.rows[r].push_back(en);
+        }
+    // ports: one Norton source entry per right-hand-side column, on the port's own signal row
+    std::vector<int> rhs_count(P, 0);
+    for (int r = 0; r < n; ++r)
+        for (const Entry& en : a.rows[r])
+            if (en.col >= n) {
+                const int q = en.col - n;
+                if (q >= P || g.port_rows[3 * q] != r || en.neg) return no("right-hand side is not one source entry per port row");
+                rhs_count[q]++;
+            }
+    a.tap_of_row.assign(n, -1);
+    std::vector<std::pair<int, int>> taps;
+    for (int q = 0; q < P; ++q) {
+        const int r = g.port_rows[3 * q];
+        if (r < 0 || r >= n || rhs_count[q] < 1 || g.epi_port_of_row[r] != q) return no("port without a private signal row");
+        taps.push_back({r, q});
+    }
+    std::sort(taps.begin(), taps.end());
+    for (size_t f = 0; f < taps.size(); ++f) {
+        if (f && taps[f].first == taps[f - 1].first) return no("two ports on one row");
+        a.tap_row.push_back(taps[f].first);
+        a.tap_port.push_back(taps[f].second);
+        a.tap_of_row[taps[f].first] = (int)f;
+    }
+    // value producers and their live ranges (rows)
+    a.prod.assign(std::max(g.ndyn, 1), Prod{});
+    for (int o = 0; o < g.nfast; ++o) {
+        const int v = g.fop_out[o];
+        if (v < 0 || v >= g.ndyn) return no("bad fast-op output");
+        a.prod[v] = Prod{0, o, 0};
+    }
+    for (int o = 0; o < g.nops; ++o) {
+        const int32_t* op = &g.ops[(size_t)o * HVB_OP_WORDS];
+        const int out = op[1] - g.nvc, cnt = op[0] == OP_TLINE ? 9 : 1;
+        for (int e = 0; e < cnt; ++e) {
+            if (out + e < 0 || out + e >= g.ndyn) return no("bad op output");
+            a.prod[out + e] = Prod{1, o, e};
+        }
+    }
+    a.fop_first.assign(std::max(g.nfast, 1), n); a.fop_last.assign(std::max(g.nfast, 1), -1);
+    a.op_first.assign(std::max(g.nops, 1), n); a.op_last.assign(std::max(g.nops, 1), -1);
+    for (int r = 0; r < n; ++r)
+        for (const Entry& en : a.rows[r]) {
+            if (en.vid < g.nvc) continue;
+            const Prod& p = a.prod[en.vid - g.nvc];
+            if (p.kind < 0) return no("value without a producer");
+            std::vector<int>& fi = p.kind == 0 ? a.fop_first : a.op_first;
+            std::vector<int>& la = p.kind == 0 ? a.fop_last : a.op_last;
+            fi[p.idx] = std::min(fi[p.idx], r);
+            la[p.idx] = std::max(la[p.idx], r);
+        }
+    for (int o = 0; o < g.nfast; ++o) if (a.fop_last[o] - a.fop_first[o] > 1) return no("value used in non-adjacent rows");
+    for (int o = 0; o < g.nops; ++o) if (a.op_last[o] >= 0 && a.op_last[o] - a.op_first[o] > 1) return no("value used in non-adjacent rows");
+    a.ok = true;
+    return a;
+}
+
+// constants of one row: literals (unrolled) or per-row table slots (rolled)
+struct Sink {
+    bool rolled;
+    std::vector<int32_t>* itab;
+    std::vector<double>* dtab;
+    int ni = 0, nd = 0;                 // slots used by the current row
+    std::string d(double v) {
+        if (!rolled) {
+            if (std::isnan(v)) return "__longlong_as_double(0x7ff8000000000000LL)";
+            if (std::isinf(v)) return v > 0 ? "__longlong_as_double(0x7ff0000000000000LL)" : "__longlong_as_double(0xfff0000000000000LL)";
+            return fmt("(%a)", v);
+        }
+        dtab->push_back(v);
+        return fmt("__ldg(dt + %d)", nd++);
+    }
+    std::string i(int v) {
+        if (!rolled) return fmt("%d", v);
+        itab->push_back(v);
+        return fmt("__ldg(it + %d)", ni++);
+    }
+};
+
+struct ValRef { std::string re, im; };   // "0" = exactly zero, known at generation time
+
+struct Gen {
+    const GenPlan& g;
+    const Analysis& a;
+    const int32_t* prefs;
+    bool rolled, scratch;
+    int max_vs[2] = {0, 0}, max_vc[2] = {0, 0}, max_vt[2] = {0, 0};
+    std::map<int, std::string> fop_name, op_name;     // producer index -> variable (current rows only)
+    long long flops = 0;
+
+    Gen(const GenPlan& g_, const Analysis& a_, const int32_t* p, bool r, bool s) : g(g_), a(a_), prefs(p), rolled(r), scratch(s) {}
+
+    std::string param(int pi, Sink& s) {
+        const int kind = prefs[2 * pi], idx = prefs[2 * pi + 1];
+        switch (kind) {
+            case PK_CONST: return "D.pv.consts[" + s.i(idx) + "]";
+            case PK_SAMPLE: return "cmk(srow[" + s.i(idx) + "], 0.0)";
+            case PK_SAMPLE_NEG: return "cmk(-srow[" + s.i(idx) + "], 0.0)";
+            case PK_SAMPLE_INV: return "cmk(1.0 / srow[" + s.i(idx) + "], 0.0)";
+            case PK_TABLE: return "D.pv.tables[(long long)" + s.i(idx) + " * D.pv.table_ld + fi]";
+            case PK_SPLINE: return "spline_eval(D.pv.spl_t, D.pv.spl_c, D.pv.spl_trace, D.pv.spl_fill, D.pv.spl_range, " + s.i(idx) + ", f)";
+            case PK_SMD: return "eval_smd(D.pv.consts + " + s.i(idx) + ", f)";
+            case PK_BETA_MUL: return "cmk(__dmul_rn(w, D.pv.consts[" + s.i(idx) + "].x) / HVB_C0, 0.0)";
+            case PK_BETA: return "gen_beta(w, D.pv.consts[" + s.i(idx) + "])";
+        }
+        return "cmk(0.0, 0.0)";
+    }
+
+    // code that evaluates the value ops first used at row r; registers their variable names
+    std::string value_code(int r, Sink& s) {
+        std::string t;
+        const int p = r & 1;
+        int ns = 0, nc = 0, nt = 0;
+        for (int o = 0; o < g.nfast; ++o) {
+            if (a.fop_first[o] != r || a.fop_last[o] < 0) continue;
+            const int code = g.fop_code[o];
+            const std::string name = fmt("vs%d_%d", p, ns++);
+            std::string arg = (code & 4) ? "srow[" + s.i((int)g.fop_arg[o]) + "]" : s.d(g.fop_arg[o]);
+            if (code & 2) arg = "__dmul_rn(w, " + arg + ")";
+            if (code & 1) arg = ((code & 2) ? "-(1.0 / " : "(1.0 / ") + arg + ")";
+            t += "    " + name + " = " + arg + ";\n";
+            fop_name[o] = name;
+        }
+        for (int o = 0; o < g.nops; ++o) {
+            if (a.op_first[o] != r || a.op_last[o] < 0) continue;
+            const int32_t* op = &g.ops[(size_t)o * HVB_OP_WORDS];
+            const int code = op[0];
+            if (code == OP_TLINE) {
+                const std::string name = fmt("vt%d_%d", p, nt++);
+                t += "    eval_tline_fast(" + param(op[2], s) + ", " + param(op[3], s) + ", D.pv.consts[" + s.i(op[4]) + "].x, " + name + ");\n";
+                op_name[o] = name;
+                continue;
+            }
+            const std::string name = fmt("vc%d_%d", p, nc++);
+            const std::string p0 = param(op[2], s);
+            if (code == OP_COPY) t += "    " + name + " = " + p0 + ";\n";
+            else if (code == OP_RECIP) t += "    " + name + " = crecip_np(" + p0 + ");\n";
+            else if (code == OP_CAP) t += "    " + name + " = gen_cap(w, " + p0 + ");\n";
+            else t += "    " + name + " = gen_ind(w, " + p0 + ");\n";
+            op_name[o] = name;
+        }
+        max_vs[p] = std::max(max_vs[p], ns); max_vc[p] = std::max(max_vc[p], nc); max_vt[p] = std::max(max_vt[p], nt);
+        return t;
+    }
+
+    ValRef value(int vid, Sink& s) {
+        if (vid < g.nvc) {
+            const double re = g.const_vals[2 * (size_t)vid], im = g.const_vals[2 * (size_t)vid + 1];
+            return ValRef{re == 0.0 ? "0" : s.d(re), im == 0.0 ? "0" : s.d(im)};
+        }
+        const Prod& p = a.prod[vid - g.nvc];
+        if (p.kind == 0) {
+            const std::string& nm = fop_name[p.idx];
+            return (g.fop_code[p.idx] & 2) ? ValRef{"0", nm} : ValRef{nm, "0"};
+        }
+        const std::string& nm = op_name[p.idx];
+        const bool line = g.ops[(size_t)p.idx * HVB_OP_WORDS] == OP_TLINE;
+        const std::string base = line ? nm + fmt("[%d]", p.sub) : nm;
+        return ValRef{base + ".x", base + ".y"};
+    }
+
+    // one matrix / right-hand-side cell: the entries' values summed in component order (the reference's `+=`)
+    std::string cell(int r, int col, Sink& s) {
+        std::string re, im;
+        auto add = [](std::string& acc, const std::string& term, bool neg) {
+            if (term == "0") return;
+            if (acc.empty()) acc = neg ? "-" + term : term;
+            else acc += (neg ? " - " : " + ") + term;
+        };
+        for (const Entry& en : a.rows[r]) {
+            if (en.col != col) continue;
+            const ValRef v = value(en.vid, s);
+            add(re, v.re, en.neg);
+            add(im, v.im, en.neg);
+        }
+        return "cmk(" + (re.empty() ? std::string("0.0") : re) + ", " + (im.empty() ? std::string("0.0") : im) + ")";
+    }
+
+    // assemble row r: into the current row (r == 0) or the incoming row (r >= 1)
+    std::string assemble(int r, Sink& s) {
+        std::string t = value_code(r, s);
+        const int n = g.n;
+        if (r == 0) {
+            t += "    c0 = " + cell(0, 0, s) + ";\n";
+            t += "    c1 = " + (n > 1 ? cell(0, 1, s) : std::string("cmk(0.0, 0.0)")) + ";\n";
+            t += "    c2 = cmk(0.0, 0.0);\n";
+            if (a.tap_of_row[0] >= 0) t += "    GM_0 = " + cell(0, n + a.tap_port[0], s) + ";\n";
+        } else {
+            t += "    n0 = " + cell(r, r - 1, s) + ";\n";
+            t += "    n1 = " + cell(r, r, s) + ";\n";
+            t += "    n2 = " + (r + 1 < n ? cell(r, r + 1, s) : std::string("cmk(0.0, 0.0)")) + ";\n";
+            if (a.tap_of_row[r] >= 0) t += "    gf = " + cell(r, n + a.tap_port[a.tap_of_row[r]], s) + ";\n";
+        }
+        // values last used here die; forget their names so a stale reference cannot compile silently
+        return t;
+    }
+
+    std::string acc_ref(int o, int j) const {                     // accumulator of (output tap o, source tap j)
+        if (!scratch) return fmt("ACC_%d_%d", o, j);
+        return fmt("Sp[%dLL * D.ldS]", a.tap_port[o] * g.P + a.tap_port[j]);
+    }
+
+    // fold gamma_j * T_o of the epoch that just ended into the pair accumulators; f = taps that are old now
+    std::string flush(int f, bool final_) {
+        std::string t;
+        for (int o = 0; o < f; ++o) {
+            for (int j = 0; j < f; ++j) {
+                const bool first = scratch && o == f - 1;              // first touch of (o, j): see the header comment
+                const std::string prodt = fmt("cmul(GM_%d, TT_%d)", j, o);
+                if (final_) {
+                    t += fmt("    { cplx x = %s; ", prodt.c_str());
+                    if (!first) t += "const cplx x0 = " + acc_ref(o, j) + "; x.x += x0.x; x.y += x0.y; ";
+                    const int po = a.tap_port[o], pj = a.tap_port[j];
+                    t += fmt("x.x = fma(2.0, x.x, %s); x.y = 2.0 * x.y; ", po == pj ? "-1.0" : "0.0");
+                    const double sc = g.epi_scale[(size_t)po * g.P + pj];
+                    if (sc != 1.0) t += fmt("x = cscale(x, %a); ", sc);
+                    t += "if (!(isfinite(x.x) && isfinite(x.y))) bad |= HVB_STATUS_NONFINITE_BIT; ";
+                    t += fmt("Sp[%dLL * D.ldS] = x; }\n", po * g.P + pj);
+                } else if (first) {
+                    t += "    " + acc_ref(o, j) + " = " + prodt + ";\n";
+                } else if (scratch) {
+                    t += "    { cplx x = " + acc_ref(o, j) + fmt("; cfma(x, GM_%d, TT_%d); ", j, o) + acc_ref(o, j) + " = x; }\n";
+                } else {
+                    t += fmt("    cfma(ACC_%d_%d, GM_%d, TT_%d);\n", o, j, j, o);
+                }
+                flops += 8;
+            }
+            if (!final_) t += fmt("    TT_%d = cmk(0.0, 0.0);\n", o);
+        }
+        return t;
+    }
+
+    // elimination step k: nb = ports whose row is <= k, newly = row k is a port row, fresh = row k+1 is a port
+    // row (its source column joins the old ones after this step), last = no row k+1
+    std::string step(int nb, bool newly, bool fresh, bool last) {
+        std::string t;
+        const bool old = nb > 0;                                       // old source columns exist (ports at rows <= k)
+        if (last) {
+            t += "    { double best = fabs(c0.x) + fabs(c0.y); if (!(best >= 0.0)) best = -1.0;\n";
+            t += "      pmin = fmin(pmin, best); pmax = fmax(pmax, best);\n";
+            t += "      const cplx p0 = c0;\n";
+        } else {
+            t += "    { double best = fabs(c0.x) + fabs(c0.y); if (!(best >= 0.0)) best = -1.0;\n";
+            t += "      const double mn = fabs(n0.x) + fabs(n0.y); const bool sw = mn > best; if (sw) best = mn;\n";
+            t += "      pmin = fmin(pmin, best); pmax = fmax(pmax, best);\n";
+            t += "      const cplx p0 = sw ? n0 : c0, p1 = sw ? n1 : c1, p2 = sw ? n2 : c2;\n";
+            t += "      const cplx r0 = sw ? c0 : n0; cplx r1 = sw ? c1 : n1, r2 = sw ? c2 : n2;\n";
+        }
+        t += "      const cplx inv = crecip_fast(p0);\n";
+        flops += 8;
+        if (!last) {
+            t += "      const cplx m = cmul(r0, inv); cfnma(r1, m, p1); cfnma(r2, m, p2);\n";
+            flops += 6 + 16;
+        }
+        if (old) {
+            if (last) t += "      const cplx zeta = z;\n";
+            else {
+                t += "      const cplx zeta = sw ? cmk(0.0, 0.0) : z;\n";
+                t += "      const cplx znext = sw ? z : cneg(cmul(m, z));\n";
+                flops += 6;
+            }
+        }
+        if (fresh) {
+            t += "      const cplx yf = sw ? gf : cmk(0.0, 0.0);\n";
+            t += "      const cplx rf = sw ? cneg(cmul(m, gf)) : gf;\n";
+            flops += 6;
+        }
+        for (int o = 0; o < nb; ++o) {
+            if (newly && o == nb - 1) t += "      { const cplx wk = inv;\n";
+            else {
+                t += fmt("      { cplx wk = cmul(W1_%d, h1); cfma(wk, W2_%d, h2); wk = cneg(cmul(wk, inv));\n", o, o);
+                flops += 6 + 8 + 6;
+            }
+            if (newly && o == nb - 1) t += fmt("        TT_%d = cmul(wk, zeta);\n", o);
+            else t += fmt("        cfma(TT_%d, wk, zeta);\n", o);
+            flops += 8;
+            if (fresh) { t += "        " + acc_ref(o, nb) + " = cmul(wk, yf);\n"; flops += 6; }
+            t += fmt("        W2_%d = W1_%d; W1_%d = wk; }\n", o, o, o);
+        }
+        if (!last) {
+            t += "      h2 = hq; hq = p2; h1 = p1;\n";
+            t += "      c0 = r1; c1 = r2; c2 = cmk(0.0, 0.0);\n";
+            if (old) t += "      z = znext;\n";
+        }
+        if (fresh) {
+            // the source column of port nb becomes an old column: close the epoch
+            t += flush(nb, false);
+            for (int j = 0; j < nb; ++j) { t += fmt("      GM_%d = cmul(GM_%d, z);\n", j, j); flops += 6; }
+            t += fmt("      GM_%d = rf; z = cmk(1.0, 0.0);\n", nb);
+        }
+        t += "    }\n";
+        return t;
+    }
+};
+
+}  // namespace
+
+bool hvb_gen_supported(const GenPlan& g, std::string* why) {
+    const Analysis a = analyse(g);
+    if (why) *why = a.why;
+    return a.ok;
+}
+
+int hvb_gen_source(const GenPlan& g, const int32_t* prefs, int mode, const char* prelude, GenResult* out, std::string* err) {
+    const Analysis a = analyse(g);
+    if (!a.ok) { if (err) *err = a.why; return -1; }
+    const int n = g.n, P = g.P;
+    const bool rolled = mode == 2 || (mode == 0 && n > HVB_GEN_UNROLL_MAX);
+    const bool scratch = P > HVB_GEN_REG_ACC_PORTS;
+    out->rolled = rolled;
+    out->scratch_acc = scratch;
+    out->rows.clear(); out->itab.clear(); out->dtab.clear();
+    Gen G(g, a, prefs, rolled, scratch);
+
+    // nb(k): ports at rows <= k
+    std::vector<int> nb(n, 0);
+    { int c = 0; for (int k = 0; k < n; ++k) { if (a.tap_of_row[k] >= 0) ++c; nb[k] = c; } }
+
+    std::string body;                   // code of one point, after row 0 is assembled
+    Sink s0{false, &out->itab, &out->dtab};
+    std::string head = G.assemble(0, s0);            // row 0 is always literal code
+    std::vector<std::string> asm_cases, step_cases;
+    std::map<std::string, int> asm_id, step_id;
+    if (!rolled) {
+        for (int k = 0; k + 1 < n; ++k) {
+            Sink s{false, &out->itab, &out->dtab};
+            body += fmt("    // ---- row %d enters, column %d is eliminated\n", k + 1, k);
+            body += G.assemble(k + 1, s);
+            body += G.step(nb[k], a.tap_of_row[k] >= 0, a.tap_of_row[k + 1] >= 0, false);
+        }
+    } else {
+        for (int k = 0; k + 1 < n; ++k) {
+            Sink s{true, &out->itab, &out->dtab};
+            const int ib = (int)out->itab.size(), db = (int)out->dtab.size();
+            const std::string at = G.assemble(k + 1, s);
+            const long long fl0 = G.flops;
+            const std::string st = G.step(nb[k], a.tap_of_row[k] >= 0, a.tap_of_row[k + 1] >= 0, false);
+            auto ia = asm_id.find(at);
+            int ca, cs;
+            if (ia == asm_id.end()) { ca = (int)asm_cases.size(); asm_id[at] = ca; asm_cases.push_back(at); } else ca = ia->second;
+            auto is = step_id.find(st);
+            if (is == step_id.end()) { cs = (int)step_cases.size(); step_id[st] = cs; step_cases.push_back(st); } else cs = is->second;
+            (void)fl0;
+            out->rows.push_back(ca); out->rows.push_back(cs); out->rows.push_back(ib); out->rows.push_back(db);
+        }
+        body += "    for (int k = 0; k < " + std::to_string(n - 1) + "; ++k) {\n";
+        body += "      const int4 rw = __ldg(reinterpret_cast<const int4*>(D.gen_rows) + k);\n";
+        body += "      const int* __restrict__ it = D.gen_itab + rw.z; const double* __restrict__ dt = D.gen_dtab + rw.w;\n";
+        body += "      switch (rw.x) {\n";
+        for (size_t c = 0; c < asm_cases.size(); ++c) body += fmt("      case %d: {\n", (int)c) + asm_cases[c] + "      } break;\n";
+        body += "      }\n      switch (rw.y) {\n";
+        for (size_t c = 0; c < step_cases.size(); ++c) body += fmt("      case %d:\n", (int)c) + step_cases[c] + "      break;\n";
+        body += "      }\n    }\n";
+        out->n_cases = (int)(asm_cases.size() + step_cases.size());
+    }
+    body += "    // ---- last column\n";
+    body += G.step(nb[n - 1], a.tap_of_row[n - 1] >= 0, false, true);
+    body += "    // ---- fold the last epoch, voltages -> S (solvers/spfn.py:159-176, closed form for ground-referenced ports)\n";
+    body += G.flush(P, true);
+
+    // ---- declarations ------------------------------------------------------------------------
+    std::string decl;
+    for (int p = 0; p < 2; ++p) {
+        for (int i = 0; i < G.max_vs[p]; ++i) decl += fmt("    double vs%d_%d;\n", p, i);
+        for (int i = 0; i < G.max_vc[p]; ++i) decl += fmt("    cplx vc%d_%d;\n", p, i);
+        for (int i = 0; i < G.max_vt[p]; ++i) decl += fmt("    cplx vt%d_%d[9];\n", p, i);
+    }
+    decl += "    cplx c0, c1, c2, n0 = cmk(0.0, 0.0), n1 = n0, n2 = n0, gf = n0, z = cmk(1.0, 0.0), h1 = n0, h2 = n0, hq = n0;\n";
+    for (int o = 0; o < P; ++o) decl += fmt("    cplx W1_%d = cmk(0.0, 0.0), W2_%d = W1_%d, TT_%d = W1_%d, GM_%d = W1_%d;\n", o, o, o, o, o, o, o);
+    if (!scratch)
+        for (int o = 0; o < P; ++o)
+            for (int j = 0; j < P; ++j) decl += fmt("    cplx ACC_%d_%d = cmk(0.0, 0.0);\n", o, j);
+
+    std::string src;
+    src += "// generated by heavi_b200 (csrc/hvb_gen.cpp): kernel D for one netlist\n";
+    src += prelude;
+    src += "\n__device__ __forceinline__ void cfma(cplx& acc, cplx a, cplx b) {\n"
+           "    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);\n"
+           "    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);\n}\n"
+           "__device__ __forceinline__ cplx gen_beta(double w, cplx s) {\n"
+           "    const double b0 = w / HVB_C0;\n"
+           "    return cmk(__dmul_rn(b0, s.x), s.y == 0.0 ? 0.0 : __dmul_rn(b0, s.y));\n}\n"
+           "__device__ __forceinline__ cplx gen_cap(double w, cplx p0) {\n"
+           "    return (p0.y == 0.0) ? cmk(0.0, __dmul_rn(w, p0.x)) : cmk(-__dmul_rn(w, p0.y), __dmul_rn(w, p0.x));\n}\n"
+           "__device__ __forceinline__ cplx gen_ind(double w, cplx p0) {\n"
+           "    if (p0.y == 0.0) return cmk(0.0, -(1.0 / __dmul_rn(w, p0.x)));\n"
+           "    return cdiv_np(cmk(1.0, 0.0), cmk(-__dmul_rn(w, p0.y), __dmul_rn(w, p0.x)));\n}\n\n";
+    out->kernel_name = "hvb_gen_kernel";
+    src += "extern \"C\" __global__ void __launch_bounds__(128) hvb_gen_kernel(const HvbDev D) {\n";
+    src += "  const long long T = (long long)gridDim.x * blockDim.x;\n";
+    src += "  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;\n";
+    src += "  const long long total = D.nS * D.nF;\n  unsigned bad = 0;\n";
+    src += "  for (long long q = t0; q < total; q += T) {\n";
+    src += "    const long long s = q / D.nF, fi = q - s * D.nF;\n";
+    src += "    const double f = __ldg(D.f + fi);\n";
+    src += "    if (D.f32 && s == 0) D.f32[fi] = (float)f;\n";
+    src += "    const double* __restrict__ srow = D.samples + s * D.nR; (void)srow;\n";
+    src += "    const double w = __dmul_rn(HVB_TWOPI, f); (void)w;\n";
+    src += fmt("    cplx* __restrict__ Sp = D.S + s * %dLL * D.ldS + fi;\n", P * P);
+    src += "    double pmin = 1e300, pmax = 0.0;\n";
+    src += decl;
+    src += "    // ---- row 0\n" + head + body;
+    src += "    if (!(pmin >= 2.2250738585072014e-308)) bad |= HVB_STATUS_ZERO_PIVOT_BIT;\n";
+    src += "    if (!(pmax <= 1.7976931348623157e308)) bad |= HVB_STATUS_NONFINITE_BIT;\n";
+    src += "  }\n  if (bad && D.status) atomicOr(D.status, (int)bad);\n}\n";
+    out->src.swap(src);
+    out->flops_per_solve = G.flops;
+    return 0;
+}

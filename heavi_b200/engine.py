@@ -44,12 +44,19 @@ class RunArgs(C.Structure):
 
 class KernelInfo(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("kernel_class", "group", "pmax", "threads", "smem_bytes", "regs",
-                                         "ctas_per_sm", "sm_count", "rows_per_lane", "stream_words")] + [("launches", C.c_int64)]
+                                         "ctas_per_sm", "sm_count", "rows_per_lane", "stream_words")] + [("launches", C.c_int64)] + [
+        (k, C.c_int32) for k in ("gen_rolled", "gen_cases", "local_bytes", "gen_scratch_acc")] + [("gen_flops_per_solve", C.c_int64)]
+
+
+class CodegenInfo(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("supported", "rolled", "n_cases", "scratch_acc")] + [
+        (k, C.c_int64) for k in ("src_len", "n_rows", "n_itab", "n_dtab", "flops_per_solve")] + [("reason", C.c_char * 256)]
 
 
 EXPORTS = ("hvb_warp_shape", "hvb_plan_create", "hvb_plan_destroy", "hvb_run_host", "hvb_run_device",
            "hvb_run_stats_host", "hvb_assemble_host",
-           "hvb_plan_kernel_info", "hvb_measure_dfma_peak", "hvb_last_error", "hvb_version")
+           "hvb_plan_kernel_info", "hvb_measure_dfma_peak", "hvb_last_error", "hvb_version",
+           "hvb_codegen_source", "hvb_codegen_compile")
 
 _lib = None
 
@@ -82,6 +89,11 @@ def load_library():
     lib.hvb_plan_kernel_info.restype = C.c_int
     lib.hvb_measure_dfma_peak.argtypes = [C.c_int, _f64p]
     lib.hvb_measure_dfma_peak.restype = C.c_int
+    lib.hvb_codegen_source.argtypes = [C.POINTER(PlanDesc), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                       C.c_void_p, C.POINTER(CodegenInfo)]
+    lib.hvb_codegen_source.restype = C.c_int
+    lib.hvb_codegen_compile.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    lib.hvb_codegen_compile.restype = C.c_int
     lib.hvb_last_error.restype = C.c_char_p
     lib.hvb_version.restype = C.c_char_p
     _lib = lib
@@ -128,23 +140,18 @@ def _ptr(a: np.ndarray):
     return a.__array_interface__["data"][0] if a is not None and a.size else None
 
 
-class DevicePlanHandle:
-    """Owns one `hvb_plan*`."""
+def make_desc(plan: pl.DevicePlan, kernel_hint: int = 0):
+    """(PlanDesc, arrays it points into) for a compiled plan."""
+    keep = {}
 
-    def __init__(self, plan: pl.DevicePlan, device: int | None = None, kernel_hint: int = 0):
-        """`kernel_hint`: 0 library decides, 1 dense kernels only, 2 banded kernel when the structure allows."""
-        self.lib = load_library()
-        self.plan = plan
-        self.device = current_device() if device is None else device
-        keep = self._keep = {}
+    def arr(name, a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        if a.size == 0:
+            a = np.zeros(1, dtype=dt)
+        keep[name] = a
+        return a
 
-        def arr(name, a, dt):
-            a = np.ascontiguousarray(a, dtype=dt)
-            if a.size == 0:
-                a = np.zeros(1, dtype=dt)
-            keep[name] = a
-            return a
-
+    if True:
         d = PlanDesc()
         d.n, d.ncols, d.P = plan.n, plan.ncols, plan.P
         d.n_consts, d.n_prefs = len(plan.consts), len(plan.prefs)
@@ -174,6 +181,49 @@ class DevicePlanHandle:
         d.spl_trace = arr("str", plan.spl_trace, np.int32).ctypes.data_as(_i32p)
         d.spl_fill = arr("sf", plan.spl_fill, np.complex128).ctypes.data_as(_f64p)
         d.spl_range = arr("sr", plan.spl_range, np.float64).ctypes.data_as(_f64p)
+    return d, keep
+
+
+def codegen_source(plan: pl.DevicePlan, prefs: np.ndarray | None = None, mode: int = 0) -> dict:
+    """Source of the kernel the library would generate for `plan` (kernel class 3), without touching a
+    GPU: {"supported", "reason", "src", "rolled", "rows", "itab", "dtab", "n_cases", "flops_per_solve"}."""
+    lib = load_library()
+    d, keep = make_desc(plan, 2)
+    prefs = np.ascontiguousarray(plan.prefs if prefs is None else prefs, dtype=np.int32)
+    info = CodegenInfo()
+    _check(lib.hvb_codegen_source(C.byref(d), _ptr(prefs), mode, None, 0, None, None, None, C.byref(info)))
+    out = {"supported": bool(info.supported), "reason": info.reason.decode(), "rolled": bool(info.rolled),
+           "n_cases": info.n_cases, "scratch_acc": bool(info.scratch_acc), "flops_per_solve": info.flops_per_solve}
+    if not info.supported:
+        return out
+    src = C.create_string_buffer(info.src_len + 1)
+    rows = np.zeros(max(info.n_rows, 1), dtype=np.int32)
+    itab = np.zeros(max(info.n_itab, 1), dtype=np.int32)
+    dtab = np.zeros(max(info.n_dtab, 1), dtype=np.float64)
+    _check(lib.hvb_codegen_source(C.byref(d), _ptr(prefs), mode, C.cast(src, C.c_void_p), info.src_len + 1,
+                                  _ptr(rows), _ptr(itab), _ptr(dtab), C.byref(info)))
+    out.update(src=src.value.decode(), rows=rows[:info.n_rows], itab=itab[:info.n_itab], dtab=dtab[:info.n_dtab])
+    return out
+
+
+def codegen_compile(src: str) -> str:
+    """NVRTC-compile generated source for sm_100a (no GPU needed); returns the compiler log, raises on errors."""
+    lib = load_library()
+    log = C.create_string_buffer(1 << 16)
+    size = C.c_int64(0)
+    _check(lib.hvb_codegen_compile(src.encode(), C.cast(log, C.c_void_p), len(log), C.byref(size)))
+    return log.value.decode()
+
+
+class DevicePlanHandle:
+    """Owns one `hvb_plan*`."""
+
+    def __init__(self, plan: pl.DevicePlan, device: int | None = None, kernel_hint: int = 0):
+        """`kernel_hint`: 0 library decides, 1 dense kernels only, 2 banded / generated kernel when the structure allows."""
+        self.lib = load_library()
+        self.plan = plan
+        self.device = current_device() if device is None else device
+        d, self._keep = make_desc(plan, kernel_hint)
         handle = C.c_void_p()
         _check(self.lib.hvb_plan_create(C.byref(d), self.device, C.byref(handle)))
         self.handle = handle
@@ -298,6 +348,20 @@ class CompiledNetwork:
     def __init__(self, net, mode: str | None = None, device: int | None = None):
         self.table = net.stamp_table()
         mode = mode or os.environ.get("HVB_MODE", "auto")
+        self._dump = None
+        # chain-like netlists (ladders, filters, cascaded lines: tridiagonal after the bandwidth-reducing
+        # order): the library generates a kernel for exactly this netlist (kernel class 3), which serves
+        # every batch size
+        if os.environ.get("HVB_NO_GEN") != "1" and os.environ.get("HVB_FORCE_BLOCK") != "1":
+            try:
+                cplan = pl.compile_plan(self.table, mode, order="rcm")
+            except ValueError:
+                cplan = None
+            if cplan is not None and cplan.band == 1 and cplan.epi_simple and not len(cplan.coops):
+                handle = DevicePlanHandle(cplan, device, kernel_hint=2)
+                if handle.kernel_info()["kernel_class"] == 3:
+                    self.plan, self.handle, self.rows_per_lane, self._band = cplan, handle, 1, False
+                    return
         plan = pl.compile_plan(self.table, mode)
         shape = warp_shape(plan.n_real, plan.P, plan.max_nport)
         if shape is not None and shape != (plan.n, plan.ncols - plan.n):
@@ -305,7 +369,6 @@ class CompiledNetwork:
         self.plan = plan
         self.handle = DevicePlanHandle(self.plan, device, kernel_hint=1 if shape is not None else 0)
         self.rows_per_lane = self.handle.kernel_info()["rows_per_lane"]
-        self._dump = None
         self._band = None            # (plan, handle) | False once known not to exist
         if shape is None or os.environ.get("HVB_NO_BAND") == "1" or plan.n_real < pl.BAND_SMALL_MIN_ROWS:
             self._band = False

@@ -155,7 +155,8 @@ int hvb_warp_shape(int32_t n, int32_t P, int32_t max_nport, int32_t* n_pad, int3
 
 /* Introspection for the benchmark / tests. */
 typedef struct hvb_kernel_info {
-    int32_t kernel_class;   /* 0 = warp kernel (n <= 32), 1 = dense block kernel, 2 = banded kernel */
+    int32_t kernel_class;   /* 0 = warp kernel (n <= 32), 1 = dense block kernel, 2 = banded kernel,
+                               3 = generated chain kernel (see hvb_codegen_source)                */
     int32_t group;          /* warp kernel: padded rows N;  block kernel: panel width NB;
                                banded kernel: instantiated half bandwidth B                       */
     int32_t pmax;           /* warp kernel: padded RHS columns                                   */
@@ -168,8 +169,35 @@ typedef struct hvb_kernel_info {
     int32_t stream_words;   /* banded kernel: complex words of pivot-row records one point writes
                                to global memory once and reads back once; 0 for the other classes */
     int64_t launches;       /* kernel launches issued by this plan so far                        */
+    int32_t gen_rolled;     /* generated kernel: -1 not compiled yet, 0 straight-line, 1 row loop */
+    int32_t gen_cases;      /* generated kernel, row loop: distinct row shapes                    */
+    int32_t local_bytes;    /* generated kernel: local memory per thread (spills)                 */
+    int32_t gen_scratch_acc;/* generated kernel: port-pair sums kept in the output array (P > 4)  */
+    int64_t gen_flops_per_solve; /* generated kernel: executed real flops of elimination + port
+                               recurrences per point (stamp values excluded)                      */
 } hvb_kernel_info;
 int hvb_plan_kernel_info(hvb_plan* plan, hvb_kernel_info* out);
+
+/* Kernel class 3, "generated": when the netlist is a chain -- the MNA matrix is tridiagonal in the plan's
+ * row order, every port is ground-referenced with a constant real Z0 -- the library writes CUDA source for
+ * exactly this netlist (stamp formulas, matrix cells and port positions as straight-line code or a loop over
+ * row shapes), compiles it with NVRTC for sm_100a at the first run and launches one thread per point.  It
+ * replaces the same reference lines as hvb_run_host (network.py:385-416, solvers/spfn.py:106-179).
+ * The two entries below are host-only (no CUDA call, usable without a GPU): they return that source
+ * and check that it compiles.  Call hvb_codegen_source with NULL buffers first to get the sizes. */
+typedef struct hvb_codegen_info {
+    int32_t supported;      /* 0: the plan cannot be served by a generated kernel, see `reason`   */
+    int32_t rolled;
+    int32_t n_cases;
+    int32_t scratch_acc;
+    int64_t src_len;        /* strlen of the source                                               */
+    int64_t n_rows, n_itab, n_dtab;   /* elements of the row-loop tables (0 for straight-line code) */
+    int64_t flops_per_solve;
+    char reason[256];
+} hvb_codegen_info;
+int hvb_codegen_source(const hvb_plan_desc* desc, const int32_t* prefs, int32_t mode, char* src_out, int64_t src_cap,
+                       int32_t* rows_out, int32_t* itab_out, double* dtab_out, hvb_codegen_info* info);
+int hvb_codegen_compile(const char* src, char* log_out, int64_t log_cap, int64_t* cubin_bytes);
 
 /* FP64 FMA peak of the device, measured with a register-resident DFMA loop on `stream`
  * (TFLOP/s).  bench.py uses it as the roofline denominator because MEASURED_PEAKS.json has no
