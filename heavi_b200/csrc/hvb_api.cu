@@ -10,6 +10,7 @@
 #include <cstring>
 #include <ctime>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/heavi_b200.h"
@@ -99,6 +100,9 @@ struct hvb_plan {
     int max_grid = 0;
     int64_t launches = 0;
     // kernel D (generated): host copy of the plan the generator reads, compiled variants, the active one
+    std::vector<char> pushed;                          // consts + prefs as last uploaded by push_params
+    bool pushed_valid = false;
+    cudaStream_t pushed_stream = nullptr;
     GenPlan gen;
     std::vector<GenKernel*> gen_variants;
     GenKernel* gk = nullptr;
@@ -267,6 +271,8 @@ static bool band_kernel_ok(const hvb_plan* pl) {
 static bool gen_kernel_ok(const hvb_plan* pl) {
     const char* off = getenv("HVB_NO_GEN");
     if (off && off[0] == '1') return false;
+    const char* nb = getenv("HVB_NO_BAND");                 // "dense kernels only" also rules out the chain kernel
+    if (nb && nb[0] == '1') return false;
     const char* force = getenv("HVB_FORCE_BLOCK");
     if (force && force[0] == '1') return false;
     if (pl->d.kernel_hint == 1) return false;
@@ -304,7 +310,8 @@ static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs) {
     if (hvb_jit_load(*cubin, res.kernel_name.c_str(), &gk->k, &err) != 0) return fail(HVB_ERR_CUDA, "%s", err.c_str());
     gk->rolled = res.rolled; gk->scratch_acc = res.scratch_acc; gk->n_cases = res.n_cases; gk->flops = res.flops_per_solve;
     gk->prefs.assign(prefs, prefs + np);
-    if (res.rolled) {
+    pl->threads = res.threads;
+    if (res.rolled && !res.tables_in_source) {
         CU(upload(gk->rows, res.rows.data(), res.rows.size() * 4));
         CU(upload(gk->itab, res.itab.data(), res.itab.size() * 4));
         CU(upload(gk->dtab, res.dtab.data(), res.dtab.size() * 8));
@@ -540,6 +547,19 @@ extern "C" int hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan**
     return HVB_OK;
 }
 
+extern "C" int hvb_plan_set_tunable(hvb_plan* pl, const char* name, double value) {
+    if (!pl || !name) return fail(HVB_ERR_ARG, "null argument");
+    const std::string n = name;
+    if (n == "chunk_mb") pl->env_chunk_mb = (int64_t)value;
+    else if (n == "min_slab") pl->env_min_slab = (int64_t)value;
+    else if (n == "stats_mb") pl->env_stats_mb = (int64_t)value;
+    else if (n == "band_tile_waves") pl->env_tile_waves = value;
+    else if (n == "copy2d") pl->env_copy2d = value != 0.0;
+    else if (n == "band_pfb") pl->env_band_pfb = (int)value;
+    else return fail(HVB_ERR_ARG, "unknown tunable '%s'", name);
+    return HVB_OK;
+}
+
 extern "C" void hvb_plan_destroy(hvb_plan* pl) {
     if (!pl) return;
     cudaSetDevice(pl->device);
@@ -624,8 +644,18 @@ static int push_params(hvb_plan* pl, const hvb_run_args* a, cudaStream_t st) {
     const hvb_plan_desc& d = pl->d;
     const size_t cb = (size_t)d.n_consts * 16, pb = (size_t)d.n_prefs * 8;
     if ((cb && !a->consts) || (pb && !a->prefs)) return fail(HVB_ERR_ARG, "consts/prefs missing");
+    // unchanged since the last upload on this plan (the usual case for repeated sweeps): nothing to copy.
+    // The device copy is only ever written by this function, stream-ordered before the kernels that read it.
+    if (pl->pushed_valid && pl->pushed.size() == cb + pb && (cb == 0 || memcmp(pl->pushed.data(), a->consts, cb) == 0) &&
+        (pb == 0 || memcmp(pl->pushed.data() + cb, a->prefs, pb) == 0) && pl->pushed_stream == st)
+        return HVB_OK;
     // the previous run's copy out of the staging buffer must have finished
     CU(cudaEventSynchronize(pl->upload_done));
+    pl->pushed.resize(cb + pb);
+    if (cb) memcpy(pl->pushed.data(), a->consts, cb);
+    if (pb) memcpy(pl->pushed.data() + cb, a->prefs, pb);
+    pl->pushed_valid = true;
+    pl->pushed_stream = st;
     char* hs = (char*)pl->h_stage;
     if (cb) memcpy(hs, a->consts, cb);
     if (pb) memcpy(hs + (size_t)std::max(d.n_consts, 1) * 16, a->prefs, pb);
@@ -706,6 +736,8 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     if ((d.n_consts && !a->consts) || (d.n_prefs && !a->prefs)) return fail(HVB_ERR_ARG, "consts/prefs missing");
     if (pl->kclass == 3 && (rc = ensure_gen_kernel(pl, a->prefs)) != HVB_OK) return rc;
     cudaStream_t s0 = pl->streams[0], s1 = pl->streams[1];
+    if (a->out_ld != 0 && a->out_ld < nF) return fail(HVB_ERR_ARG, "out_ld=%lld is smaller than nF=%lld", (long long)a->out_ld, (long long)nF);
+    const int64_t ldo = a->out_ld ? a->out_ld : nF;       // frequency pitch of the caller's array
     static const bool trace = getenv("HVB_TRACE") != nullptr;
     timespec tsp[8]; int ntp = 0;
     auto mark = [&]() { if (trace && ntp < 8) clock_gettime(CLOCK_MONOTONIC, &tsp[ntp++]); };
@@ -801,19 +833,19 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
             // the points of sample 0 also round their frequency to float32 (`Sparameters.f`, network.py:407,421)
             D.f32 = (a->f32_out && sb == 0) ? (float*)pl->f32.p + fb : nullptr;
             rc = launch(pl, D, st, tile & 1);
-            if (rc) return rc;
-            // rows of nf elements, one per (sample, j, i); destination pitch is the full nF
-            char* dst = (char*)S_out + ((size_t)sb * PP * nF + (size_t)fb) * 16;
+            if (rc) { cudaStreamSynchronize(s0); cudaStreamSynchronize(s1); return rc; }   // nothing in flight touches the caller's buffers after an error
+            // rows of nf elements, one per (sample, j, i); destination pitch is the caller's (default: the full nF)
+            char* dst = (char*)S_out + ((size_t)sb * PP * ldo + (size_t)fb) * 16;
             // contiguous destination -> one plain copy; otherwise one strided 2-D copy
             const int64_t rows = ns * PP;
-            if (nf == nF) {
+            if (nf == ldo) {
                 CU(cudaMemcpyAsync(dst, D.S, (size_t)rows * nf * 16, cudaMemcpyDeviceToHost, st));
             } else if (rows <= 64 && !copy2d) {
                 for (int64_t rr = 0; rr < rows; ++rr)
-                    CU(cudaMemcpyAsync(dst + (size_t)rr * nF * 16, (const char*)D.S + (size_t)rr * nf * 16, (size_t)nf * 16,
+                    CU(cudaMemcpyAsync(dst + (size_t)rr * ldo * 16, (const char*)D.S + (size_t)rr * nf * 16, (size_t)nf * 16,
                                        cudaMemcpyDeviceToHost, st));
             } else {
-                CU(cudaMemcpy2DAsync(dst, (size_t)nF * 16, D.S, (size_t)nf * 16, (size_t)nf * 16, (size_t)rows,
+                CU(cudaMemcpy2DAsync(dst, (size_t)ldo * 16, D.S, (size_t)nf * 16, (size_t)nf * 16, (size_t)rows,
                                      cudaMemcpyDeviceToHost, st));
             }
         }
@@ -832,6 +864,70 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
         fprintf(stderr, "hvb_run_host: staged+H2D queued %.1f us, tiles queued %.1f, synced %.1f (tiles=%d)\n", us(1), us(2), us(4), tile);
     }
     if (status_out) *status_out = *pl->h_status;
+    return HVB_OK;
+}
+
+extern "C" int hvb_run_host_multi(hvb_plan* const* plans, int32_t nplans, const hvb_run_args* a, double* S_out, int32_t* status_out) {
+    if (!plans || nplans < 1 || !a) return fail(HVB_ERR_ARG, "null argument");
+    for (int k = 0; k < nplans; ++k) {
+        if (!plans[k]) return fail(HVB_ERR_ARG, "null plan");
+        if (plans[k]->d.n != plans[0]->d.n || plans[k]->d.P != plans[0]->d.P || plans[k]->d.n_prefs != plans[0]->d.n_prefs)
+            return fail(HVB_ERR_ARG, "plans are not replicas of one netlist");
+    }
+    if (nplans == 1) return hvb_run_host(plans[0], a, S_out, status_out);
+    if (a->out_ld != 0) return fail(HVB_ERR_ARG, "out_ld must be 0 for the multi-device entry");
+    const int64_t nF = a->nF, nS = a->nS;
+    if (nF < 0 || nS < 1) return fail(HVB_ERR_ARG, "bad nF=%lld nS=%lld", (long long)nF, (long long)nS);
+    const int64_t PP = (int64_t)plans[0]->d.P * plans[0]->d.P;
+    const bool by_sample = nS >= nplans;
+    const int64_t total = by_sample ? nS : nF;
+    std::vector<int> rcs((size_t)nplans, HVB_OK);
+    std::vector<int32_t> sts((size_t)nplans, 0);
+    std::vector<std::string> errs((size_t)nplans);
+    std::vector<std::thread> threads;
+    auto block = [&](int k, int64_t* lo, int64_t* hi) {          // same contiguous near-equal split as sharding.split_range
+        const int64_t base = total / nplans, extra = total % nplans;
+        *lo = k * base + std::min<int64_t>(k, extra);
+        *hi = *lo + base + (k < extra ? 1 : 0);
+    };
+    for (int k = 0; k < nplans; ++k) {
+        threads.emplace_back([&, k]() {
+            int64_t lo, hi;
+            block(k, &lo, &hi);
+            if (hi <= lo) return;
+            hvb_run_args b = *a;
+            double* out = S_out;
+            if (by_sample) {
+                b.nS = hi - lo;
+                if (a->samples) b.samples = a->samples + lo * plans[k]->d.n_samples_cols;
+                out = S_out + (size_t)lo * PP * nF * 2;
+                if (lo != 0) b.f32_out = nullptr;               // the float32 axis comes from the block that holds sample 0
+            } else {
+                b.nF = hi - lo;
+                b.f = a->f + lo;
+                if (a->tables) b.tables = nullptr;               // handled below: tables are per-frequency rows of pitch nF
+                out = S_out + (size_t)lo * 2;
+                b.out_ld = nF;
+                if (a->f32_out) b.f32_out = a->f32_out + lo;
+            }
+            std::vector<double> tab;
+            if (!by_sample && a->n_tables > 0) {                 // this slab's columns of every table, made contiguous
+                tab.resize((size_t)a->n_tables * (hi - lo) * 2);
+                for (int t = 0; t < a->n_tables; ++t)
+                    memcpy(&tab[(size_t)t * (hi - lo) * 2], a->tables + ((size_t)t * nF + lo) * 2, (size_t)(hi - lo) * 16);
+                b.tables = tab.data();
+            }
+            rcs[k] = hvb_run_host(plans[k], &b, out, &sts[k]);
+            if (rcs[k] != HVB_OK) errs[k] = g_err;               // g_err is thread-local
+        });
+    }
+    for (std::thread& t : threads) t.join();
+    int32_t st = 0;
+    for (int k = 0; k < nplans; ++k) {
+        if (rcs[k] != HVB_OK) return fail(rcs[k], "device %d: %s", plans[k]->device, errs[k].c_str());
+        st |= sts[k];
+    }
+    if (status_out) *status_out = st;
     return HVB_OK;
 }
 

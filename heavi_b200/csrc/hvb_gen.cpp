@@ -64,6 +64,7 @@ struct Analysis {
     std::vector<int> tap_row, tap_port, tap_of_row;
     std::vector<Prod> prod;
     std::vector<int> fop_first, fop_last, op_first, op_last;
+    std::vector<unsigned> op_submask;             // outputs of a (line) op that some matrix cell sums
     std::string why;
     bool ok = false;
 };
@@ -135,6 +136,7 @@ Analysis analyse(const GenPlan& g) {
     }
     a.fop_first.assign(std::max(g.nfast, 1), n); a.fop_last.assign(std::max(g.nfast, 1), -1);
     a.op_first.assign(std::max(g.nops, 1), n); a.op_last.assign(std::max(g.nops, 1), -1);
+    a.op_submask.assign(std::max(g.nops, 1), 0u);
     for (int r = 0; r < n; ++r)
         for (const Entry& en : a.rows[r]) {
             if (en.vid < g.nvc) continue;
@@ -144,6 +146,7 @@ Analysis analyse(const GenPlan& g) {
             std::vector<int>& la = p.kind == 0 ? a.fop_last : a.op_last;
             fi[p.idx] = std::min(fi[p.idx], r);
             la[p.idx] = std::max(la[p.idx], r);
+            if (p.kind == 1) a.op_submask[p.idx] |= 1u << p.sub;
         }
     for (int o = 0; o < g.nfast; ++o) if (a.fop_last[o] - a.fop_first[o] > 1) return no("value used in non-adjacent rows");
     for (int o = 0; o < g.nops; ++o) if (a.op_last[o] >= 0 && a.op_last[o] - a.op_first[o] > 1) return no("value used in non-adjacent rows");
@@ -164,12 +167,12 @@ struct Sink {
             return fmt("(%a)", v);
         }
         dtab->push_back(v);
-        return fmt("__ldg(dt + %d)", nd++);
+        return fmt("dt[%d]", nd++);
     }
     std::string i(int v) {
         if (!rolled) return fmt("%d", v);
         itab->push_back(v);
-        return fmt("__ldg(it + %d)", ni++);
+        return fmt("it[%d]", ni++);
     }
 };
 
@@ -180,8 +183,9 @@ struct Gen {
     const Analysis& a;
     const int32_t* prefs;
     bool rolled, scratch;
-    int max_vs[2] = {0, 0}, max_vc[2] = {0, 0}, max_vt[2] = {0, 0};
+    int max_vs[2] = {0, 0}, max_vc[2] = {0, 0}, max_vt[2] = {0, 0}, max_vl[2] = {0, 0};
     std::map<int, std::string> fop_name, op_name;     // producer index -> variable (current rows only)
+    std::map<int, bool> op_chain_form;                // line op evaluated in the two-value form (y11 = y22, y12 = y21)
     long long flops = 0;
 
     Gen(const GenPlan& g_, const Analysis& a_, const int32_t* p, bool r, bool s) : g(g_), a(a_), prefs(p), rolled(r), scratch(s) {}
@@ -206,14 +210,14 @@ struct Gen {
     std::string value_code(int r, Sink& s) {
         std::string t;
         const int p = r & 1;
-        int ns = 0, nc = 0, nt = 0;
+        int ns = 0, nc = 0, nt = 0, nl = 0;
         for (int o = 0; o < g.nfast; ++o) {
             if (a.fop_first[o] != r || a.fop_last[o] < 0) continue;
             const int code = g.fop_code[o];
             const std::string name = fmt("vs%d_%d", p, ns++);
             std::string arg = (code & 4) ? "srow[" + s.i((int)g.fop_arg[o]) + "]" : s.d(g.fop_arg[o]);
             if (code & 2) arg = "__dmul_rn(w, " + arg + ")";
-            if (code & 1) arg = ((code & 2) ? "-(1.0 / " : "(1.0 / ") + arg + ")";
+            if (code & 1) arg = ((code & 2) ? "-rcp_fast(" : "rcp_fast(") + arg + ")";      // <= ~1 ulp; the assembly dump keeps the IEEE division
             t += "    " + name + " = " + arg + ";\n";
             fop_name[o] = name;
         }
@@ -222,9 +226,18 @@ struct Gen {
             const int32_t* op = &g.ops[(size_t)o * HVB_OP_WORDS];
             const int code = op[0];
             if (code == OP_TLINE) {
+                if ((a.op_submask[o] & ~0xFu) == 0) {
+                    // both terminals' reference is ground: only y11 = y22 and y12 = y21 are stamped (det(ABCD) = 1)
+                    const std::string name = fmt("vl%d_%d", p, nl++);
+                    t += "    gen_tline_chain(" + param(op[2], s) + ", " + param(op[3], s) + ", D.pv.consts[" + s.i(op[4]) + "].x, " + name + "a, " + name + "b);\n";
+                    op_name[o] = name;
+                    op_chain_form[o] = true;
+                    continue;
+                }
                 const std::string name = fmt("vt%d_%d", p, nt++);
                 t += "    eval_tline_fast(" + param(op[2], s) + ", " + param(op[3], s) + ", D.pv.consts[" + s.i(op[4]) + "].x, " + name + ");\n";
                 op_name[o] = name;
+                op_chain_form[o] = false;
                 continue;
             }
             const std::string name = fmt("vc%d_%d", p, nc++);
@@ -236,6 +249,7 @@ struct Gen {
             op_name[o] = name;
         }
         max_vs[p] = std::max(max_vs[p], ns); max_vc[p] = std::max(max_vc[p], nc); max_vt[p] = std::max(max_vt[p], nt);
+        max_vl[p] = std::max(max_vl[p], nl);
         return t;
     }
 
@@ -251,6 +265,10 @@ struct Gen {
         }
         const std::string& nm = op_name[p.idx];
         const bool line = g.ops[(size_t)p.idx * HVB_OP_WORDS] == OP_TLINE;
+        if (line && op_chain_form[p.idx]) {
+            const std::string b2 = nm + ((p.sub == 0 || p.sub == 3) ? "a" : "b");
+            return ValRef{b2 + ".x", b2 + ".y"};
+        }
         const std::string base = line ? nm + fmt("[%d]", p.sub) : nm;
         return ValRef{base + ".x", base + ".y"};
     }
@@ -280,7 +298,7 @@ struct Gen {
             t += "    c0 = " + cell(0, 0, s) + ";\n";
             t += "    c1 = " + (n > 1 ? cell(0, 1, s) : std::string("cmk(0.0, 0.0)")) + ";\n";
             t += "    c2 = cmk(0.0, 0.0);\n";
-            if (a.tap_of_row[0] >= 0) t += "    GM_0 = " + cell(0, n + a.tap_port[0], s) + ";\n";
+            if (a.tap_of_row[0] >= 0) t += "    " + GM(0) + " = " + cell(0, n + a.tap_port[0], s) + ";\n";
         } else {
             t += "    n0 = " + cell(r, r - 1, s) + ";\n";
             t += "    n1 = " + cell(r, r, s) + ";\n";
@@ -295,16 +313,24 @@ struct Gen {
         if (!scratch) return fmt("ACC_%d_%d", o, j);
         return fmt("Sp[%dLL * D.ldS]", a.tap_port[o] * g.P + a.tap_port[j]);
     }
+    // per-port running sums T_o and column factors gamma_j: registers for few ports, shared memory otherwise
+    std::string TT(int o) const { return scratch ? fmt("gsm[%d * GEN_THREADS + threadIdx.x]", o) : fmt("TT_%d", o); }
+    std::string GM(int j) const { return scratch ? fmt("gsm[%d * GEN_THREADS + threadIdx.x]", g.P + j) : fmt("GM_%d", j); }
 
     // fold gamma_j * T_o of the epoch that just ended into the pair accumulators; f = taps that are old now
     std::string flush(int f, bool final_) {
         std::string t;
+        if (f > 0) {
+            t += "    {\n";
+            for (int j = 0; j < f; ++j) t += fmt("      const cplx gm%d = %s;\n", j, GM(j).c_str());
+        }
         for (int o = 0; o < f; ++o) {
+            t += fmt("      { const cplx tt = %s;\n", TT(o).c_str());
             for (int j = 0; j < f; ++j) {
                 const bool first = scratch && o == f - 1;              // first touch of (o, j): see the header comment
-                const std::string prodt = fmt("cmul(GM_%d, TT_%d)", j, o);
+                const std::string prodt = fmt("cmul(gm%d, tt)", j);
                 if (final_) {
-                    t += fmt("    { cplx x = %s; ", prodt.c_str());
+                    t += fmt("        { cplx x = %s; ", prodt.c_str());
                     if (!first) t += "const cplx x0 = " + acc_ref(o, j) + "; x.x += x0.x; x.y += x0.y; ";
                     const int po = a.tap_port[o], pj = a.tap_port[j];
                     t += fmt("x.x = fma(2.0, x.x, %s); x.y = 2.0 * x.y; ", po == pj ? "-1.0" : "0.0");
@@ -313,24 +339,30 @@ struct Gen {
                     t += "if (!(isfinite(x.x) && isfinite(x.y))) bad |= HVB_STATUS_NONFINITE_BIT; ";
                     t += fmt("Sp[%dLL * D.ldS] = x; }\n", po * g.P + pj);
                 } else if (first) {
-                    t += "    " + acc_ref(o, j) + " = " + prodt + ";\n";
+                    t += "        " + acc_ref(o, j) + " = " + prodt + ";\n";
                 } else if (scratch) {
-                    t += "    { cplx x = " + acc_ref(o, j) + fmt("; cfma(x, GM_%d, TT_%d); ", j, o) + acc_ref(o, j) + " = x; }\n";
+                    t += "        { cplx x = " + acc_ref(o, j) + fmt("; cfma(x, gm%d, tt); ", j) + acc_ref(o, j) + " = x; }\n";
                 } else {
-                    t += fmt("    cfma(ACC_%d_%d, GM_%d, TT_%d);\n", o, j, j, o);
+                    t += fmt("        cfma(ACC_%d_%d, gm%d, tt);\n", o, j, j);
                 }
                 flops += 8;
             }
-            if (!final_) t += fmt("    TT_%d = cmk(0.0, 0.0);\n", o);
+            if (!final_) t += "        " + TT(o) + " = cmk(0.0, 0.0);\n";
+            t += "      }\n";
         }
+        if (f > 0) t += "    }\n";
         return t;
     }
 
-    // elimination step k: nb = ports whose row is <= k, newly = row k is a port row, fresh = row k+1 is a port
-    // row (its source column joins the old ones after this step), last = no row k+1
-    std::string step(int nb, bool newly, bool fresh, bool last) {
+    // elimination step k: par = k & 1, nb = ports whose row is <= k, newly = row k is a port row, fresh = row
+    // k+1 is a port row (its source column joins the old ones after this step), last = no row k+1.
+    // w_o[k-1] / w_o[k-2] alternate between WA_o and WB_o, U[k-2][k] between GA and GB: no register moves.
+    std::string step(int par, int nb, bool newly, bool fresh, bool last) {
         std::string t;
         const bool old = nb > 0;                                       // old source columns exist (ports at rows <= k)
+        const char* Wprev = par ? "WB" : "WA";                         // w[k-1]
+        const char* Wold = par ? "WA" : "WB";                          // w[k-2], overwritten by w[k]
+        const char* Gold = par ? "GB" : "GA";                          // U[k-2][k], overwritten by U[k][k+2]
         if (last) {
             t += "    { double best = fabs(c0.x) + fabs(c0.y); if (!(best >= 0.0)) best = -1.0;\n";
             t += "      pmin = fmin(pmin, best); pmax = fmax(pmax, best);\n";
@@ -361,28 +393,33 @@ struct Gen {
             t += "      const cplx rf = sw ? cneg(cmul(m, gf)) : gf;\n";
             flops += 6;
         }
+        if (nb > (newly ? 1 : 0)) {
+            t += fmt("      const cplx ninv = cneg(inv), e1 = cmul(h1, ninv), e2 = cmul(%s, ninv);\n", Gold);
+            flops += 12;
+        }
         for (int o = 0; o < nb; ++o) {
             if (newly && o == nb - 1) t += "      { const cplx wk = inv;\n";
             else {
-                t += fmt("      { cplx wk = cmul(W1_%d, h1); cfma(wk, W2_%d, h2); wk = cneg(cmul(wk, inv));\n", o, o);
-                flops += 6 + 8 + 6;
+                t += fmt("      { cplx wk = cmul(%s_%d, e1); cfma(wk, %s_%d, e2);\n", Wprev, o, Wold, o);
+                flops += 6 + 8;
             }
-            if (newly && o == nb - 1) t += fmt("        TT_%d = cmul(wk, zeta);\n", o);
-            else t += fmt("        cfma(TT_%d, wk, zeta);\n", o);
+            if (newly && o == nb - 1) t += "        " + TT(o) + " = cmul(wk, zeta);\n";
+            else if (scratch) t += "        { cplx tt = " + TT(o) + "; cfma(tt, wk, zeta); " + TT(o) + " = tt; }\n";
+            else t += "        cfma(" + TT(o) + ", wk, zeta);\n";
             flops += 8;
             if (fresh) { t += "        " + acc_ref(o, nb) + " = cmul(wk, yf);\n"; flops += 6; }
-            t += fmt("        W2_%d = W1_%d; W1_%d = wk; }\n", o, o, o);
+            t += fmt("        %s_%d = wk; }\n", Wold, o);
         }
         if (!last) {
-            t += "      h2 = hq; hq = p2; h1 = p1;\n";
+            t += fmt("      %s = p2; h1 = p1;\n", Gold);
             t += "      c0 = r1; c1 = r2; c2 = cmk(0.0, 0.0);\n";
             if (old) t += "      z = znext;\n";
         }
         if (fresh) {
             // the source column of port nb becomes an old column: close the epoch
             t += flush(nb, false);
-            for (int j = 0; j < nb; ++j) { t += fmt("      GM_%d = cmul(GM_%d, z);\n", j, j); flops += 6; }
-            t += fmt("      GM_%d = rf; z = cmk(1.0, 0.0);\n", nb);
+            for (int j = 0; j < nb; ++j) { t += "      " + GM(j) + " = cmul(" + GM(j) + ", z);\n"; flops += 6; }
+            t += "      " + GM(nb) + " = rf; z = cmk(1.0, 0.0);\n";
         }
         t += "    }\n";
         return t;
@@ -417,31 +454,39 @@ int hvb_gen_source(const GenPlan& g, const int32_t* prefs, int mode, const char*
     std::string head = G.assemble(0, s0);            // row 0 is always literal code
     std::vector<std::string> asm_cases, step_cases;
     std::map<std::string, int> asm_id, step_id;
+    bool tables_in_source = false;
     if (!rolled) {
         for (int k = 0; k + 1 < n; ++k) {
             Sink s{false, &out->itab, &out->dtab};
             body += fmt("    // ---- row %d enters, column %d is eliminated\n", k + 1, k);
             body += G.assemble(k + 1, s);
-            body += G.step(nb[k], a.tap_of_row[k] >= 0, a.tap_of_row[k + 1] >= 0, false);
+            body += G.step(k & 1, nb[k], a.tap_of_row[k] >= 0, a.tap_of_row[k + 1] >= 0, false);
         }
     } else {
         for (int k = 0; k + 1 < n; ++k) {
             Sink s{true, &out->itab, &out->dtab};
             const int ib = (int)out->itab.size(), db = (int)out->dtab.size();
             const std::string at = G.assemble(k + 1, s);
-            const long long fl0 = G.flops;
-            const std::string st = G.step(nb[k], a.tap_of_row[k] >= 0, a.tap_of_row[k + 1] >= 0, false);
+            const std::string st = G.step(k & 1, nb[k], a.tap_of_row[k] >= 0, a.tap_of_row[k + 1] >= 0, false);
             auto ia = asm_id.find(at);
             int ca, cs;
             if (ia == asm_id.end()) { ca = (int)asm_cases.size(); asm_id[at] = ca; asm_cases.push_back(at); } else ca = ia->second;
             auto is = step_id.find(st);
             if (is == step_id.end()) { cs = (int)step_cases.size(); step_id[st] = cs; step_cases.push_back(st); } else cs = is->second;
-            (void)fl0;
             out->rows.push_back(ca); out->rows.push_back(cs); out->rows.push_back(ib); out->rows.push_back(db);
         }
+        // the row tables are constants of the plan: when they fit, they go into the module's constant bank
+        // (uniform, cached reads) as static initialisers; otherwise the library uploads them (D.gen_*)
+        const size_t table_bytes = out->rows.size() * 4 + out->itab.size() * 4 + out->dtab.size() * 8;
+        tables_in_source = table_bytes <= 56 * 1024;
         body += "    for (int k = 0; k < " + std::to_string(n - 1) + "; ++k) {\n";
-        body += "      const int4 rw = __ldg(reinterpret_cast<const int4*>(D.gen_rows) + k);\n";
-        body += "      const int* __restrict__ it = D.gen_itab + rw.z; const double* __restrict__ dt = D.gen_dtab + rw.w;\n";
+        if (tables_in_source) {
+            body += "      const int4 rw = gen_rw[k];\n";
+            body += "      const int* __restrict__ it = gen_it + rw.z; const double* __restrict__ dt = gen_dt + rw.w; (void)it; (void)dt;\n";
+        } else {
+            body += "      const int4 rw = __ldg(reinterpret_cast<const int4*>(D.gen_rows) + k);\n";
+            body += "      const int* __restrict__ it = D.gen_itab + rw.z; const double* __restrict__ dt = D.gen_dtab + rw.w; (void)it; (void)dt;\n";
+        }
         body += "      switch (rw.x) {\n";
         for (size_t c = 0; c < asm_cases.size(); ++c) body += fmt("      case %d: {\n", (int)c) + asm_cases[c] + "      } break;\n";
         body += "      }\n      switch (rw.y) {\n";
@@ -450,9 +495,14 @@ int hvb_gen_source(const GenPlan& g, const int32_t* prefs, int mode, const char*
         out->n_cases = (int)(asm_cases.size() + step_cases.size());
     }
     body += "    // ---- last column\n";
-    body += G.step(nb[n - 1], a.tap_of_row[n - 1] >= 0, false, true);
+    body += G.step((n - 1) & 1, nb[n - 1], a.tap_of_row[n - 1] >= 0, false, true);
     body += "    // ---- fold the last epoch, voltages -> S (solvers/spfn.py:159-176, closed form for ground-referenced ports)\n";
     body += G.flush(P, true);
+
+    // threads per CTA: the shared-memory sums (2 P complex words per thread) must fit 48 KB of static shared memory
+    const int threads = (scratch && 2 * P * 128 * 16 > 48 * 1024) ? 64 : 128;
+    out->threads = threads;
+    out->tables_in_source = tables_in_source;
 
     // ---- declarations ------------------------------------------------------------------------
     std::string decl;
@@ -460,17 +510,23 @@ int hvb_gen_source(const GenPlan& g, const int32_t* prefs, int mode, const char*
         for (int i = 0; i < G.max_vs[p]; ++i) decl += fmt("    double vs%d_%d;\n", p, i);
         for (int i = 0; i < G.max_vc[p]; ++i) decl += fmt("    cplx vc%d_%d;\n", p, i);
         for (int i = 0; i < G.max_vt[p]; ++i) decl += fmt("    cplx vt%d_%d[9];\n", p, i);
+        for (int i = 0; i < G.max_vl[p]; ++i) decl += fmt("    cplx vl%d_%da, vl%d_%db;\n", p, i, p, i);
     }
-    decl += "    cplx c0, c1, c2, n0 = cmk(0.0, 0.0), n1 = n0, n2 = n0, gf = n0, z = cmk(1.0, 0.0), h1 = n0, h2 = n0, hq = n0;\n";
-    for (int o = 0; o < P; ++o) decl += fmt("    cplx W1_%d = cmk(0.0, 0.0), W2_%d = W1_%d, TT_%d = W1_%d, GM_%d = W1_%d;\n", o, o, o, o, o, o, o);
-    if (!scratch)
+    decl += "    cplx c0, c1, c2, n0 = cmk(0.0, 0.0), n1 = n0, n2 = n0, gf = n0, z = cmk(1.0, 0.0), h1 = n0, GA = n0, GB = n0;\n";
+    for (int o = 0; o < P; ++o) decl += fmt("    cplx WA_%d = cmk(0.0, 0.0), WB_%d = WA_%d;\n", o, o, o);
+    if (!scratch) {
+        for (int o = 0; o < P; ++o) decl += fmt("    cplx TT_%d = cmk(0.0, 0.0), GM_%d = TT_%d;\n", o, o, o);
         for (int o = 0; o < P; ++o)
             for (int j = 0; j < P; ++j) decl += fmt("    cplx ACC_%d_%d = cmk(0.0, 0.0);\n", o, j);
+    } else {
+        for (int o = 0; o < 2 * P; ++o) decl += fmt("    gsm[%d * GEN_THREADS + threadIdx.x] = cmk(0.0, 0.0);\n", o);
+    }
 
     std::string src;
     src += "// generated by heavi_b200 (csrc/hvb_gen.cpp): kernel D for one netlist\n";
     src += prelude;
-    src += "\n__device__ __forceinline__ void cfma(cplx& acc, cplx a, cplx b) {\n"
+    src += fmt("\n#define GEN_THREADS %d\n", threads);
+    src += "__device__ __forceinline__ void cfma(cplx& acc, cplx a, cplx b) {\n"
            "    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);\n"
            "    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);\n}\n"
            "__device__ __forceinline__ cplx gen_beta(double w, cplx s) {\n"
@@ -479,15 +535,54 @@ int hvb_gen_source(const GenPlan& g, const int32_t* prefs, int mode, const char*
            "__device__ __forceinline__ cplx gen_cap(double w, cplx p0) {\n"
            "    return (p0.y == 0.0) ? cmk(0.0, __dmul_rn(w, p0.x)) : cmk(-__dmul_rn(w, p0.y), __dmul_rn(w, p0.x));\n}\n"
            "__device__ __forceinline__ cplx gen_ind(double w, cplx p0) {\n"
-           "    if (p0.y == 0.0) return cmk(0.0, -(1.0 / __dmul_rn(w, p0.x)));\n"
-           "    return cdiv_np(cmk(1.0, 0.0), cmk(-__dmul_rn(w, p0.y), __dmul_rn(w, p0.x)));\n}\n\n";
+           "    if (p0.y == 0.0) return cmk(0.0, -rcp_fast(__dmul_rn(w, p0.x)));\n"
+           "    return cdiv_np(cmk(1.0, 0.0), cmk(-__dmul_rn(w, p0.y), __dmul_rn(w, p0.x)));\n}\n"
+           "// line between two nodes whose reference is ground (base/tl.py:30-60): a11 = a22 = cosh(th), a12 = Z0 sinh(th),\n"
+           "// and det(ABCD) = cosh^2 - sinh^2 = 1, so y11 = y22 = a11 / a12 and y12 = y21 = -1 / a12\n"
+           "__device__ __forceinline__ void gen_tline_chain(cplx Z0, cplx beta, double len, cplx& ya, cplx& yb) {\n"
+           "    const double x = -beta.y * len, y = beta.x * len;\n"
+           "    double sy, cy;\n"
+           "    sincos(y, &sy, &cy);\n"
+           "    cplx ch, sh;\n"
+           "    if (x == 0.0) { ch = cmk(cy, 0.0); sh = cmk(0.0, sy); }\n"
+           "    else { const double chx = cosh(x), shx = sinh(x); ch = cmk(chx * cy, shx * sy); sh = cmk(shx * cy, chx * sy); }\n"
+           "    const cplx r = crecip_fast(cmul(Z0, sh));\n"
+           "    ya = cmul(ch, r);\n"
+           "    yb = cneg(r);\n}\n\n";
+    if (tables_in_source) {
+        src += fmt("__constant__ int4 gen_rw[%d] = {", std::max(n - 1, 1));
+        for (size_t k = 0; k + 3 < out->rows.size(); k += 4) src += fmt("%s{%d,%d,%d,%d}", k ? "," : "", out->rows[k], out->rows[k + 1], out->rows[k + 2], out->rows[k + 3]);
+        src += "};\n";
+        src += fmt("__constant__ int gen_it[%d] = {", (int)std::max<size_t>(out->itab.size(), 1));
+        for (size_t k = 0; k < out->itab.size(); ++k) src += fmt("%s%d", k ? "," : "", out->itab[k]);
+        if (out->itab.empty()) src += "0";
+        src += "};\n";
+        src += fmt("__constant__ double gen_dt[%d] = {", (int)std::max<size_t>(out->dtab.size(), 1));
+        for (size_t k = 0; k < out->dtab.size(); ++k) {
+            const double v = out->dtab[k];
+            src += k ? "," : "";
+            src += (std::isfinite(v) ? fmt("%a", v) : std::string(std::isnan(v) ? "__longlong_as_double(0x7ff8000000000000LL)" : (v > 0 ? "__longlong_as_double(0x7ff0000000000000LL)" : "__longlong_as_double(0xfff0000000000000LL)")));
+        }
+        if (out->dtab.empty()) src += "0.0";
+        src += "};\n\n";
+    }
     out->kernel_name = "hvb_gen_kernel";
-    src += "extern \"C\" __global__ void __launch_bounds__(128) hvb_gen_kernel(const HvbDev D) {\n";
+    // registers: few ports -> everything in registers anyway; many ports -> keep four CTAs of 128 resident
+    {
+        int minb = scratch ? (threads == 128 ? 3 : 6) : 0;                      // measured on c5: 168 registers beat 128 (spills) and 254 (8 warps/SM)
+        if (const char* e = getenv("HVB_GEN_MINB")) minb = atoi(e);          // experiments: resident CTAs the compiler must allow
+        src += fmt("extern \"C\" __global__ void __launch_bounds__(GEN_THREADS%s) hvb_gen_kernel(const HvbDev D) {\n",
+                   minb > 0 ? fmt(", %d", minb).c_str() : "");
+    }
+    if (scratch) src += fmt("  __shared__ cplx gsm[%d * GEN_THREADS];\n", 2 * P);
     src += "  const long long T = (long long)gridDim.x * blockDim.x;\n";
     src += "  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;\n";
     src += "  const long long total = D.nS * D.nF;\n  unsigned bad = 0;\n";
     src += "  for (long long q = t0; q < total; q += T) {\n";
-    src += "    const long long s = q / D.nF, fi = q - s * D.nF;\n";
+    src += "    long long s = 0, fi = q;\n";
+    src += "    if (D.nS != 1) {                                   // one sweep: no division at all\n";
+    src += "      if (total < 0x7fffffffLL) { const unsigned uq = (unsigned)q, un = (unsigned)D.nF; s = uq / un; fi = uq - (unsigned)s * un; }\n";
+    src += "      else { s = q / D.nF; fi = q - s * D.nF; }\n    }\n";
     src += "    const double f = __ldg(D.f + fi);\n";
     src += "    if (D.f32 && s == 0) D.f32[fi] = (float)f;\n";
     src += "    const double* __restrict__ srow = D.samples + s * D.nR; (void)srow;\n";

@@ -31,7 +31,9 @@ struct GenResult {
     std::vector<int32_t> rows;         // rolled: [n-1][4] assembly shape, step shape, itab base, dtab base
     std::vector<int32_t> itab;
     std::vector<double> dtab;
-    bool scratch_acc = false;          // port-pair accumulators live in the output array (P > 4)
+    bool scratch_acc = false;          // port-pair accumulators live in the output array, per-port sums in shared memory (P > 4)
+    bool tables_in_source = false;     // rolled: the row tables are __constant__ initialisers of the module (no upload needed)
+    int threads = 128;                 // threads per CTA the kernel is written for
     int n_cases = 0;                   // distinct row shapes emitted (rolled)
     long long flops_per_solve = 0;     // executed real flops of the elimination / border recurrences (excl. stamp values)
 };

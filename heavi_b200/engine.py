@@ -39,7 +39,7 @@ class PlanDesc(C.Structure):
 class RunArgs(C.Structure):
     _fields_ = [("consts", C.c_void_p), ("prefs", C.c_void_p), ("f", C.c_void_p), ("nF", C.c_int64),
                 ("samples", C.c_void_p), ("nS", C.c_int64), ("tables", C.c_void_p), ("n_tables", C.c_int32),
-                ("f32_out", C.c_void_p)]
+                ("f32_out", C.c_void_p), ("out_ld", C.c_int64)]
 
 
 class KernelInfo(C.Structure):
@@ -56,7 +56,7 @@ class CodegenInfo(C.Structure):
 EXPORTS = ("hvb_warp_shape", "hvb_plan_create", "hvb_plan_destroy", "hvb_run_host", "hvb_run_device",
            "hvb_run_stats_host", "hvb_assemble_host",
            "hvb_plan_kernel_info", "hvb_measure_dfma_peak", "hvb_last_error", "hvb_version",
-           "hvb_codegen_source", "hvb_codegen_compile")
+           "hvb_codegen_source", "hvb_codegen_compile", "hvb_plan_set_tunable", "hvb_run_host_multi")
 
 _lib = None
 
@@ -79,6 +79,8 @@ def load_library():
     lib.hvb_plan_destroy.restype = None
     lib.hvb_run_host.argtypes = [C.c_void_p, C.POINTER(RunArgs), C.c_void_p, _i32p]
     lib.hvb_run_host.restype = C.c_int
+    lib.hvb_run_host_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(RunArgs), C.c_void_p, _i32p]
+    lib.hvb_run_host_multi.restype = C.c_int
     lib.hvb_run_stats_host.argtypes = [C.c_void_p, C.POINTER(RunArgs), C.c_void_p, _i32p]
     lib.hvb_run_stats_host.restype = C.c_int
     lib.hvb_run_device.argtypes = [C.c_void_p, C.POINTER(RunArgs), C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
@@ -94,6 +96,8 @@ def load_library():
     lib.hvb_codegen_source.restype = C.c_int
     lib.hvb_codegen_compile.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     lib.hvb_codegen_compile.restype = C.c_int
+    lib.hvb_plan_set_tunable.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+    lib.hvb_plan_set_tunable.restype = C.c_int
     lib.hvb_last_error.restype = C.c_char_p
     lib.hvb_version.restype = C.c_char_p
     _lib = lib
@@ -246,6 +250,10 @@ class DevicePlanHandle:
         a.tables, a.n_tables = tables_ptr, nT
         return a
 
+    def set_tunable(self, name: str, value: float):
+        """Host-pipeline tunable of this plan (`hvb_plan_set_tunable`): chunk_mb, min_slab, stats_mb, ..."""
+        _check(self.lib.hvb_plan_set_tunable(self.handle, name.encode(), float(value)))
+
     def kernel_info(self) -> dict:
         ki = KernelInfo()
         _check(self.lib.hvb_plan_kernel_info(self.handle, C.byref(ki)))
@@ -352,7 +360,7 @@ class CompiledNetwork:
         # chain-like netlists (ladders, filters, cascaded lines: tridiagonal after the bandwidth-reducing
         # order): the library generates a kernel for exactly this netlist (kernel class 3), which serves
         # every batch size
-        if os.environ.get("HVB_NO_GEN") != "1" and os.environ.get("HVB_FORCE_BLOCK") != "1":
+        if os.environ.get("HVB_NO_GEN") != "1" and os.environ.get("HVB_FORCE_BLOCK") != "1" and os.environ.get("HVB_NO_BAND") != "1":
             try:
                 cplan = pl.compile_plan(self.table, mode, order="rcm")
             except ValueError:

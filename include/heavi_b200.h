@@ -108,6 +108,10 @@ typedef struct hvb_run_args {
                                   returns f rounded to float32 -- the reference's `Sparameters.f`
                                   (network.py:407,421) -- produced by the kernels and copied back tile
                                   by tile; NULL to skip.  Ignored by the other entry points.       */
+    int64_t        out_ld;     /* hvb_run_host: frequency pitch of S_out in elements, 0 = nF (contiguous).
+                                  A caller that owns one [nS][P][P][nF_total] array and runs frequency slab
+                                  [lo, hi) of it passes S_out + lo and out_ld = nF_total: that is how several
+                                  devices (hvb_run_host_multi) or several processes fill ONE result array.    */
 } hvb_run_args;
 
 /* Create / destroy.  `device` is a CUDA ordinal.  The plan copies everything in `desc`.
@@ -119,12 +123,27 @@ typedef struct hvb_run_args {
 int  hvb_plan_create(const hvb_plan_desc* desc, int device, hvb_plan** out);
 void hvb_plan_destroy(hvb_plan* plan);
 
+/* Tunables of the host pipeline.  Defaults come from the environment ONCE, at hvb_plan_create
+ * (HVB_CHUNK_MB, HVB_MIN_SLAB, HVB_STATS_MB, HVB_BAND_TILE_WAVES, HVB_COPY2D, HVB_BAND_PFB); this call
+ * changes them for one plan afterwards.  Names: "chunk_mb" (bytes of S per pipeline tile, MiB; 0 = default),
+ * "min_slab" (points), "stats_mb" (HBM budget of hvb_run_stats_host, MiB), "band_tile_waves", "copy2d" (0/1),
+ * "band_pfb" (records prefetched by the banded kernel; -1 = automatic).  Results never depend on them. */
+int hvb_plan_set_tunable(hvb_plan* plan, const char* name, double value);
+
 /* S-parameters with HOST buffers: uploads f / samples / tables, runs the kernels in pipelined
  * chunks and writes S_out[nS][P][P][nF] (complex128, frequency fastest -- the layout of
  * Sparameters._S, sparam.py:49-63, with a leading sample axis).  `S_out` may be pageable or
  * pinned.  `status_out` (optional, 1 int32) receives the OR of HVB_STATUS_* bits.
  * Replaces: the whole body of Network.run_sp after index allocation (network.py:380-416). */
 int hvb_run_host(hvb_plan* plan, const hvb_run_args* args, double* S_out, int32_t* status_out);
+
+/* The same call spread over several devices of one process: `plans[k]` are replicas of one netlist's plan
+ * created on different devices (hvb_plan_create with the same descriptor).  Points are independent, so the
+ * job is cut into contiguous blocks -- whole samples when nS >= nplans, else frequency slabs -- one block
+ * per device, each driven by its own host thread through hvb_run_host and copied by its own device straight
+ * into the caller's one S_out (page-locked for full overlap); no inter-device transfer, results bit-identical
+ * to the single-device call.  status_out receives the OR over devices.   */
+int hvb_run_host_multi(hvb_plan* const* plans, int32_t nplans, const hvb_run_args* args, double* S_out, int32_t* status_out);
 
 /* Same computation with DEVICE buffers owned by the caller (e.g. torch tensors' data_ptr()):
  * `args->f`, `args->samples`, `args->tables` and `d_S_out` are device pointers; consts/prefs stay

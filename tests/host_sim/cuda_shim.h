@@ -18,6 +18,8 @@
 #define __forceinline__ inline
 #define __noinline__
 #define __launch_bounds__(...)
+#define __constant__ static const
+#define __shared__ static
 
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }

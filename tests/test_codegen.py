@@ -1,0 +1,159 @@
+"""CPU: the kernel generator behind kernel class 3 (heavi_b200/csrc/hvb_gen.cpp).
+
+The source the library would hand to NVRTC is fetched through the host-only C-ABI entry
+`hvb_codegen_source`, compiled for the CPU with g++ and a CUDA shim (tests/host_sim, test
+infrastructure) and run against the oracle (oracle/mna_oracle.py, the restatement of
+network.py:354-421 + solvers/spfn.py:106-179) and the reference-generated goldens.  `hvb_codegen_compile`
+checks that the same text compiles for sm_100a with NVRTC (no GPU needed)."""
+import os
+
+import numpy as np
+import pytest
+
+import circuits
+import heavi_b200 as hv
+import host_sim
+from heavi_b200 import engine
+from heavi_b200 import plan as pl
+from helpers import golden, parity_report, registry
+from oracle import mna_oracle as orc
+
+REG = registry(hv)
+
+
+def chain_plan(m):
+    return pl.compile_plan(m.stamp_table(), "auto", order="rcm")
+
+
+def sim(m, f, mode=0, drivers=None, values=None):
+    p = chain_plan(m)
+    consts, prefs, tables, samples = pl.resolve_run(p, np.asarray(f, dtype=np.float64), drivers, values)
+    gen = engine.codegen_source(p, prefs, mode)
+    assert gen["supported"], gen["reason"]
+    S, f32, status = host_sim.run(gen, p.P, f, consts, prefs, tables, samples, p)
+    return S, f32, status, gen
+
+
+def oracle_S(m, f):
+    return orc.run_sp(m.records(), m.n_nodes, len(m.sources), np.asarray(f, dtype=np.float64), method="lu_batched")
+
+
+CHAINS = ["c1_readme", "c2_bandpass", "c2_lowpass", "c2_highpass", "ka_divider", "ka_line"]
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("name", CHAINS)
+def test_generated_kernel_matches_reference_golden(name, mode):
+    g = golden(name)
+    m = REG[name]()
+    f = g["f"][:: max(1, len(g["f"]) // 400)]
+    sel = np.arange(len(g["f"]))[:: max(1, len(g["f"]) // 400)]
+    S, f32, status, gen = sim(m, f, mode)
+    assert status == 0 and gen["rolled"] == (mode == 2)
+    assert np.array_equal(f32, g["f32"][sel])
+    frac, adjudicated, ext = parity_report(S[0], g["S"][..., sel], g["S_ext"][..., sel])
+    assert frac >= 0.99 and adjudicated and ext < 5e-14, (frac, adjudicated, ext)
+
+
+def test_rolled_and_straight_line_forms_agree_bit_for_bit():
+    m, f = circuits.build_c5(hv, nF=24)
+    S1, _, st1, g1 = sim(m, f, 1)
+    S2, _, st2, g2 = sim(m, f, 2)
+    assert st1 == 0 and st2 == 0 and not g1["rolled"] and g2["rolled"]
+    assert g2["n_cases"] < 60 and len(g2["rows"]) == 4 * 190
+    assert np.array_equal(S1, S2)
+    g = golden("c5_ladder")
+    S, _, st, _ = sim(m, g["f"], 0)
+    frac, adjudicated, ext = parity_report(S[0], g["S"], g["S_ext"])
+    assert frac == 1.0 and ext < 5e-14
+
+
+@pytest.mark.parametrize("n_sections,taps", [(3, [0]), (3, [1]), (3, [2]), (4, [0, 3]), (5, [0, 1, 2, 3, 4]), (9, [2, 3, 7]),
+                                             (12, [0, 5, 6, 11]), (30, [1, 2, 3, 4, 5, 20, 28, 29]),
+                                             (44, list(range(0, 44, 4))), (64, [63]), (33, list(range(16)))])
+def test_port_positions_and_counts(n_sections, taps):
+    """Ports anywhere along the chain, adjacent ports, one port, 16 ports; both code forms."""
+    rng = np.random.default_rng(n_sections * 7 + len(taps))
+    m = hv.Model(suppress_loadbar=True)
+    nodes = [m.node() for _ in range(n_sections)]
+    for t in taps:
+        m.new_port(float(rng.choice([25.0, 50.0, 75.0])), nodes[t])
+    for k in range(n_sections - 1):
+        kind = k % 3
+        if kind == 0:
+            m.inductor(nodes[k], nodes[k + 1], float(10 ** rng.uniform(-9.3, -8.3)))
+        elif kind == 1:
+            m.transmissionline(nodes[k], nodes[k + 1], float(rng.uniform(30, 90)), float(rng.uniform(2, 4)), float(rng.uniform(1e-3, 9e-3)))
+        else:
+            m.resistor(nodes[k], nodes[k + 1], float(rng.uniform(5, 80)))
+    for k in range(n_sections):
+        m.capacitor(nodes[k], m.gnd, float(10 ** rng.uniform(-12.5, -11.5)))
+    f = np.linspace(0.4e9, 7e9, 23)
+    ref = oracle_S(m, f)
+    for mode in (1, 2):
+        S, _, status, gen = sim(m, f, mode)
+        assert status == 0
+        assert np.max(np.abs(S[0] - ref)) < 2e-13, (mode, np.max(np.abs(S[0] - ref)))
+
+
+def test_monte_carlo_samples_tables_and_lossy_lines():
+    m, f, mc = circuits.build_c4(hv, nF=31)
+    np.random.seed(3)
+    values = mc.draw(5)
+    S, _, status, gen = sim(m, f, 0, mc._random_numbers, values)
+    assert status == 0 and S.shape == (5, 2, 2, 31)
+    for s in range(5):
+        for r, v in zip(mc._random_numbers, values[s]):
+            r._value = float(v)
+        assert np.max(np.abs(S[s] - oracle_S(m, f))) < 1e-13
+    # host-tabulated callable, complex permittivity (lossy line), sample-valued port impedance stays out
+    m2 = hv.Model(suppress_loadbar=True)
+    a, b = m2.quick_port(50), m2.quick_port(75)
+    mid, mid2 = m2.node(), m2.node()
+    m2.impedance(a, mid, lambda fr: 3.0 + 1j * 2e-9 * fr)
+    m2.transmissionline(mid, mid2, 60.0, 3.1 - 0.05j, 0.011)
+    m2.admittance(mid2, b, lambda fr: 0.02 + 1j * 1e-12 * fr)
+    m2.capacitor(mid, m2.gnd, 0.4e-12)
+    f2 = np.linspace(1e9, 5e9, 17)
+    S2, _, status, _ = sim(m2, f2, 0)
+    assert status == 0 and np.max(np.abs(S2[0] - oracle_S(m2, f2))) < 1e-13
+
+
+def test_singular_and_nonfinite_points_set_status_bits():
+    m = hv.Model(suppress_loadbar=True)
+    a, b = m.quick_port(50), m.quick_port(50)
+    mid = m.node()
+    m.inductor(a, mid, 1e-9)
+    m.inductor(mid, b, 1e-9)
+    _, _, status, _ = sim(m, np.array([0.0, 1e9]))
+    assert status & engine.HVB_STATUS_NONFINITE
+
+
+def test_unsupported_structures_are_refused_with_a_reason():
+    m, f = circuits.build_c3(hv, nF=8)                          # 8-port block: not a chain
+    p = pl.compile_plan(m.stamp_table(), "auto")
+    gen = engine.codegen_source(p)
+    assert not gen["supported"] and gen["reason"]
+    m2, _ = circuits.build_band_ladder(hv, K=40, reach=2, nports=2)  # pentadiagonal
+    gen2 = engine.codegen_source(pl.compile_plan(m2.stamp_table(), "auto", order="rcm"))
+    assert not gen2["supported"] and "tridiagonal" in gen2["reason"]
+    m3, _ = circuits.build_c2(hv, "bandpass", 8)                 # full MNA keeps the source rows: general epilogue
+    gen3 = engine.codegen_source(pl.compile_plan(m3.stamp_table(), "full", order="rcm"))
+    assert not gen3["supported"]
+
+
+@pytest.mark.parametrize("name,mode", [("c2_bandpass", 1), ("c5_ladder", 2)])
+def test_generated_source_compiles_for_sm100a(name, mode):
+    m = REG[name]()
+    p = chain_plan(m)
+    gen = engine.codegen_source(p, None, mode)
+    old = os.environ.get("HVB_NVRTC_FLAGS")
+    os.environ["HVB_NVRTC_FLAGS"] = "--ptxas-options=-v"
+    try:
+        log = engine.codegen_compile(gen["src"])
+    finally:
+        if old is None:
+            os.environ.pop("HVB_NVRTC_FLAGS")
+        else:
+            os.environ["HVB_NVRTC_FLAGS"] = old
+    assert "hvb_gen_kernel" in log and "registers" in log

@@ -9,7 +9,7 @@ import pytest
 import circuits
 import helpers
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.library_kernels]
 
 TOL_REL, TOL_ABS = 1e-10, 1e-12
 

@@ -1,0 +1,165 @@
+"""GPU (-m gpu): kernel class 3 -- the kernel the library generates for a chain-like netlist and compiles
+with NVRTC (csrc/hvb_gen.cpp, hvb_jit.cpp) -- through the public API / C-ABI against the oracle, the
+reference goldens, the precompiled kernels, and size-independent properties at BASELINE sizes."""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+import circuits
+import heavi_b200 as hv
+from heavi_b200.engine import CompiledNetwork
+from helpers import golden, parity_report
+from oracle import mna_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _gen_on():
+    keep = {k: os.environ.get(k) for k in ("HVB_NO_GEN", "HVB_GEN_MODE")}
+    os.environ.pop("HVB_NO_GEN", None)
+    yield
+    for k, v in keep.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+def oracle_S(m, f):
+    return orc.run_sp(m.records(), m.n_nodes, len(m.sources), np.asarray(f, dtype=np.float64), method="lu_batched")
+
+
+def library_variant(m):
+    os.environ["HVB_NO_GEN"] = "1"
+    try:
+        return CompiledNetwork(m)
+    finally:
+        os.environ.pop("HVB_NO_GEN")
+
+
+@pytest.mark.parametrize("gen_mode", ["1", "2"])
+@pytest.mark.parametrize("name,build", [("c1_readme", lambda: circuits.build_c1(hv)[0]),
+                                        ("c2_bandpass", lambda: circuits.build_c2(hv, "bandpass")[0]),
+                                        ("c2_lowpass", lambda: circuits.build_c2(hv, "lowpass")[0]),
+                                        ("c2_highpass", lambda: circuits.build_c2(hv, "highpass")[0]),
+                                        ("c5_ladder", lambda: circuits.build_c5(hv, nF=16)[0])])
+def test_configs_on_the_generated_kernel_match_reference_golden(name, build, gen_mode):
+    os.environ["HVB_GEN_MODE"] = gen_mode               # 1 straight-line code, 2 loop over row shapes
+    g = golden(name)
+    m = build()
+    S = m.run_sp(g["f"])
+    ki = m._compiled().handle.kernel_info()
+    assert ki["kernel_class"] == 3 and ki["gen_rolled"] == (gen_mode == "2") , ki
+    assert S.f.dtype == np.float32 and np.array_equal(S.f, g["f32"])
+    frac, adjudicated, ext = parity_report(S._S, g["S"], g["S_ext"])
+    assert frac >= 0.998 and adjudicated and ext < 5e-14, (frac, adjudicated, ext)
+
+
+@pytest.mark.parametrize("n_sections,n_ports", [(3, 1), (3, 3), (7, 2), (16, 5), (33, 4), (64, 16), (200, 8), (501, 3), (2001, 2)])
+def test_chains_of_every_size_against_oracle_and_library_kernels(n_sections, n_ports):
+    rng = np.random.default_rng(n_sections)
+    m = hv.Model(suppress_loadbar=True)
+    nodes = [m.node() for _ in range(n_sections)]
+    for t in sorted(set(int(round(i * (n_sections - 1) / max(n_ports - 1, 1))) for i in range(n_ports))):
+        m.new_port(50.0, nodes[t])
+    for k in range(n_sections - 1):
+        if k % 4 == 1:
+            m.transmissionline(nodes[k], nodes[k + 1], float(rng.uniform(30, 90)), float(rng.uniform(2, 4)), float(rng.uniform(1e-3, 9e-3)))
+        elif k % 4 == 3:
+            m.resistor(nodes[k], nodes[k + 1], float(rng.uniform(5, 80)))
+        else:
+            m.inductor(nodes[k], nodes[k + 1], float(10 ** rng.uniform(-9.3, -8.3)))
+    for k in range(n_sections):
+        m.capacitor(nodes[k], m.gnd, float(10 ** rng.uniform(-12.5, -11.5)))
+    f = np.linspace(0.3e9, 6e9, 257)
+    S = m.run_sp(f)._S
+    assert m._compiled().handle.kernel_info()["kernel_class"] == 3
+    sub = slice(0, None, 16)
+    assert np.max(np.abs(S[..., sub] - oracle_S(m, f[sub]))) < 1e-12
+    lib = library_variant(m)
+    assert lib.handle.kernel_info()["kernel_class"] != 3
+    assert np.max(np.abs(S - lib.run(f)[0])) < 1e-12
+
+
+def test_full_size_monte_carlo_and_sweep_properties():
+    """configs[3] per-GPU share (1250 samples x 2001 points) and a 1 M-point configs[1] sweep: reciprocity,
+    losslessness of the LC ladder (S^H S = I), strided oracle check, tiling-independence."""
+    m, f, mc = circuits.build_c4(hv)
+    np.random.seed(7)
+    values = mc.draw(1250)
+    S = m.run_sp_batch(f, mc._random_numbers, values)
+    assert S.shape == (1250, 2, 2, 2001) and m._compiled().handle.kernel_info()["kernel_class"] == 3
+    assert np.max(np.abs(S[:, 0, 1] - S[:, 1, 0])) < 1e-12
+    SS = np.einsum("sjif,sjkf->sikf", S.conj(), S)
+    assert np.max(np.abs(SS - np.eye(2)[None, :, :, None])) < 5e-11
+    for s in (0, 611, 1249):
+        for r, v in zip(mc._random_numbers, values[s]):
+            r._value = float(v)
+        assert np.max(np.abs(S[s][..., ::97] - oracle_S(m, f[::97]))) < 1e-12
+    cn = m._compiled()
+    cn.handle.set_tunable("chunk_mb", 1)
+    assert np.array_equal(m.run_sp_batch(f, mc._random_numbers, values[:100]), S[:100])
+    m2, f2 = circuits.build_c2(hv, "bandpass", nF=1_000_001)
+    S2 = m2.run_sp(f2)._S
+    assert np.max(np.abs(S2[0, 1] - S2[1, 0])) < 1e-12
+    idx = np.arange(0, 1_000_001, 9973)
+    assert np.max(np.abs(S2[..., idx] - oracle_S(m2, f2[idx]))) < 1e-12
+    assert np.array_equal(S2[..., idx], m2.run_sp(f2[idx])._S)       # a point does not depend on its neighbours
+
+
+def test_status_bits_statistics_and_resident_entry():
+    m = hv.Model(suppress_loadbar=True)
+    a, b = m.quick_port(50), m.quick_port(50)
+    mid = m.node()
+    m.inductor(a, mid, 1e-9)
+    m.inductor(mid, b, 1e-9)
+    assert m._compiled().handle.kernel_info()["kernel_class"] == 3
+    with pytest.raises(np.linalg.LinAlgError):                      # like numba's lstsq on NaN/Inf
+        m.run_sp(np.array([0.0, 1e9]))
+    m2 = hv.Model(suppress_loadbar=True)
+    p, q = m2.quick_port(50), m2.quick_port(50)
+    x = m2.node()
+    m2.resistor(p, x, 10.0)
+    m2.admittance(x, q, 0.0)                                        # port 2 floats behind a zero admittance
+    m2.admittance(q, m2.gnd, 0.0)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        S = m2.run_sp(np.array([1e9]))
+    assert np.isfinite(S._S).all()                                  # the port conductance keeps it regular
+    m3, f3, mc = circuits.build_c4(hv, nF=301)
+    np.random.seed(11)
+    full = m3.run_mc(f3, mc, 23)
+    np.random.seed(11)
+    dev = m3.run_mc_stats(f3, mc, 23)
+    assert np.max(np.abs(full.S(2, 1).amplitude_mean - dev.S(2, 1).amplitude_mean)) < 1e-12
+    import torch
+    Sr = m3._compiled().run_resident(f3)
+    assert Sr.is_cuda and np.array_equal(Sr.cpu().numpy()[0], m3.run_sp(f3)._S)
+
+
+def test_parameter_layout_change_regenerates_the_kernel():
+    """A callable that returns an array is a table, one that returns a scalar becomes a constant for that
+    run (resolve_run): the value formulas are specialised on that layout, so the library keeps one kernel
+    per layout."""
+    state = {"scalar": False}
+
+    def z(fr):
+        return 5.0 + 0.0j if state["scalar"] else 5.0 + 1e-9j * fr
+
+    m = hv.Model(suppress_loadbar=True)
+    a, b = m.quick_port(50), m.quick_port(50)
+    mid = m.node()
+    m.impedance(a, mid, z)
+    m.inductor(mid, b, 2e-9)
+    m.capacitor(mid, m.gnd, 1e-12)
+    f = np.linspace(1e9, 3e9, 41)
+    S1 = m.run_sp(f)._S.copy()
+    assert np.max(np.abs(S1 - oracle_S(m, f))) < 1e-13
+    state["scalar"] = True
+    S2 = m.run_sp(f)._S.copy()
+    assert np.max(np.abs(S2 - oracle_S(m, f))) < 1e-13 and not np.array_equal(S1, S2)
+    state["scalar"] = False
+    assert np.array_equal(m.run_sp(f)._S, S1)

@@ -145,7 +145,7 @@ def test_config3_touchstone_large_sweep_properties():
     assert frac == 1.0 and ext < 5e-14
 
 
-def test_config5_ladder_block_and_banded_kernel_properties():
+def test_config5_ladder_block_and_banded_kernel_properties(kernel_path):
     import circuits
     from oracle import mna_oracle as orc
     m, f = circuits.build_c5(hv, nF=2048)
@@ -156,7 +156,7 @@ def test_config5_ladder_block_and_banded_kernel_properties():
         os.environ.pop("HVB_NO_BAND")
     assert dense.handle.kernel_info()["kernel_class"] == 1 and dense.plan.n_real == 191
     cn = m._compiled()                                                            # default: banded kernel
-    assert cn.handle.kernel_info()["kernel_class"] == 2 and cn.plan.band == 1
+    assert cn.handle.kernel_info()["kernel_class"] == (3 if kernel_path == "generated" else 2) and cn.plan.band == 1
     sub = slice(0, None, 128)
     ref = orc.run_sp(m.records(), m.n_nodes, len(m.sources), f[sub], method="lu_batched")
     for S in (dense.run(f)[0], m.run_sp(f)._S):
@@ -170,10 +170,10 @@ def test_chunking_and_sharding_are_bit_identical():
     from heavi_b200 import sharding as sh
     m, f = circuits.build_c2(hv, "bandpass", nF=150_001)
     whole = m.run_sp(f)._S.copy()
-    os.environ["HVB_CHUNK_MB"] = "1"
-    assert np.array_equal(m.run_sp(f)._S, whole)
-    os.environ.pop("HVB_CHUNK_MB")
     cn = m._compiled()
+    cn.handle.set_tunable("chunk_mb", 1)                     # many small pipeline tiles
+    assert np.array_equal(m.run_sp(f)._S, whole)
+    cn.handle.set_tunable("chunk_mb", 0)
     for world in (2, 8):
         parts = [sh.run_sharded(lambda fb, vb: cn.run(fb).copy(), f, None, world, r) for r in range(world)]
         assert np.array_equal(np.concatenate([p[1] for p in parts], axis=3)[0], whole)
@@ -193,11 +193,13 @@ def test_nonfinite_raises_and_singular_warns():
     m2.resistor(x, y, 10.0)                                         # floating island -> singular
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
+        raised = False
         try:
             m2.run_sp(np.array([1e9]))
         except np.linalg.LinAlgError:
-            pass
-        assert any("singular" in str(x.message) for x in w) or True
+            raised = True                                           # the zero pivot turned into NaN/Inf
+        # the reference returns the SVD minimum-norm solution silently (App. B-7); here the point is flagged
+        assert raised or any("singular" in str(x.message) for x in w)
 
 
 def test_known_answers_on_gpu():
@@ -240,10 +242,10 @@ def test_device_monte_carlo_statistics_match_numpy_reduction():
             assert y.shape == x.shape
             assert np.max(np.abs(x - y)) <= 1e-12 * max(1.0, np.max(np.abs(x))), name
     # slabbed reduction (small device budget) is bit-identical
-    os.environ["HVB_STATS_MB"] = "1"
+    for _, h in ([(m._compiled().plan, m._compiled().handle)] + ([m._compiled()._band] if m._compiled()._band else [])):
+        h.set_tunable("stats_mb", 1)
     np.random.seed(11)
     dev2 = m.run_mc_stats(f, mc, 37)
-    os.environ.pop("HVB_STATS_MB")
     assert np.array_equal(dev2._moments, dev._moments)
 
 
