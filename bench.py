@@ -1,30 +1,37 @@
 """Benchmark of the frequency-sweep S-parameter path (BASELINE.json metric: S-matrix
 frequency-point solves/sec; % FP64 peak).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c1|c3|c4|c5] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5|c1|c2|c3|c4] [--impl ours|reference]
 
-One "step" = one pass of the hot path (stamp assembly -> complex solve -> S) over one batch of
-synthetic input.  Default workload = BASELINE.json configs[1]: the demo2 Cauer filter set (band-,
-low- and high-pass, 2 ports) on a 100 001-point sweep each = 300 003 solves per step per GPU.
-With N > 1 (launched by torchrun, one rank per GPU) the sweep is N times longer and rank r takes
-frequency block r (weak scaling, no data-path collective).
+Headline workload = BASELINE.json configs[4]: the ~200-node ladder / transmission-line network with 8
+ports on a 1 000 000-point sweep, STRONG-scaled: the million points are split over the N ranks
+(torchrun, one rank per GPU; frequency slabs, no data-path collective).  One "step" = R back-to-back
+passes of the hot path (stamp assembly -> complex solve -> S) over this rank's share, R chosen during
+warm-up so that a step lasts >= 10 ms on the slowest rank (K = 20 steps then time >= 0.2 s); R is in
+`config.passes_per_step`, `value` counts every pass.
 
-  value     whole-job solves/s with inputs resident in HBM and S left in HBM (kernel only),
-            CUDA events on the launching stream, L2 flushed between timed steps
-  e2e       the same metric through the public API `Model.run_sp(f)` with host buffers: H2D of f,
-            kernels, D2H of S into pinned memory all inside the timed region
-  roofline  dominant kernel against the FP64 FMA pipe (the bound SURVEY.md section 8d derives);
-            `peak` is a DFMA probe measured in this run because MEASURED_PEAKS.json has no FP64
-            entry; `roofline_hbm` is the same launch against the measured HBM copy rate
-  cpu_baseline   the oracle port of the reference's algorithm (numba prange + zgelsd per port per
-            frequency, oracle/mna_oracle_numba.py) on the host cores, bounded sample
+  value     whole-job solves/s with inputs resident in HBM and S left in HBM (kernels only), CUDA events on
+            the launching stream, max over ranks, L2 flushed between timed steps
+  e2e       the same metric through the public API with host buffers -- N = 1: `Model.run_sp(f)`;
+            N > 1: `sharding.run_sp_distributed` (every rank's GPU copies its block over its own PCIe link
+            into ONE page-locked shared array, rank 0 ends up holding the whole S) -- H2D of f, kernels and
+            D2H of S inside the timed region
+  roofline  dominant kernel: executed FP64 flops of the factorisation / port recurrences against the DFMA
+            peak measured in this run (MEASURED_PEAKS.json has no FP64 entry); `roofline_hbm`: algorithmic
+            bytes 8 + 16 P^2 per solve against the measured HBM copy rate; `traffic` =
+            ncu dram bytes per launch from profiles/traffic.json (capture of this build)
+  parity    untimed: a strided subset of the timed e2e result against oracle.run_sp(..., "lu_batched")
+  cpu_baseline   the oracle port of the reference's algorithm (numba prange + zgelsd per port per frequency,
+            oracle/mna_oracle_numba.py) on the host cores, bounded sample
+  per_config     the same measurements (shorter) for configs[0..4], configs[3] as 10 000 samples split over N
 
-`--impl reference` times that CPU path alone (rank 0 only under torchrun).
+`--impl reference` times the CPU path alone (rank 0 only under torchrun).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -39,47 +46,52 @@ import numpy as np  # noqa: E402
 
 METRIC = "S-matrix frequency-point solves/sec (freq x MC samples)"
 UNIT = "solves/s"
+TARGET_STEP_MS = 10.0
+
+DESCS = {
+    "c1": "configs[0]: README demo (5th-order Cauer band-pass + SMD resistor), 2001 points 1.8-2.2 GHz",
+    "c2": "configs[1]: demo2 Cauer band/low/high-pass set, 2-port, 100001-point sweep each",
+    "c3": "configs[2]: synthetic 8-port Touchstone block in LC matching network, 1M freq points",
+    "c4": "configs[3]: Monte-Carlo Cauer band-pass, 10k samples x 2001 freqs",
+    "c5": "configs[4]: ladder/TL network (~200 nodes, 8 ports), 1M-point sweep",
+}
 
 
 # --------------------------------------------------------------------------------------------
-# workloads; each returns a list of jobs (model, f, drivers, values)
+# workloads: whole jobs; the caller shards them
 # --------------------------------------------------------------------------------------------
-def make_jobs(hv, workload: str, rank: int, world: int):
+def make_jobs(hv, workload: str):
+    """-> list of (model, f[nF], drivers | None, values[nS, nR] | None): the WHOLE job."""
     import circuits
-    jobs = []
-
-    def slab(f_lo, f_hi, n_per_gpu):
-        full = np.linspace(f_lo, f_hi, n_per_gpu * world)
-        return np.ascontiguousarray(full[rank * n_per_gpu:(rank + 1) * n_per_gpu])
-
     if workload == "c2":
-        for band in ("bandpass", "lowpass", "highpass"):
-            m, _ = circuits.build_c2(hv, band, nF=8)
-            jobs.append((m, slab(2e9, 3e9, 100_001), None, None))
-        desc = "configs[1]: demo2 Cauer band/low/high-pass set, 2-port, 100001-point sweep each (per GPU)"
-    elif workload == "c1":
-        m, _ = circuits.build_c1(hv, nF=8)
-        jobs.append((m, slab(1.8e9, 2.2e9, 2001), None, None))
-        desc = "configs[0]: README demo, 2001 points (per GPU)"
-    elif workload == "c3":
-        m, _ = circuits.build_c3(hv, nF=8)
+        return [(circuits.build_c2(hv, band, nF=8)[0], np.linspace(2e9, 3e9, 100_001), None, None)
+                for band in ("bandpass", "lowpass", "highpass")]
+    if workload == "c1":
+        return [(circuits.build_c1(hv, nF=8)[0], np.linspace(1.8e9, 2.2e9, 2001), None, None)]
+    if workload == "c3":
         npts = int(os.environ.get("HVB_C3_POINTS", "1000000"))
-        jobs.append((m, slab(1e9, 6e9, npts), None, None))
-        desc = "configs[2]: synthetic 8-port Touchstone block in LC matching network, %d points (per GPU)" % npts
-    elif workload == "c4":
+        return [(circuits.build_c3(hv, nF=8)[0], np.linspace(1e9, 6e9, npts), None, None)]
+    if workload == "c4":
         m, f, mc = circuits.build_c4(hv)
-        nS = 10_000 // 8                      # the config shards 10k samples over 8 GPUs
-        rs = np.random.RandomState(7 + rank)
+        nS = int(os.environ.get("HVB_C4_SAMPLES", "10000"))
+        rs = np.random.RandomState(7)
         vals = np.stack([rs.normal(r._mean, r._std, size=nS) for r in mc._random_numbers], axis=1)
-        jobs.append((m, np.ascontiguousarray(f), mc._random_numbers, vals))
-        desc = "configs[3]: Monte-Carlo Cauer band-pass, 1250 samples x 2001 freqs per GPU"
-    elif workload == "c5":
-        m, _ = circuits.build_c5(hv, nF=8)
-        jobs.append((m, slab(0.5e9, 6e9, int(os.environ.get("HVB_C5_POINTS", "1000000"))), None, None))
-        desc = "configs[4]: ladder/TL network n=207, 8 ports, %s points per GPU" % os.environ.get("HVB_C5_POINTS", "1000000")
-    else:
-        raise SystemExit("unknown workload " + workload)
-    return jobs, desc
+        return [(m, np.ascontiguousarray(f), mc._random_numbers, vals)]
+    if workload == "c5":
+        npts = int(os.environ.get("HVB_C5_POINTS", "1000000"))
+        return [(circuits.build_c5(hv, nF=8)[0], np.linspace(0.5e9, 6e9, npts), None, None)]
+    raise SystemExit("unknown workload " + workload)
+
+
+def shard_job(job, world: int, rank: int):
+    """This rank's share of a job (strong scaling): whole samples when nS >= world, else a frequency slab."""
+    from heavi_b200 import sharding as sh
+    m, f, drivers, values = job
+    nS = 1 if values is None else values.shape[0]
+    s = sh.plan_shard(nS, len(f), world, rank)
+    if s.axis == "sample":
+        return (m, f, drivers, None if values is None else np.ascontiguousarray(values[s.lo:s.hi]))
+    return (m, np.ascontiguousarray(f[s.lo:s.hi]), drivers, values)
 
 
 def job_points(job) -> int:
@@ -147,7 +159,7 @@ def measured_peaks():
 
 
 def ncu_traffic(workload: str):
-    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture, if any."""
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture of this build, if any."""
     try:
         return json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload)
     except Exception:
@@ -160,16 +172,14 @@ def ncu_traffic(workload: str):
 def cpu_job_sample(job, budget_points: int):
     m, f, drivers, values = job
     n = max(1, min(len(f), budget_points))
-    sel = np.ascontiguousarray(f[:: max(1, len(f) // n)][:n])
-    return sel
+    return np.ascontiguousarray(f[:: max(1, len(f) // n)][:n])
 
 
 def time_cpu(jobs, steps: int, warmup: int, per_step_seconds: float = 4.0):
-    """Bounded sample of the same workload through the oracle port; returns (solves/s, info)."""
+    """Bounded sample of the same workload through the oracle port; returns (solves/s, ms/step, info)."""
     from oracle import mna_oracle_numba as onb
     recs = [(j[0].records(), j[0].n_nodes, len(j[0].sources)) for j in jobs]
-    # size the sample: calibrate on tiny runs (the first also triggers the JIT once)
-    for (r, N, M), j in zip(recs, jobs):
+    for (r, N, M), j in zip(recs, jobs):          # the first call also triggers the JIT once
         onb.run_sp(r, N, M, cpu_job_sample(j, 4))
     t = time.perf_counter()
     for (r, N, M), j in zip(recs, jobs):
@@ -194,33 +204,251 @@ def time_cpu(jobs, steps: int, warmup: int, per_step_seconds: float = 4.0):
 
 
 # --------------------------------------------------------------------------------------------
+def kernel_name(ki, cn) -> str:
+    kc = ki["kernel_class"]
+    if kc == 0:
+        return "hvb_warp%s_kernel<%d,%d>" % ("2" if cn.rows_per_lane == 2 else "", ki["group"], ki["pmax"])
+    if kc == 1:
+        return "hvb_block_kernel<%d>" % ki["group"]
+    if kc == 2:
+        return "hvb_bandf_kernel<%d>" % ki["group"]
+    return "hvb_gen_kernel (NVRTC, %s, n=%d, P=%d)" % ("row loop, %d shapes" % ki["gen_cases"] if ki["gen_rolled"] == 1 else "straight-line",
+                                                        cn.plan.n_real, cn.plan.P)
+
+
+def executed_flops_per_solve(ki, plan) -> tuple[float, str]:
+    """FP64 flops of the factorisation + substitutions the kernel really executes for one point (stamp
+    values excluded)."""
+    n, P = plan.n_real, plan.P
+    if ki["kernel_class"] == 3:
+        return float(ki["gen_flops_per_solve"]), "counted by the generator: tridiagonal LU with partial pivoting + forward port recurrences"
+    if ki["kernel_class"] == 2:
+        B = ki["group"]
+        return 8.0 * n * B * (2 * B + P) + 8.0 * n * 2 * B * P, "banded LU n*B*(2B+P) + back substitution n*2B*P complex FMAs"
+    return plan.flops_per_solve(), "dense complex LU + P substitutions: 8/3 n^3 + 8 n^2 P, n = dimension factored"
+
+
+class Measurement:
+    """One workload on this rank's GPU: device-resident state, kernel-only timing, e2e timing."""
+
+    def __init__(self, hv, workload, world, rank, dev, dist):
+        import torch
+        self.torch, self.dist, self.dev, self.world, self.rank, self.workload, self.hv = torch, dist, dev, world, rank, workload, hv
+        self.jobs_whole = make_jobs(hv, workload)
+        self.jobs = [shard_job(j, world, rank) for j in self.jobs_whole]
+        self.points_whole = sum(job_points(j) for j in self.jobs_whole)
+        self.points_rank = sum(job_points(j) for j in self.jobs)
+        self.state = []
+        for (m, f, drivers, values) in self.jobs:
+            cn = m._compiled()
+            whole = self.points_whole                       # every rank picks the kernel variant of the WHOLE job
+            plan, handle = cn.variant(whole)
+            consts, prefs, tables, samples = cn.resolve(f, drivers, values, plan)
+            P = plan.P
+            self.state.append(dict(cn=cn, plan=plan, handle=handle, consts=consts, prefs=prefs,
+                                   d_f=torch.from_numpy(f).to(dev),
+                                   d_tab=torch.from_numpy(tables).to(dev) if tables.shape[0] else None,
+                                   d_smp=torch.from_numpy(samples).to(dev),
+                                   d_S=torch.empty((samples.shape[0], P, P, len(f)), dtype=torch.complex128, device=dev),
+                                   d_status=torch.zeros(1, dtype=torch.int32, device=dev)))
+
+    def launch_all(self):
+        for st in self.state:
+            if st["d_f"].numel():
+                st["handle"].run_device(st["d_f"], st["consts"], st["prefs"], st["d_tab"], st["d_smp"], st["d_S"], st["d_status"])
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def allmax(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def launches(self) -> int:
+        return sum(st["handle"].kernel_info()["launches"] for st in self.state)
+
+    def time_kernels(self, steps, warmup, flush, sampler=None):
+        torch = self.torch
+        for _ in range(warmup):
+            self.launch_all()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); self.launch_all(); b.record(); torch.cuda.synchronize()
+        t_pass = self.allmax(a.elapsed_time(b))
+        passes = max(1, int(math.ceil(TARGET_STEP_MS / max(t_pass, 1e-4))))
+        passes = min(passes, 4096)
+        l0 = self.launches()
+        if sampler:
+            sampler.start()
+            time.sleep(0.25)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        self.barrier()
+        t_wall0 = time.time()
+        for k in range(steps):
+            flush.zero_()                                                   # evict L2 (untimed)
+            ev[k][0].record()
+            for _ in range(passes):
+                self.launch_all()
+            ev[k][1].record()
+        self.barrier()
+        t_wall1 = time.time()
+        dev_ms = self.allmax(sum(x.elapsed_time(y) for x, y in ev))
+        status = int(sum(int(st["d_status"].item()) for st in self.state))
+        clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+        return dict(value=self.points_whole * passes * steps / (dev_ms * 1e-3), ms_per_step=dev_ms / steps, passes=passes,
+                    ms_per_pass=dev_ms / steps / passes, launches=self.launches() - l0, status=status, clocks=clocks)
+
+    # ---- e2e: public API, host buffers ----------------------------------------------------------
+    def e2e_once(self):
+        """One pass of the whole job through the public API; returns the results rank 0 holds."""
+        from heavi_b200 import sharding
+        out = []
+        for (m, f, drivers, values) in self.jobs_whole:
+            if self.world > 1:
+                out.append(sharding.run_sp_distributed(m, f, drivers, values))
+            elif values is None:
+                out.append(m.run_sp(f)._S[None])
+            else:
+                out.append(m.run_sp_batch(f, drivers, values))
+        return out
+
+    def time_e2e(self, min_seconds=0.25, min_steps=3, max_steps=400):
+        for _ in range(2):
+            res = self.e2e_once()
+        self.barrier()
+        t0 = time.perf_counter()
+        res = self.e2e_once()
+        acc = float(res[0].reshape(-1)[-1].real) if res[0] is not None else 0.0
+        self.barrier()
+        t_one = self.allmax(time.perf_counter() - t0)
+        steps = int(min(max_steps, max(min_steps, math.ceil(min_seconds / max(t_one, 1e-6)))))
+        self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            res = self.e2e_once()
+            if res[0] is not None:
+                acc += float(res[0].reshape(-1)[-1].real)                   # the host reads the step's result
+        self.barrier()
+        dt = self.allmax(time.perf_counter() - t0)
+        h2d = sum(j[1].nbytes + (0 if j[3] is None else j[3].nbytes) for j in self.jobs_whole)
+        d2h = sum(job_points(j) * st["plan"].P ** 2 * 16 for j, st in zip(self.jobs_whole, self.state))
+        api = ("sharding.run_sp_distributed(model, f) -> S on rank 0 (one page-locked shared array, each GPU copies its block)"
+               if self.world > 1 else "Model.run_sp(f) / run_sp_batch -> Sparameters (pinned host result)")
+        return dict(value=self.points_whole * steps / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
+                    steps=steps, ms_per_step=dt / steps * 1e3, api=api), res
+
+    # ---- parity spot check of the timed e2e result (rank 0, untimed) ----------------------------
+    def parity(self, results, max_points):
+        from oracle import mna_oracle as orc
+        worst, checked, worst_rel = 0.0, 0, 0.0
+        for (m, f, drivers, values), S in zip(self.jobs_whole, results):
+            if S is None:
+                continue
+            n = max(1, min(len(f), max_points))
+            idx = np.unique(np.linspace(0, len(f) - 1, n).astype(np.int64))
+            rows = [0] if values is None else sorted({0, values.shape[0] // 2, values.shape[0] - 1})
+            saved = None if values is None else [d._value for d in drivers]
+            for s in rows:
+                if values is not None:
+                    for d, v in zip(drivers, values[s]):
+                        d._value = float(v)
+                ref = orc.run_sp(m.records(), m.n_nodes, len(m.sources), f[idx], method="lu_batched")
+                err = np.abs(S[s][..., idx] - ref)
+                worst = max(worst, float(err.max()))
+                worst_rel = max(worst_rel, float((err / (1e-12 + 1e-10 * np.abs(ref))).max()))
+                checked += len(idx)
+            if saved is not None:
+                for d, v in zip(drivers, saved):
+                    d._value = v
+        return {"checked_points": checked, "max_abs_err": worst, "max_err_over_tolerance": worst_rel,
+                "tolerance": "1e-12 + 1e-10 |S| against oracle.run_sp(method='lu_batched')", "ok": bool(worst_rel <= 1.0)}
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    def roofline(self, flush, peak_tflops, reps=8):
+        torch = self.torch
+        cost = [executed_flops_per_solve(st["handle"].kernel_info(), st["plan"])[0] * job_points(j) for j, st in zip(self.jobs, self.state)]
+        top = int(np.argmax(cost))
+        st, job = self.state[top], self.jobs[top]
+        h = st["handle"]
+        single = []
+        for _ in range(reps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            h.run_device(st["d_f"], st["consts"], st["prefs"], st["d_tab"], st["d_smp"], st["d_S"], st["d_status"])
+            b.record()
+            torch.cuda.synchronize()
+            single.append(a.elapsed_time(b))
+        k_ms = float(np.mean(single))
+        ki = h.kernel_info()
+        plan = st["plan"]
+        pts = job_points(job)
+        fl, how = executed_flops_per_solve(ki, plan)
+        achieved = fl * pts / (k_ms * 1e-3) / 1e12
+        mp = measured_peaks()
+        hbm_peak = mp["hbm_gbs"] if mp else 6650.0
+        bytes_alg = 8 + 16 * plan.P ** 2
+        roof = {"bound": "fp64", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                "traffic": ncu_traffic(self.workload), "kernel": kernel_name(ki, st["cn"]), "launch_ms": k_ms,
+                "n_factored": plan.n_real, "solver_mode": plan.mode, "flops_per_solve": fl, "flops_basis": how,
+                "dense_lu_equivalent_flops_per_solve": plan.flops_per_solve(), "solves_per_launch": pts,
+                "peak_source": "DFMA probe measured in this run (hvb_measure_dfma_peak); MEASURED_PEAKS.json has no FP64 entry",
+                "regs": ki["regs"], "ctas_per_sm": ki["ctas_per_sm"], "smem_bytes": ki["smem_bytes"], "local_bytes": ki["local_bytes"]}
+        roof_hbm = {"bound": "hbm", "achieved": bytes_alg * pts / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": bytes_alg * pts / (k_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_solve": bytes_alg,
+                    "traffic": ncu_traffic(self.workload),
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if mp else "fallback 6650 GB/s (B200_PROFILING.md)"}
+        return roof, roof_hbm
+
+
+def workload_config(workload, world, m: Measurement, passes):
+    return {"workload": DESCS[workload] + (" -- STRONG-scaled over %d GPUs" % world if world > 1 else ""),
+            "solves_per_pass": m.points_whole, "solves_per_pass_per_gpu": m.points_rank, "passes_per_step": passes,
+            "l2": "flushed between timed steps (256 MiB memset); S of one pass (%d MB per GPU) is rewritten by the next"
+                  % (sum(st["d_S"].numel() * 16 for st in m.state) // 1000000),
+            "sharding": ("frequency slab / sample block per rank, no data-path collective" if world > 1 else "single GPU")}
+
+
+# --------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default=os.environ.get("HVB_WORKLOAD", "c2"))
+    ap.add_argument("--workload", default=os.environ.get("HVB_WORKLOAD", "c5"))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-per-config", action="store_true", help="headline workload only")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1:
+        # one process = one GPU here; N > 1 is launched by torchrun (one rank per GPU).  The single-process
+        # multi-device mode of Model.run_sp is measured by tools/multi_device_bench.py.
+        os.environ["HVB_DEVICES"] = "1"
+        if args.gpus > 1:
+            print("bench.py: --gpus %d without torchrun: measuring 1 GPU" % args.gpus, file=sys.stderr)
     import heavi_b200 as hv
 
     if args.impl == "reference":
         if rank != 0:
             return
-        jobs, desc = make_jobs(hv, args.workload, 0, max(world, args.gpus, 1))
-        steps, warmup = max(1, args.steps), max(0, args.warmup)
-        val, ms, info = time_cpu(jobs, min(steps, 3), min(warmup, 1))
+        jobs = make_jobs(hv, args.workload)
+        steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+        val, ms, info = time_cpu(jobs, steps, warmup)
         info["value"] = val
         print(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": min(steps, 3),
-            "warmup": min(warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "c128", "data": "synthetic",
-            "config": {"workload": desc, "cpu_path": "reference algorithm (zgelsd per port per frequency) on host cores"},
+            "config": {"workload": DESCS[args.workload], "cpu_path": "reference algorithm (zgelsd per port per frequency) on host cores"},
             "cpu_baseline": info,
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
@@ -236,155 +464,57 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     from heavi_b200 import engine
 
-    jobs, desc = make_jobs(hv, args.workload, rank, world)
     steps, warmup = max(1, args.steps), max(3, args.warmup)
-    pts_step = sum(job_points(j) for j in jobs)
-
-    # ---- device-resident state per job ------------------------------------------------------
-    state = []
-    for (m, f, drivers, values) in jobs:
-        cn = m._compiled()
-        consts, prefs, tables, samples = cn.resolve(f, drivers, values)
-        P = cn.plan.P
-        st = dict(cn=cn, consts=consts, prefs=prefs,
-                  d_f=torch.from_numpy(f).to(dev),
-                  d_tab=torch.from_numpy(tables).to(dev) if tables.shape[0] else None,
-                  d_smp=torch.from_numpy(samples).to(dev),
-                  d_S=torch.empty((samples.shape[0], P, P, len(f)), dtype=torch.complex128, device=dev),
-                  d_status=torch.zeros(1, dtype=torch.int32, device=dev), nT=tables.shape[0])
-        state.append(st)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)       # > 126 MB L2
+    peak = engine.measure_dfma_peak(local_rank)
 
-    def launch_all():
-        for st in state:
-            st["cn"].handle.run_device(st["d_f"], st["consts"], st["prefs"], st["d_tab"], st["d_smp"], st["d_S"], st["d_status"])
+    def run_workload(wl, k_steps, k_warm, headline):
+        m = Measurement(hv, wl, world, rank, dev, dist)
+        sampler = ClockSampler(local_rank) if headline else None
+        kt = m.time_kernels(k_steps, k_warm, flush, sampler)
+        e2e, results = m.time_e2e(min_seconds=0.25 if headline else 0.1)
+        out = None
+        if rank == 0:
+            roof, roof_hbm = m.roofline(flush, peak, reps=8 if headline else 4)
+            par = m.parity(results, 48 if wl in ("c5", "c3") else 512)
+            cpu = None
+            if not args.no_cpu and world == 1:
+                v, ms, info = time_cpu(m.jobs_whole, 2 if headline else 1, 1 if headline else 0, per_step_seconds=4.0 if headline else 2.0)
+                info["value"], info["unit"] = v, UNIT
+                cpu = info
+            out = {"value": kt["value"], "unit": UNIT, "ms_per_step": kt["ms_per_step"], "ms_per_pass": kt["ms_per_pass"],
+                   "config": workload_config(wl, world, m, kt["passes"]), "e2e": e2e, "gpu_launches": int(kt["launches"]),
+                   "status_word": kt["status"], "roofline": roof, "roofline_hbm": roof_hbm, "parity": par, "cpu_baseline": cpu,
+                   "clocks": kt["clocks"]}
+        del m, results
+        torch.cuda.empty_cache()
+        return out
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- value: kernels only ---------------------------------------------------------------
-    for _ in range(warmup):
-        launch_all()
-    torch.cuda.synchronize()
-    launches0 = sum(st["cn"].handle.kernel_info()["launches"] for st in state)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    time.sleep(0.25)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    barrier()
-    t_wall0 = time.time()
-    for k in range(steps):
-        flush.zero_()                                                   # evict L2 (untimed)
-        ev[k][0].record()
-        launch_all()
-        ev[k][1].record()
-    barrier()
-    t_wall1 = time.time()
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    launches = sum(st["cn"].handle.kernel_info()["launches"] for st in state) - launches0
-    clocks = sampler.stop(t_wall0, t_wall1)
-    status = int(sum(int(st["d_status"].item()) for st in state))
-
-    # ---- e2e: public API, host buffers -------------------------------------------------------
-    def e2e_step():
-        acc = 0.0
-        for (m, f, drivers, values) in jobs:
-            if values is None:
-                S = m.run_sp(f)
-                acc += float(S._S[0, 0, -1].real)
-            else:
-                S4 = m.run_sp_batch(f, drivers, values)
-                acc += float(S4[-1, 0, 0, -1].real)
-        return acc
-
-    for _ in range(3):
-        e2e_step()
-    e2e_steps = max(3, min(steps, 10))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    h2d = sum(j[1].nbytes + (0 if j[3] is None else j[3].nbytes) for j in jobs)
-    d2h = sum(job_points(j) * st["cn"].plan.P ** 2 * 16 for j, st in zip(jobs, state))
-
-    # ---- reduce over ranks -----------------------------------------------------------------
-    tot = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_s_max = float(tot[0]), float(tot[1])
-    value = world * pts_step * steps / (dev_ms_max * 1e-3)
-    e2e_value = world * pts_step * e2e_steps / e2e_s_max
-
+    head = run_workload(args.workload, steps, warmup, True)
+    per = {}
+    if not args.no_per_config:
+        for wl in ("c1", "c2", "c3", "c4", "c5"):
+            if wl == args.workload:
+                continue
+            r = run_workload(wl, min(steps, 10), 3, False)
+            if rank == 0:
+                r.pop("clocks", None)
+                per[wl] = r
     if rank == 0:
-        # dominant kernel = the job with the most algorithmic flops; time it alone
-        flops = [st["cn"].plan.flops_per_solve() * job_points(j) for j, st in zip(jobs, state)]
-        top = int(np.argmax(flops))
-        st = state[top]
-        h = st["cn"].handle
-        single = []
-        for _ in range(max(5, steps)):
-            flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            h.run_device(st["d_f"], st["consts"], st["prefs"], st["d_tab"], st["d_smp"], st["d_S"], st["d_status"])
-            b.record()
-            torch.cuda.synchronize()
-            single.append(a.elapsed_time(b))
-        k_ms = float(np.mean(single))
-        peak = engine.measure_dfma_peak(local_rank)
-        achieved = flops[top] / (k_ms * 1e-3) / 1e12
-        ki = h.kernel_info()
-        plan = st["cn"].plan
-        bytes_alg = (8 + 16 * plan.P ** 2) * job_points(jobs[top])
-        mp = measured_peaks()
-        hbm_peak = mp["hbm_gbs"] if mp else 6650.0
-        roof = {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": ncu_traffic(args.workload),
-                "kernel": ("hvb_warp%s_kernel<%d,%d>" % ("2" if ki["threads"] and st["cn"].rows_per_lane == 2 else "", ki["group"], ki["pmax"]))
-                          if ki["kernel_class"] == 0 else "hvb_block_kernel<%d>" % ki["group"],
-                "launch_ms": k_ms, "n_factored": plan.n, "solver_mode": plan.mode,
-                "flops_per_solve": plan.flops_per_solve(), "solves_per_launch": job_points(jobs[top]),
-                "peak_source": "DFMA probe measured in this run (hvb_measure_dfma_peak); MEASURED_PEAKS.json has no FP64 entry",
-                "regs": ki["regs"], "ctas_per_sm": ki["ctas_per_sm"], "smem_bytes": ki["smem_bytes"]}
-        roof_hbm = {"bound": "hbm", "achieved": bytes_alg / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": bytes_alg / (k_ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_solve": 8 + 16 * plan.P ** 2,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if mp else "fallback 6650 GB/s"}
-        if ki["kernel_class"] == 2:
-            # banded kernel: thread per point, pivot-row records stream through HBM (write once, read once);
-            # its flop count is O(n B (2B+P)), so the bound is memory, and the dense-LU flop figure is only
-            # reported as an equivalent
-            per_solve = 8 + 16 * (2 * ki["stream_words"] + plan.P ** 2)
-            gbs = per_solve * job_points(jobs[top]) / (k_ms * 1e-3) / 1e9
-            roof = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                    "traffic": ncu_traffic(args.workload), "kernel": "hvb_bandf_kernel<%d,false>" % ki["group"],
-                    "launch_ms": k_ms, "n_factored": plan.n, "solver_mode": plan.mode, "half_bandwidth": plan.band,
-                    "bytes_per_solve": per_solve, "solves_per_launch": job_points(jobs[top]),
-                    "dense_lu_equivalent_tflops": achieved,
-                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if mp else "fallback 6650 GB/s",
-                    "regs": ki["regs"], "ctas_per_sm": ki["ctas_per_sm"], "smem_bytes": ki["smem_bytes"]}
-        cpu = None
-        if not args.no_cpu:
-            v, ms, info = time_cpu(jobs, 2, 1)
-            info["value"], info["unit"] = v, UNIT
-            cpu = info
+        brief = {k: head[k] for k in ("value", "unit", "ms_per_step", "ms_per_pass", "config", "e2e", "gpu_launches", "status_word",
+                                      "roofline", "roofline_hbm", "parity", "cpu_baseline")}
+        per[args.workload] = brief
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": dev_ms_max / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "c128", "data": "synthetic",
-            "config": {"workload": desc, "solves_per_step_per_gpu": pts_step, "l2": "flushed between timed steps (256 MiB memset)",
-                       "sharding": "frequency block per rank, no collective" if world > 1 else "single GPU"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "api": "Model.run_sp(f) -> Sparameters (pinned host result)"},
-            "gpu_launches": int(launches), "status_word": status,
-            "roofline": roof, "roofline_hbm": roof_hbm, "cpu_baseline": cpu,
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "c128", "data": "synthetic", "config": head["config"], "clocks": head["clocks"], "e2e": head["e2e"],
+            "gpu_launches": head["gpu_launches"], "status_word": head["status_word"], "roofline": head["roofline"],
+            "roofline_hbm": head["roofline_hbm"], "parity": head["parity"], "cpu_baseline": head["cpu_baseline"],
+            "per_config": {k: per[k] for k in sorted(per)},
         }
         print(json.dumps(out))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -129,6 +129,31 @@ def current_device() -> int:
     return 0
 
 
+def visible_devices() -> list[int]:
+    """CUDA ordinals one `run_sp` call may use.  One process per GPU (torchrun: WORLD_SIZE > 1) or an explicit
+    `HVB_DEVICE` pins the process to its own device; otherwise `HVB_DEVICES` ("all", a count, or a comma list)
+    decides, default "all" -- a plain `Model.run_sp(f)` on an 8-GPU box uses the 8 GPUs for large sweeps."""
+    first = current_device()
+    if os.environ.get("HVB_DEVICE") is not None or int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return [first]
+    spec = os.environ.get("HVB_DEVICES", "all").strip().lower()
+    try:
+        import torch
+        count = torch.cuda.device_count()
+    except Exception:
+        count = 1
+    if spec in ("", "all"):
+        devs = list(range(count))
+    elif "," in spec:
+        devs = [int(x) for x in spec.split(",") if x.strip() != ""]
+    else:
+        devs = list(range(min(int(spec), count)))
+    devs = [d for d in devs if 0 <= d < max(count, 1)] or [first]
+    if first in devs:                                   # the caller's current device leads (it owns block 0)
+        devs.remove(first)
+    return [first] + devs
+
+
 def pinned_empty(shape, dtype=np.complex128) -> np.ndarray:
     """numpy array on page-locked memory (torch's caching host allocator), so that the D2H of S runs
     at full PCIe rate and asynchronously."""
@@ -227,6 +252,7 @@ class DevicePlanHandle:
         self.lib = load_library()
         self.plan = plan
         self.device = current_device() if device is None else device
+        self.kernel_hint = kernel_hint
         d, self._keep = make_desc(plan, kernel_hint)
         handle = C.c_void_p()
         _check(self.lib.hvb_plan_create(C.byref(d), self.device, C.byref(handle)))
@@ -261,13 +287,16 @@ class DevicePlanHandle:
 
     # ---- host buffers in, host buffer out ------------------------------------------------------
     def run_host(self, f, consts, prefs, tables, samples, out: np.ndarray | None = None,
-                 f32_out: np.ndarray | None = None):
+                 f32_out: np.ndarray | None = None, out_ptr: int | None = None, out_ld: int = 0, replicas=None):
         """`f32_out` (float32 [nF], optional) receives the frequencies rounded to float32, filled in by
-        the library while the GPU works (the reference's `Sparameters.f`)."""
+        the library while the GPU works (the reference's `Sparameters.f`).  `out_ptr` / `out_ld`: write into
+        a caller-owned array at that address with frequency pitch `out_ld` (a slab of a larger result).
+        `replicas`: handles of the same plan on other devices -> the call is spread over all of them
+        (`hvb_run_host_multi`)."""
         p = self.plan
         f = np.ascontiguousarray(f, dtype=np.float64)
         nF, nS = f.shape[0], samples.shape[0]
-        if out is None:
+        if out is None and out_ptr is None:
             out = pinned_empty((nS, p.P, p.P, nF))
         tables = np.ascontiguousarray(tables, dtype=np.complex128)
         samples = np.ascontiguousarray(samples, dtype=np.float64)
@@ -276,8 +305,14 @@ class DevicePlanHandle:
             if f32_out.dtype != np.float32 or f32_out.shape != (nF,) or not f32_out.flags.c_contiguous:
                 raise ValueError("f32_out must be a contiguous float32 array of nF elements")
             a.f32_out = _ptr(f32_out)
+        a.out_ld = int(out_ld)
+        dst = C.c_void_p(out_ptr if out_ptr is not None else out.__array_interface__["data"][0])
         status = C.c_int32(0)
-        _check(self.lib.hvb_run_host(self.handle, C.byref(a), C.c_void_p(out.__array_interface__["data"][0]), C.byref(status)))
+        if replicas:
+            handles = (C.c_void_p * (1 + len(replicas)))(self.handle, *[r.handle for r in replicas])
+            _check(self.lib.hvb_run_host_multi(handles, len(handles), C.byref(a), dst, C.byref(status)))
+        else:
+            _check(self.lib.hvb_run_host(self.handle, C.byref(a), dst, C.byref(status)))
         return out, status.value
 
     def run_stats_host(self, f, consts, prefs, tables, samples):
@@ -345,6 +380,7 @@ class CompiledNetwork:
     to the latency of a single point; `run` picks by the number of points of the call."""
 
     BAND_MIN_POINTS = 49152          # about half a grid of the banded kernel (148 SMs x 5 CTAs x 128 threads)
+    MULTI_MIN_POINTS = 131072        # points per extra device from which a call is spread over several GPUs
 
     @classmethod
     def band_min_points(cls, n: int) -> int:
@@ -399,6 +435,23 @@ class CompiledNetwork:
                 return band
         return self.plan, self.handle
 
+    def replicas(self, handle, points: int):
+        """Handles of `handle`'s plan on the other visible devices this call should use (created on first use)."""
+        devs = visible_devices()
+        if len(devs) < 2 or handle.device != devs[0]:
+            return []
+        want = min(len(devs), max(1, points // self.MULTI_MIN_POINTS))
+        if want < 2:
+            return []
+        cache = self.__dict__.setdefault("_replica_cache", {})
+        out = []
+        for d in devs[1:want]:
+            key = (id(handle), d)
+            if key not in cache:
+                cache[key] = DevicePlanHandle(handle.plan, d, kernel_hint=handle.kernel_hint)
+            out.append(cache[key])
+        return out
+
     def resolve(self, f, drivers=None, values=None, plan=None):
         return pl.resolve_run(plan or self.plan, f, drivers, values)
 
@@ -423,12 +476,14 @@ class CompiledNetwork:
         return any(not np.array_equal(a, b) for other in rows[1:] for a, b in zip(rows[0], other))
 
     def run(self, f: np.ndarray, drivers=None, values=None, out=None, f32_out=None,
-            batch_points: int | None = None) -> np.ndarray:
+            batch_points: int | None = None, out_ptr: int | None = None, out_ld: int = 0) -> np.ndarray:
         """S[nS,P,P,nF] complex128 on pinned host memory.  `batch_points`: size of the whole job when this
         call is one shard of it, so that every shard picks the same kernel variant (and the result does
         not depend on how the job was cut)."""
         if drivers is not None and self._tables_follow_drivers(f, drivers, values):
             # sample-dependent callables: one run per sample with the drivers set, like the reference's loop
+            if out_ptr is not None:
+                raise NotImplementedError("sample-dependent callables cannot write into a caller-owned slab (out_ptr)")
             values = np.asarray(values, dtype=np.float64)
             nS = values.shape[0]
             S = out if out is not None else pinned_empty((nS, self.plan.P, self.plan.P, len(f)))
@@ -447,7 +502,8 @@ class CompiledNetwork:
         points = len(f) * (1 if values is None else len(values))
         plan, handle = self.variant(points if batch_points is None else batch_points)
         consts, prefs, tables, samples = self.resolve(f, drivers, values, plan)
-        S, status = handle.run_host(f, consts, prefs, tables, samples, out, f32_out)
+        reps = self.replicas(handle, points) if (out_ptr is None and batch_points is None) else []
+        S, status = handle.run_host(f, consts, prefs, tables, samples, out, f32_out, out_ptr=out_ptr, out_ld=out_ld, replicas=reps)
         if status & HVB_STATUS_NONFINITE:
             # the reference's numba lstsq raises for NaN/Inf input
             raise np.linalg.LinAlgError("MNA matrix or S-parameters contain NaN/Inf (e.g. f = 0 with an inductor)")
@@ -505,6 +561,21 @@ class CompiledNetwork:
                              np.sqrt(pw).mean(axis=0), np.sqrt(pw).std(axis=0)])
         plan, handle = self.variant(len(f) * len(values))
         consts, prefs, tables, samples = self.resolve(f, drivers, values, plan)
+        reps = self.replicas(handle, len(f) * len(values))
+        if reps and samples.shape[0] >= 1 + len(reps):
+            # sample blocks on several devices, each reduced on its device; the [6,P,P,nF] moments of the
+            # blocks are merged on the host (counts, means, centred second moments: stable for any split)
+            from concurrent.futures import ThreadPoolExecutor
+            from .sharding import merge_moments, split_range
+            hs = [handle] + reps
+            blocks = [split_range(samples.shape[0], len(hs), r) for r in range(len(hs))]
+            with ThreadPoolExecutor(len(hs)) as ex:        # ctypes releases the GIL for the duration of each call
+                res = list(ex.map(lambda hb: hb[0].run_stats_host(f, consts, prefs, tables, samples[hb[1][0]:hb[1][1]]), zip(hs, blocks)))
+            status = 0
+            for _, st in res:
+                status |= st
+            self._raise_for_status(status)
+            return merge_moments([r[0] for r in res], [hi - lo for lo, hi in blocks])
         out, status = handle.run_stats_host(f, consts, prefs, tables, samples)
         self._raise_for_status(status)
         return out

@@ -10,8 +10,10 @@ import bench
 wl = sys.argv[1] if len(sys.argv) > 1 else "c2"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 dev = torch.device("cuda", 0)
-jobs, desc = bench.make_jobs(hv, wl, 0, 1)
+jobs = bench.make_jobs(hv, wl)
 m, f, drivers, values = jobs[0]
+if wl == "c4":
+    values = values[:1250]
 cn = m._compiled()
 consts, prefs, tables, samples = cn.resolve(f, drivers, values)
 P = cn.plan.P
