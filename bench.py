@@ -426,6 +426,15 @@ def main():
     ap.add_argument("--no-per-config", action="store_true", help="headline workload only")
     args = ap.parse_args()
 
+    # the contract is ONE JSON line on stdout: whatever libraries print to fd 1 (NCCL's version banner, ...)
+    # goes to stderr instead; the line itself is written to the real stdout at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -444,14 +453,14 @@ def main():
         steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
         val, ms, info = time_cpu(jobs, steps, warmup)
         info["value"] = val
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "c128", "data": "synthetic",
             "config": {"workload": DESCS[args.workload], "cpu_path": "reference algorithm (zgelsd per port per frequency) on host cores"},
             "cpu_baseline": info,
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
+        })
         return
 
     import torch
@@ -512,7 +521,7 @@ def main():
             "roofline_hbm": head["roofline_hbm"], "parity": head["parity"], "cpu_baseline": head["cpu_baseline"],
             "per_config": {k: per[k] for k in sorted(per)},
         }
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -137,13 +137,18 @@ class SharedResult:
             pass
 
 
-def _shared_result(shape, group, dst: int) -> SharedResult:
-    """Every rank's view of one pooled shared array of `shape` (created by rank `dst` on first use)."""
+def _shared_result(shape, group, dst: int, owner=None) -> SharedResult:
+    """Every rank's view of one pooled shared array of `shape` (created by rank `dst` on first use).  The pool
+    is keyed by shape AND owner (the compiled netlist): two models never share a buffer, repeated runs of one
+    model reuse -- and overwrite -- theirs."""
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    key = (tuple(int(x) for x in shape), id(group), dst)
+    key = (tuple(int(x) for x in shape), id(group), dst, id(owner))
     if key in _SHARED_POOL:
-        return _SHARED_POOL[key]
+        ref, res = _SHARED_POOL[key]
+        if owner is None or ref() is owner:               # id() of a dead object may be reused
+            return res
+        del _SHARED_POOL[key]
     box = [None]
     if rank == dst:
         box[0] = "hvb_%d_%d_%s" % (os.getpid(), len(_SHARED_POOL), "x".join(str(int(x)) for x in shape))
@@ -155,7 +160,12 @@ def _shared_result(shape, group, dst: int) -> SharedResult:
     dist.barrier(group)
     if rank == dst:
         res.unlink()                                     # the mapping lives on; the name does not
-    _SHARED_POOL[key] = res
+    import weakref
+    try:
+        ref = weakref.ref(owner) if owner is not None else (lambda: None)
+    except TypeError:
+        ref = (lambda o=owner: o)
+    _SHARED_POOL[key] = (ref, res)
     return res
 
 
@@ -165,8 +175,8 @@ def run_sp_distributed(net, frequencies, drivers=None, values=None, group=None, 
     returns S[nS,P,P,nF]; the others return None.
 
     gather="shared" (ranks on one node, the default): every rank's GPU writes its block directly into one
-    page-locked shared-memory array; the array rank `dst` gets back is pooled per shape and is overwritten by
-    the next call of the same shape.  gather="collective": `dist.gather` of the blocks (NCCL or gloo), then
+    page-locked shared-memory array; the array rank `dst` gets back is pooled per (model, shape) and is
+    overwritten by the next call of the same model with the same shape (copy it to keep it).  gather="collective": `dist.gather` of the blocks (NCCL or gloo), then
     one assembly on `dst` -- for ranks that do not share a host.
 
     `writer(shard, f_block, values_block, result)` (tests): fills this rank's block of `result.array` on the
@@ -186,7 +196,7 @@ def run_sp_distributed(net, frequencies, drivers=None, values=None, group=None, 
         return gather_to_root(blk, sh, nS, nF, group=group, dst=dst)
     if gather != "shared":
         raise ValueError(gather)
-    res = _shared_result((nS, P, P, nF), group, dst)
+    res = _shared_result((nS, P, P, nF), group, dst, owner=compiled if compiled is not None else net)
     sh = plan_shard(nS, nF, world, rank)
     if sh.size > 0 and writer is not None:
         if sh.axis == "sample":
