@@ -320,7 +320,7 @@ __device__ __forceinline__ unsigned band_run_schedule(const HvbDev& D, int r, do
             if (line) {
                 const cplx Z0 = eval_param(D.pv, __ldg(op + 2), f, fi, srow);
                 const cplx beta = eval_param(D.pv, __ldg(op + 3), f, fi, srow);
-                eval_tline_fast(Z0, beta, D.pv.consts[__ldg(op + 4)].x, tmp);
+                eval_tline_fast(Z0, beta, eval_param(D.pv, __ldg(op + 4), f, fi, srow).x, tmp);
             } else {
                 eval_simple_op(D, op, f, fi, srow, tmp - out);
             }

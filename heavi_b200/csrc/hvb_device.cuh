@@ -365,7 +365,9 @@ __device__ __forceinline__ void eval_simple_op(const HvbDev& D, const int* __res
         }
         case OP_TLINE: {         // base/tl.py:30-60
             const cplx beta = eval_param(D.pv, op[3], f, fi, srow);
-            eval_tline(p0, beta, D.pv.consts[op[4]].x, dyn + out);
+            // the length is a parameter like any other (a sweep / Monte-Carlo / optimiser value changes it run by
+            // run: base/tl.py:52 reads `self.length.value` inside every run_sp)
+            eval_tline(p0, beta, eval_param(D.pv, op[4], f, fi, srow).x, dyn + out);
             break;
         }
     }

@@ -229,13 +229,13 @@ struct Gen {
                 if ((a.op_submask[o] & ~0xFu) == 0) {
                     // both terminals' reference is ground: only y11 = y22 and y12 = y21 are stamped (det(ABCD) = 1)
                     const std::string name = fmt("vl%d_%d", p, nl++);
-                    t += "    gen_tline_chain(" + param(op[2], s) + ", " + param(op[3], s) + ", D.pv.consts[" + s.i(op[4]) + "].x, " + name + "a, " + name + "b);\n";
+                    t += "    gen_tline_chain(" + param(op[2], s) + ", " + param(op[3], s) + ", " + param(op[4], s) + ".x, " + name + "a, " + name + "b);\n";
                     op_name[o] = name;
                     op_chain_form[o] = true;
                     continue;
                 }
                 const std::string name = fmt("vt%d_%d", p, nt++);
-                t += "    eval_tline_fast(" + param(op[2], s) + ", " + param(op[3], s) + ", D.pv.consts[" + s.i(op[4]) + "].x, " + name + ");\n";
+                t += "    eval_tline_fast(" + param(op[2], s) + ", " + param(op[3], s) + ", " + param(op[4], s) + ".x, " + name + ");\n";
                 op_name[o] = name;
                 op_chain_form[o] = false;
                 continue;

@@ -14,7 +14,8 @@
 #define PK_SMD 7         /* SMD part with parasitics: consts[idx..idx+3] = kind, a, b, c (params.py SMDImpedance) */
 #define PK_BETA 6        /* (2 pi f / c0) * consts[idx], consts[idx] = sqrt(er) taken by the plan compiler */
 
-/* simple value ops (8 int32 words: code, out, p0, p1, p2, p3, aux0, aux1) */
+/* simple value ops (8 int32 words: code, out, p0, p1, p2, p3, aux0, aux1); every p is a parameter reference.
+ * OP_TLINE: p0 = Z0, p1 = beta, p2 = length */
 #define OP_COPY 0
 #define OP_RECIP 1
 #define OP_CAP 2

@@ -214,7 +214,12 @@ class TransmissionLine(Element):
         return [self.nodes[0].index, self.nodes[1].index, self.gnd.index]
 
     def stamp_params(self):
-        return {"Z0": self.Z0, "beta": self.beta, "length": self.length.value}
+        return {"Z0": self.Z0, "beta": self.beta, "length": self.length}
+
+    def record(self) -> dict:
+        rec = super().record()
+        rec["length"] = self.length.value          # what base/tl.py:52 reads at every run
+        return rec
 
 
 class NPortS(Element):

@@ -370,6 +370,34 @@ def measure_dfma_peak(device: int | None = None) -> float:
     return out.value
 
 
+class _DriversSet:
+    """Context: batch drivers (Random / Param / optimiser variables) temporarily read the values of one row.
+    Drivers whose `_value` is not a plain attribute (OptimVar: derived from its coordinate) offer
+    `_set_physical`."""
+
+    def __init__(self, drivers):
+        self.drivers = list(drivers)
+
+    def __enter__(self):
+        self.saved = [None if hasattr(d, "_set_physical") else d._value for d in self.drivers]
+        return self
+
+    def set(self, row):
+        for d, v in zip(self.drivers, row):
+            if hasattr(d, "_set_physical"):
+                d._set_physical(float(v))
+            else:
+                d._value = float(v)
+
+    def __exit__(self, *exc):
+        for d, v in zip(self.drivers, self.saved):
+            if hasattr(d, "_set_physical"):
+                d._set_physical(None)
+            else:
+                d._value = v
+        return False
+
+
 class CompiledNetwork:
     """A frozen `Network`: stamp table + device plan(s) + the library handle(s).
 
@@ -390,7 +418,9 @@ class CompiledNetwork:
         return cls.BAND_MIN_POINTS if n <= 12 else cls.BAND_MIN_POINTS * 2 // 3 if n <= 20 else cls.BAND_MIN_POINTS // 3
 
     def __init__(self, net, mode: str | None = None, device: int | None = None):
-        self.table = net.stamp_table()
+        """`net`: a heavi_b200 `Network` / `Model`, or a `plan.StampTable` frozen by any front-end (the
+        reference's own `Network` through the binding of INTEGRATION.md)."""
+        self.table = net if isinstance(net, pl.StampTable) else net.stamp_table()
         mode = mode or os.environ.get("HVB_MODE", "auto")
         self._dump = None
         # chain-like netlists (ladders, filters, cascaded lines: tridiagonal after the bandwidth-reducing
@@ -463,16 +493,11 @@ class CompiledNetwork:
         if not self.plan.table_params or values is None or len(values) < 2 or not len(drivers):
             return False
         fp = np.ascontiguousarray(f[:: max(1, len(f) // 3)][:4], dtype=np.float64)
-        saved = [d._value for d in drivers]
-        try:
-            rows = []
+        rows = []
+        with _DriversSet(drivers) as ds:
             for row in (values[0], values[-1], values[len(values) // 2]):
-                for d, v in zip(drivers, row):
-                    d._value = float(v)
+                ds.set(row)
                 rows.append([np.array(fn(fp), dtype=np.complex128, copy=True) * np.ones(fp.shape) for (_, _, fn) in self.plan.table_params])
-        finally:
-            for d, v in zip(drivers, saved):
-                d._value = v
         return any(not np.array_equal(a, b) for other in rows[1:] for a, b in zip(rows[0], other))
 
     def run(self, f: np.ndarray, drivers=None, values=None, out=None, f32_out=None,
@@ -487,21 +512,22 @@ class CompiledNetwork:
             values = np.asarray(values, dtype=np.float64)
             nS = values.shape[0]
             S = out if out is not None else pinned_empty((nS, self.plan.P, self.plan.P, len(f)))
-            saved = [d._value for d in drivers]
-            try:
+            with _DriversSet(drivers) as ds:
                 for s in range(nS):
-                    for d, v in zip(drivers, values[s]):
-                        d._value = float(v)
+                    ds.set(values[s])
                     self.run(f, list(drivers), values[s:s + 1], out=S[s:s + 1])
-            finally:
-                for d, v in zip(drivers, saved):
-                    d._value = v
             if f32_out is not None:
                 f32_out[:] = f
             return S
         points = len(f) * (1 if values is None else len(values))
         plan, handle = self.variant(points if batch_points is None else batch_points)
-        consts, prefs, tables, samples = self.resolve(f, drivers, values, plan)
+        if drivers is not None and values is not None and len(values) == 1 and plan.table_params:
+            # one row: host-tabulated callables must see this row's driver values while they are evaluated
+            with _DriversSet(drivers) as ds:
+                ds.set(np.asarray(values, dtype=np.float64)[0])
+                consts, prefs, tables, samples = self.resolve(f, drivers, values, plan)
+        else:
+            consts, prefs, tables, samples = self.resolve(f, drivers, values, plan)
         reps = self.replicas(handle, points) if (out_ptr is None and batch_points is None) else []
         S, status = handle.run_host(f, consts, prefs, tables, samples, out, f32_out, out_ptr=out_ptr, out_ld=out_ld, replicas=reps)
         if status & HVB_STATUS_NONFINITE:

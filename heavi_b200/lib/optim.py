@@ -32,15 +32,23 @@ class OptimVar(SimParam):
         self.mapping = mapping
         self.unit = unit
         self._inf = np.inf
+        self._physical = None     # set by the batched drivers while they probe / replay single candidates
 
     # `_value` is what the plan compiler reads as this variable's per-run sample value
     @property
     def _value(self):
+        if self._physical is not None:
+            return self._physical
         return self._coord if self.mapping is None else self.mapping(self._coord)
 
     @_value.setter
     def _value(self, v):          # batched drivers write the last sample back; the coordinate rules here
         pass
+
+    def _set_physical(self, v):
+        """Batched drivers: make the variable read `v` (a physical value, i.e. after the mapping) until
+        `_set_physical(None)` -- the hook engine._tables_follow_drivers / the per-candidate fallback use."""
+        self._physical = None if v is None else float(v)
 
     def set(self, value: float):
         self._coord = value

@@ -178,11 +178,7 @@ class _Builder:
         """Normalise anything parameter-like into a description tuple (see params.py)."""
         if hasattr(p, "describe"):
             return p.describe()
-        if hasattr(p, "bspline") and p.bspline() is not None:
-            return ("spline", p)
-        if callable(p):
-            return ("table", p)
-        return ("const", complex(p))
+        return describe_foreign(p)
 
     def param(self, p) -> tuple[int, tuple]:
         """-> (pref index, description).  Table parameters get a const slot they may fall back to
@@ -255,6 +251,83 @@ class _Builder:
 _DYN = 1 << 28          # marker added to per-point value ids until the constant count is known
 
 
+class _ValueAtZero:
+    """`p.value` (= p(0), numeric.py:116-117) as a per-run scalar: `resolve_run` turns a callable that returns
+    a scalar into a constant of that run."""
+
+    def __init__(self, p):
+        self._p = p
+
+    def __call__(self, f):
+        return np.complex128(self._p.value if hasattr(self._p, "value") else self._p(0))
+
+
+def describe_foreign(p):
+    """Structural description of a parameter object that does not describe itself -- the reference's own
+    `heavi.numeric` classes when `Network.run_sp` is bound to this library.  Duck-typed on
+    the class name and the attributes those classes have (numeric.py:142-311, lib/optim.py:31-64), so that a
+    netlist built with reference objects gets the same device program as one built with heavi_b200's."""
+    name = type(p).__name__
+    inf_ok = np.isinf(getattr(p, "_inf", np.inf))
+    if name == "Scalar" and hasattr(p, "_value"):
+        return ("const", complex(p(np.float64(1.0))))
+    if name in ("Random", "Param") and hasattr(p, "_value"):
+        return ("sample", p, "id") if inf_ok else ("table", p)
+    if name == "OptimVar" and hasattr(p, "_value") and getattr(p, "mapping", None) is None:
+        return ("sample", p, "id")
+    if name in ("Negative", "Inverse") and hasattr(p, "_simparam"):
+        inner = p._simparam.describe() if hasattr(p._simparam, "describe") else describe_foreign(p._simparam)
+        if inner[0] == "sample" and inner[2] == "id" and inf_ok:
+            return ("sample", inner[1], "neg" if name == "Negative" else "inv")
+        return ("table", p)
+    if name == "Function" and hasattr(p, "_func"):
+        fn = p._func
+        # Network.transmissionline's closure (network.py:627-633): beta(f) = TWOPI * f / c0 * sqrt(func_er(f))
+        if getattr(fn, "__qualname__", "").endswith("transmissionline.<locals>.beta") and getattr(fn, "__closure__", None):
+            cells = dict(zip(fn.__code__.co_freevars, (c.cell_contents for c in fn.__closure__)))
+            er, c0 = cells.get("func_er"), cells.get("c0")
+            if er is not None and c0 == _C0 and inf_ok:
+                inner = er.describe() if hasattr(er, "describe") else describe_foreign(er)
+                if inner[0] == "const":
+                    return ("beta", inner[1])
+        return ("table", p)
+    if hasattr(p, "bspline") and p.bspline() is not None:
+        return ("spline", p)
+    if name == "interp1d" and hasattr(p, "_spline") and hasattr(p._spline, "t"):
+        # scipy.interpolate.interp1d(kind='cubic', bounds_error=False, fill_value=(y[0], y[-1])): what
+        # lib/touchstone.py:258 hands to n_port_S -- a B-spline with constant end fill, evaluated on the device
+        tr = _Interp1dTrace(p)
+        if tr.ok:
+            return ("spline", tr)
+    if callable(p):
+        return ("table", p)
+    return ("const", complex(p))
+
+
+class _Interp1dTrace:
+    """Adapter: a scipy `interp1d` spline seen as the (x, y, bspline()) trace `_Builder.add_spline` reads."""
+
+    def __init__(self, ip):
+        self._ip = ip
+        self.x = np.asarray(ip.x, dtype=np.float64)
+        self.y = np.asarray(ip.y, dtype=np.complex128).reshape(-1)
+        spl = ip._spline
+        self._tck = (np.asarray(spl.t, dtype=np.float64), np.asarray(spl.c, dtype=np.complex128).reshape(len(spl.c)), int(spl.k))
+        fv = getattr(ip, "fill_value", None)
+        try:
+            lo, hi = fv
+            same = complex(np.asarray(lo).reshape(-1)[0]) == complex(self.y[0]) and complex(np.asarray(hi).reshape(-1)[0]) == complex(self.y[-1])
+        except Exception:
+            same = False
+        self.ok = bool(same and not getattr(ip, "bounds_error", True) and self.y.shape == self.x.shape and self._tck[2] <= 3)
+
+    def __call__(self, f):
+        return self._ip(f)
+
+    def bspline(self):
+        return self._tck
+
+
 def _is_static(desc) -> bool:
     return desc[0] == "const"
 
@@ -308,7 +381,12 @@ def _component_values(b: _Builder, kind: str, par: dict, nterm: int):
     if kind == "tline":
         pz, _ = b.param(par["Z0"])
         pb, _ = b.param(par["beta"])
-        plen = b.const(complex(par["length"]))
+        # the reference reads `self.length.value` (= length(0)) inside every run_sp (base/tl.py:52): a Param /
+        # Random / optimiser variable as length is a sample column, a callable is evaluated at f = 0 per run
+        length = par["length"]
+        if callable(length) and b.describe(length)[0] not in ("const", "sample"):
+            length = _ValueAtZero(length)
+        plen, _ = b.param(length)
         base = b.dyn_values(9)
         b.ops.append([OP_TLINE, base, pz, pb, plen, 0, 0, 0])
         v = _DYN + base

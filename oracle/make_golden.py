@@ -21,6 +21,8 @@ It also prints how far the numpy oracle (oracle/mna_oracle.py) is from the refer
 `mc_twoport.npz` is different in kind: the reference's own Monte-Carlo loop (`for i in mc.iterate(6)`,
 np.random.seed(11)) over a netlist with lib/mc.py's RandomTwoPort -- per-trial draws and per-trial S.
 `python oracle/make_golden.py --only-mc-twoport` regenerates just that file.
+`optim_costs.npz` / `param_sweep.npz` (`--only-callers`): the reference's optimiser objective on a fixed
+population of candidates and its ParameterSweep loop (the repeated-run_sp callers of SURVEY.md 8f).
 """
 from __future__ import annotations
 
@@ -88,11 +90,35 @@ def mc_twoport(hv):
     print("mc_twoport     %d trials, %d randoms, nF=%d" % (len(Ss), len(mc._random_numbers), len(f)), flush=True)
 
 
+def callers(hv):
+    """The reference's own repeated-`run_sp` callers: the optimiser objective (lib/optim.py:386-438, one run_sp
+    per candidate) on a fixed population, and the ParameterSweep loop (numeric.py:418-446)."""
+    m, opt = circuits.build_optim(hv)
+    X = circuits.optim_population()
+    obj = opt.generate_objective()
+    costs = np.array([obj(X[:, k]) for k in range(X.shape[1])])
+    m2, opt2 = circuits.build_optim(hv)
+    obj_dw = opt2.generate_objective(differential_weighting=0.3)
+    costs_dw = np.array([obj_dw(X[:, k]) for k in range(X.shape[1])])
+    np.savez_compressed(os.path.join(GOLD, "optim_costs.npz"), X=X, costs=costs, costs_dw=costs_dw)
+    print("optim_costs    %d candidates, cost range %.3g .. %.3g" % (X.shape[1], costs.min(), costs.max()), flush=True)
+    m3, sweep, f = circuits.build_sweep(hv)
+    for ix, vals in sweep.iterate():
+        sweep.submit(m3.run_sp(f), f)
+    nd = sweep.S
+    np.savez_compressed(os.path.join(GOLD, "param_sweep.npz"), f=f, S=np.asarray(nd._sdata),
+                        axes0=np.asarray(nd._axes[0]), axes1=np.asarray(nd._axes[1]))
+    print("param_sweep    grid %s" % (np.asarray(nd._sdata).shape,), flush=True)
+
+
 def main():
     hv = load_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "--only-mc-twoport":
         os.makedirs(GOLD, exist_ok=True)
         return mc_twoport(hv)
+    if len(sys.argv) > 1 and sys.argv[1] == "--only-callers":
+        os.makedirs(GOLD, exist_ok=True)
+        return callers(hv)
     os.makedirs(GOLD, exist_ok=True)
     if not os.path.exists(circuits.SYNTH8):
         circuits.write_synth8()
@@ -121,6 +147,7 @@ def main():
     capture("c5_ladder", m, f[::66667][:12], y_points=1)
 
     mc_twoport(hv)
+    callers(hv)
 
     m, f = circuits.build_divider(hv)
     capture("ka_divider", m, f)

@@ -321,3 +321,45 @@ def build_twoport_cascade(hv, sections: int = 6, nF: int = 33, seed: int = 0):
         at = n2
     m.inductor(at, b, 0.8e-9)
     return m, np.linspace(0.5e9, 6e9, nF)
+
+
+# ---------------------------------------------------------------- optimiser / sweep callers
+def build_optim(hv):
+    """Small LC match driven by three optimiser variables and three band requirements
+    (lib/optim.py: Optimiser.cap / ind / add_splimit / generate_objective, :239-438)."""
+    import importlib
+    optim = importlib.import_module(hv.__name__ + ".lib.optim")
+    m = _model(hv)
+    opt = optim.Optimiser(m)
+    C1, L1, C2 = opt.cap(initial=-12.0), opt.ind(initial=-8.7), opt.cap(logscale=False, initial=-12.3)
+    a, b = m.quick_port(50), m.quick_port(50)
+    x = m.node()
+    m.capacitor(a, m.gnd, C1)
+    m.inductor(a, x, L1)
+    m.capacitor(x, m.gnd, C2)
+    m.resistor(x, b, 3.0)
+    opt.add_splimit(1e9, 2e9, 21, (2, 1), lower_limit=optim.dBabove(-1))
+    opt.add_splimit(4e9, 6e9, 31, (2, 1), upper_limit=optim.dBbelow(-20))
+    opt.add_splimit(1e9, 2e9, 21, (1, 1), upper_limit=optim.dBbelow(-15), weight=0.5)
+    return m, opt
+
+
+def optim_population():
+    rng = np.random.default_rng(4)
+    return np.stack([rng.uniform(-12.5, -11.5, 9), rng.uniform(-9.2, -8.4, 9), rng.uniform(2e-13, 2e-12, 9)])   # [vars, candidates]
+
+
+def build_sweep(hv):
+    """4 x 3 ParameterSweep over a C and an L (numeric.py:314-449)."""
+    m = _model(hv)
+    sweep = hv.ParameterSweep()
+    C = sweep.lin(0.5e-12, 2e-12).add(4)
+    L = sweep.lin(1e-9, 3e-9).add(3)
+    for p in (C, L):                       # the reference evaluates a component's value when it is created
+        p.initialize()
+    a, b = m.quick_port(50), m.quick_port(75)
+    mid = m.node()
+    m.inductor(a, mid, L)
+    m.capacitor(mid, m.gnd, C)
+    m.resistor(mid, b, 12.0)
+    return m, sweep, np.linspace(1e9, 4e9, 257)

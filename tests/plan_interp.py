@@ -131,7 +131,7 @@ class Interp:
             elif code == pl.OP_TLINE:
                 Z0 = self.param(op[2])
                 beta = self.param(op[3])
-                length = self.consts[op[4]].real
+                length = np.real(self.param(op[4]))
                 th = 1j * beta * length
                 a11 = np.cosh(th)
                 a12 = Z0 * np.sinh(th)

@@ -249,61 +249,74 @@ def test_device_monte_carlo_statistics_match_numpy_reduction():
     assert np.array_equal(dev2._moments, dev._moments)
 
 
-def test_parameter_sweep_batch_matches_serial_loop():
-    """run_sweep == the reference's `for ix, v in sweep.iterate(): sweep.submit(run_sp(f), f)` loop."""
-    def build():
-        m = hv.Model(suppress_loadbar=True)
-        sweep = hv.ParameterSweep()
-        C = sweep.lin(0.5e-12, 2e-12).add(4)
-        L = sweep.lin(1e-9, 3e-9).add(3)
-        a, b = m.quick_port(50), m.quick_port(75)
-        mid = m.node()
-        m.inductor(a, mid, L)
-        m.capacitor(mid, m.gnd, C)
-        m.resistor(mid, b, 12.0)
-        return m, sweep
-    f = np.linspace(1e9, 4e9, 257)
-    m, sweep = build()
-    for ix, vals in sweep.iterate():
+def test_parameter_sweep_batch_matches_reference_loop():
+    """run_sweep == the reference's `for ix, v in sweep.iterate(): sweep.submit(run_sp(f), f)` loop
+    (numeric.py:418-446), captured from the reference itself in tests/golden/param_sweep.npz."""
+    import circuits
+    g = golden("param_sweep")
+    m, sweep, f = circuits.build_sweep(hv)
+    assert np.array_equal(f, g["f"])
+    for ix, vals in sweep.iterate():                       # the serial loop on the GPU path
         sweep.submit(m.run_sp(f), f)
     serial = sweep.S
-    m2, sweep2 = build()
-    nd = m2.run_sweep(f, sweep2)
-    assert nd._sdata.shape == (4, 3, 2, 2, 257) == serial._sdata.shape
+    m2, sweep2, _ = circuits.build_sweep(hv)
+    nd = m2.run_sweep(f, sweep2)                           # the whole grid as one batch
+    assert nd._sdata.shape == (4, 3, 2, 2, 257) == g["S"].shape
     assert np.array_equal(nd._sdata, serial._sdata)
+    tol = ATOL + RTOL * np.abs(g["S"])
+    assert np.all(np.abs(nd._sdata - g["S"]) <= tol)
+    assert np.array_equal(np.asarray(nd._axes[0]), g["axes0"]) and np.array_equal(np.asarray(nd._axes[1]), g["axes1"])
     assert np.array_equal(nd.S(2, 1), serial.S(2, 1))
 
 
-def test_optimiser_population_objective_matches_serial_objective():
-    """One batched run over a population == the reference's one-run_sp-per-candidate objective
-    (lib/optim.py:424-436)."""
+def test_optimiser_objectives_match_reference_costs():
+    """The serial objective (one run_sp per candidate, lib/optim.py:386-438) and the batched population
+    objective against the cost vector the REFERENCE's objective produced for the same candidates
+    (tests/golden/optim_costs.npz)."""
+    import circuits
+    g = golden("optim_costs")
+    X = circuits.optim_population()
+    assert np.array_equal(X, g["X"])
+    m1, o1 = circuits.build_optim(hv)
+    serial = o1.generate_objective()
+    got_serial = np.array([serial(X[:, k]) for k in range(X.shape[1])])
+    m2, o2 = circuits.build_optim(hv)
+    batched = o2.generate_population_objective()
+    got = batched(X)
+    assert got.shape == (9,)
+    assert np.allclose(got_serial, g["costs"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(got, g["costs"], rtol=1e-9, atol=1e-12)
+    assert batched(X[:, 3]) == pytest.approx(g["costs"][3], rel=1e-9)
+    d2 = circuits.build_optim(hv)[1]
+    assert np.allclose(d2.generate_population_objective(differential_weighting=0.3)(X), g["costs_dw"], rtol=1e-9, atol=1e-12)
+
+
+def test_population_objective_with_a_callable_that_reads_an_optimiser_variable():
+    """A user callable that closes over an OptimVar is a table that differs from candidate to candidate: the
+    batched driver must notice (engine._tables_follow_drivers) and agree with the serial objective."""
     from heavi_b200.lib import optim
+    from oracle import mna_oracle as orc
 
     def build():
         m = hv.Model(suppress_loadbar=True)
         opt = optim.Optimiser(m)
-        C1, L1, C2 = opt.cap(initial=-12.0), opt.ind(initial=-8.7), opt.cap(logscale=False, initial=-12.3)
+        L1 = opt.ind(initial=-8.7)
         a, b = m.quick_port(50), m.quick_port(50)
         x = m.node()
-        m.capacitor(a, m.gnd, C1)
         m.inductor(a, x, L1)
-        m.capacitor(x, m.gnd, C2)
-        m.resistor(x, b, 3.0)
+        m.impedance(x, b, lambda fr: 2.0 + 1j * 2 * np.pi * fr * L1._value * 0.1)      # reads the variable
+        m.capacitor(x, m.gnd, 1e-12)
         opt.add_splimit(1e9, 2e9, 21, (2, 1), lower_limit=optim.dBabove(-1))
-        opt.add_splimit(4e9, 6e9, 31, (2, 1), upper_limit=optim.dBbelow(-20))
-        opt.add_splimit(1e9, 2e9, 21, (1, 1), upper_limit=optim.dBbelow(-15), weight=0.5)
         return m, opt
 
-    rng = np.random.default_rng(4)
-    X = np.stack([rng.uniform(-12.5, -11.5, 9), rng.uniform(-9.2, -8.4, 9), rng.uniform(2e-13, 2e-12, 9)])   # [vars, pop]
+    X = np.array([[-9.2, -8.8, -8.5, -8.1]])
     m1, o1 = build()
     serial = o1.generate_objective()
     ref = np.array([serial(X[:, k]) for k in range(X.shape[1])])
+    assert len(set(np.round(ref, 9))) == 4
     m2, o2 = build()
-    batched = o2.generate_population_objective()
-    got = batched(X)
-    assert got.shape == (9,) and np.allclose(got, ref, rtol=1e-12, atol=1e-14)
-    assert batched(X[:, 3]) == pytest.approx(ref[3], rel=1e-12)
-    d1, d2 = build()[1], build()[1]
-    assert d2.generate_population_objective(differential_weighting=0.3)(X)[2] == pytest.approx(
-        d1.generate_objective(differential_weighting=0.3)(X[:, 2]), rel=1e-12)
+    got = o2.generate_population_objective()(X)
+    assert np.allclose(got, ref, rtol=1e-11, atol=1e-13)
+    o1.parameters[0].set(-8.8)                              # and the serial S itself against the oracle
+    f = np.linspace(1e9, 2e9, 21)
+    assert np.max(np.abs(m1.run_sp(f)._S - orc.run_sp(m1.records(), m1.n_nodes, len(m1.sources), f, method="lu_batched"))) < 1e-13
