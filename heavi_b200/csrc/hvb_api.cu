@@ -65,7 +65,8 @@ struct GenKernel {
     HvbJitKernel k;
     DevBuf rows, itab, dtab;
     bool rolled = false, scratch_acc = false;
-    int ctas_per_sm = 0, n_cases = 0;
+    int ctas_per_sm = 0, n_cases = 0, threads = 128;
+    size_t smem = 0;
     long long flops = 0;
     std::vector<int32_t> prefs;                        // the layout the value formulas were specialised on
 };
@@ -104,6 +105,7 @@ struct hvb_plan {
     bool pushed_valid = false;
     cudaStream_t pushed_stream = nullptr;
     GenPlan gen;
+    bool gen_hub = false;                              // kernel E (N-port block + chains) instead of kernel D (one chain)
     std::vector<GenKernel*> gen_variants;
     GenKernel* gk = nullptr;
     // tunables read once, at plan creation (environment)
@@ -276,7 +278,7 @@ static bool gen_kernel_ok(const hvb_plan* pl) {
     const char* force = getenv("HVB_FORCE_BLOCK");
     if (force && force[0] == '1') return false;
     if (pl->d.kernel_hint == 1) return false;
-    return hvb_gen_supported(pl->gen, nullptr);
+    return hvb_gen_supported(pl->gen, nullptr) || hvb_gen_hub_candidate(pl->gen);
 }
 
 // ---- kernel D: generate + compile (cached per process by source text) + load ------------------------
@@ -287,12 +289,17 @@ static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs) {
     const size_t np = (size_t)pl->d.n_prefs * 2;
     if (pl->gk && pl->gk->prefs.size() == np && (np == 0 || memcmp(pl->gk->prefs.data(), prefs, np * 4) == 0)) return HVB_OK;
     for (GenKernel* v : pl->gen_variants)
-        if (v->prefs.size() == np && (np == 0 || memcmp(v->prefs.data(), prefs, np * 4) == 0)) { pl->gk = v; return HVB_OK; }
+        if (v->prefs.size() == np && (np == 0 || memcmp(v->prefs.data(), prefs, np * 4) == 0)) {
+            pl->gk = v; pl->threads = v->threads; pl->smem = v->smem; pl->regs = v->k.regs; pl->ctas_per_sm = v->ctas_per_sm;
+            pl->max_grid = v->ctas_per_sm * pl->sm_count;
+            return HVB_OK;
+        }
     GenResult res;
     std::string err;
     const char* md = getenv("HVB_GEN_MODE");
-    if (hvb_gen_source(pl->gen, prefs, md ? atoi(md) : 0, hvb_gen_prelude(), &res, &err) != 0)
-        return fail(HVB_ERR_UNSUPPORTED, "kernel generator: %s", err.c_str());
+    const int grc = pl->gen_hub ? hvb_gen_hub_source(pl->gen, prefs, hvb_gen_prelude(), &res, &err)
+                                : hvb_gen_source(pl->gen, prefs, md ? atoi(md) : 0, hvb_gen_prelude(), &res, &err);
+    if (grc != 0) return fail(HVB_ERR_UNSUPPORTED, "kernel generator: %s", err.c_str());
     std::shared_ptr<std::vector<char>> cubin;
     {
         std::lock_guard<std::mutex> lk(g_cubin_mu);
@@ -311,18 +318,24 @@ static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs) {
     gk->rolled = res.rolled; gk->scratch_acc = res.scratch_acc; gk->n_cases = res.n_cases; gk->flops = res.flops_per_solve;
     gk->prefs.assign(prefs, prefs + np);
     pl->threads = res.threads;
+    gk->threads = res.threads; gk->smem = res.smem_bytes;
+    if (res.smem_bytes > 48 * 1024) {
+        std::string e2;
+        if (hvb_jit_set_max_dynamic_smem(gk->k, res.smem_bytes, &e2) != 0) return fail(HVB_ERR_CUDA, "%s", e2.c_str());
+    }
     if (res.rolled && !res.tables_in_source) {
         CU(upload(gk->rows, res.rows.data(), res.rows.size() * 4));
         CU(upload(gk->itab, res.itab.data(), res.itab.size() * 4));
         CU(upload(gk->dtab, res.dtab.data(), res.dtab.size() * 8));
     }
     int occ = 0;
-    if (hvb_jit_occupancy(gk->k, pl->threads, 0, &occ, &err) != 0) return fail(HVB_ERR_CUDA, "%s", err.c_str());
+    if (hvb_jit_occupancy(gk->k, pl->threads, res.smem_bytes, &occ, &err) != 0) return fail(HVB_ERR_CUDA, "%s", err.c_str());
     if (occ < 1) return fail(HVB_ERR_UNSUPPORTED, "generated kernel does not fit on an SM (%d registers)", gk->k.regs);
     gk->ctas_per_sm = occ;
     pl->regs = gk->k.regs;
     pl->ctas_per_sm = occ;
     pl->max_grid = occ * pl->sm_count;
+    pl->smem = res.smem_bytes;
     pl->gk = gk.get();
     pl->gen_variants.push_back(gk.release());
     return HVB_OK;
@@ -352,8 +365,9 @@ static int select_kernel(hvb_plan* pl) {
         // kernel D: the netlist is a chain (tridiagonal in the plan's row order) -> a kernel generated for
         // exactly this netlist, one thread per point, compiled at the first run (hvb_gen.cpp, hvb_jit.cpp)
         pl->kclass = 3;
+        pl->gen_hub = !hvb_gen_supported(pl->gen, nullptr);
         pl->NB = 1;
-        pl->threads = 128;
+        pl->threads = pl->gen_hub ? 32 : 128;
         pl->smem = 0;
         pl->max_grid = pl->sm_count * 4;               // refined once the kernel exists
         return HVB_OK;
@@ -690,7 +704,7 @@ static int launch(hvb_plan* pl, HvbDev& D, cudaStream_t st, int slot = 0) {
     if (pl->kclass == 3) {
         if (!pl->gk) return fail(HVB_ERR_ARG, "generated kernel missing (internal)");
         std::string err;
-        if (hvb_jit_launch(pl->gk->k, (unsigned)grid, (unsigned)pl->threads, 0, st, args, &err) != 0) return fail(HVB_ERR_CUDA, "%s", err.c_str());
+        if (hvb_jit_launch(pl->gk->k, (unsigned)grid, (unsigned)pl->gk->threads, pl->gk->smem, st, args, &err) != 0) return fail(HVB_ERR_CUDA, "%s", err.c_str());
         pl->launches++;
         return HVB_OK;
     }
@@ -1052,6 +1066,8 @@ extern "C" int hvb_plan_kernel_info(hvb_plan* pl, hvb_kernel_info* out) {
     out->local_bytes = pl->gk ? pl->gk->k.local_bytes : 0;
     out->gen_scratch_acc = pl->gk ? (pl->gk->scratch_acc ? 1 : 0) : 0;
     out->gen_flops_per_solve = pl->gk ? pl->gk->flops : 0;
+    out->gen_hub = pl->gen_hub ? 1 : 0;
+    out->reserved = 0;
     return HVB_OK;
 }
 
@@ -1062,14 +1078,20 @@ extern "C" int hvb_codegen_source(const hvb_plan_desc* desc, const int32_t* pref
     memset(info, 0, sizeof(*info));
     GenPlan g;
     g.from_desc(*desc);
-    std::string why;
-    if (!hvb_gen_supported(g, &why)) {
-        snprintf(info->reason, sizeof(info->reason), "%s", why.c_str());
+    std::string why, why_hub;
+    if (desc->n_prefs && !prefs) return fail(HVB_ERR_ARG, "prefs missing");
+    const bool chain = hvb_gen_supported(g, &why);
+    const bool hub = !chain && hvb_gen_hub_supported(g, prefs, &why_hub);
+    if (!chain && !hub) {
+        snprintf(info->reason, sizeof(info->reason), "chain kernel: %s; hub kernel: %s", why.c_str(), why_hub.c_str());
         return HVB_OK;
     }
-    if (desc->n_prefs && !prefs) return fail(HVB_ERR_ARG, "prefs missing");
     GenResult res;
-    if (hvb_gen_source(g, prefs, mode, hvb_gen_prelude(), &res, &why) != 0) return fail(HVB_ERR_UNSUPPORTED, "kernel generator: %s", why.c_str());
+    const int grc = hub ? hvb_gen_hub_source(g, prefs, hvb_gen_prelude(), &res, &why) : hvb_gen_source(g, prefs, mode, hvb_gen_prelude(), &res, &why);
+    if (grc != 0) return fail(HVB_ERR_UNSUPPORTED, "kernel generator: %s", why.c_str());
+    info->hub = hub ? 1 : 0;
+    info->smem_bytes = (int64_t)res.smem_bytes;
+    info->threads = res.threads;
     info->supported = 1;
     info->rolled = res.rolled; info->n_cases = res.n_cases; info->scratch_acc = res.scratch_acc;
     info->src_len = (int64_t)res.src.size();

@@ -52,6 +52,8 @@ void GenPlan::from_desc(const hvb_plan_desc& d) {
     port_rows.assign(d.port_rows, d.port_rows + 3 * (size_t)P);
     epi_port_of_row.assign(d.epi_port_of_row, d.epi_port_of_row + n);
     epi_scale.assign(d.epi_scale, d.epi_scale + (size_t)std::max(P * P, 1));
+    coops.assign(d.coops, d.coops + (size_t)ncoops * HVB_COOP_WORDS);
+    spl_trace.assign(d.spl_trace, d.spl_trace + (size_t)d.n_traces * 4);
 }
 
 namespace {

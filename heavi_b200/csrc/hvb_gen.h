@@ -21,6 +21,8 @@ struct GenPlan {                       // host copy of what the generator reads 
     std::vector<double> fop_arg;
     std::vector<int32_t> port_rows, epi_port_of_row;
     std::vector<double> epi_scale;
+    std::vector<int32_t> coops;        // [ncoops*8]
+    std::vector<int32_t> spl_trace;    // [n_traces*4]
     void from_desc(const hvb_plan_desc& d);
 };
 
@@ -34,6 +36,7 @@ struct GenResult {
     bool scratch_acc = false;          // port-pair accumulators live in the output array, per-port sums in shared memory (P > 4)
     bool tables_in_source = false;     // rolled: the row tables are __constant__ initialisers of the module (no upload needed)
     int threads = 128;                 // threads per CTA the kernel is written for
+    size_t smem_bytes = 0;             // dynamic shared memory per CTA (kernel E: the per-thread dense tiles)
     int n_cases = 0;                   // distinct row shapes emitted (rolled)
     long long flops_per_solve = 0;     // executed real flops of the elimination / border recurrences (excl. stamp values)
 };
@@ -45,5 +48,10 @@ bool hvb_gen_supported(const GenPlan& g, std::string* why);
 // mode: 0 auto (unrolled up to HVB_GEN_UNROLL_MAX rows, rolled above), 1 unrolled, 2 rolled.
 // prelude: text of plan_format.h + hvb_device.cuh (embedded at build time, see Makefile).
 int hvb_gen_source(const GenPlan& g, const int32_t* prefs, int mode, const char* prelude, GenResult* out, std::string* err);
+
+// Kernel E ("hub": one N-port S block + chains hanging off its nodes, hvb_gen_hub.cpp)
+bool hvb_gen_hub_candidate(const GenPlan& g);                                   // structure only
+bool hvb_gen_hub_supported(const GenPlan& g, const int32_t* prefs, std::string* why);
+int hvb_gen_hub_source(const GenPlan& g, const int32_t* prefs, const char* prelude, GenResult* out, std::string* err);
 
 const char* hvb_gen_prelude();

@@ -184,6 +184,13 @@ int hvb_jit_occupancy(const HvbJitKernel& k, int threads, size_t smem, int* bloc
     return 0;
 }
 
+int hvb_jit_set_max_dynamic_smem(const HvbJitKernel& k, size_t bytes, std::string* err) {
+    CUresult r = drv()->FuncSetAttribute(k.func, 8 /*CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES*/, (int)bytes);
+    if (r) { if (err) *err = "cuFuncSetAttribute(max dynamic shared memory): " + cu_err(r); return -1; }
+    drv()->FuncSetAttribute(k.func, 9 /*CU_FUNC_ATTRIBUTE_PREFERRED_SHARED_MEMORY_CARVEOUT*/, 100);
+    return 0;
+}
+
 int hvb_jit_launch(const HvbJitKernel& k, unsigned grid, unsigned threads, size_t smem, void* stream, void** args, std::string* err) {
     CUresult r = drv()->LaunchKernel(k.func, grid, 1, 1, threads, 1, 1, (unsigned)smem, stream, args, nullptr);
     if (r) { if (err) *err = "cuLaunchKernel: " + cu_err(r); return -1; }

@@ -17,4 +17,5 @@ int hvb_jit_compile(const std::string& src, std::vector<char>* cubin, std::strin
 int hvb_jit_load(const std::vector<char>& cubin, const char* name, HvbJitKernel* out, std::string* err);
 void hvb_jit_unload(HvbJitKernel* k);
 int hvb_jit_occupancy(const HvbJitKernel& k, int threads, size_t smem, int* blocks_per_sm, std::string* err);
+int hvb_jit_set_max_dynamic_smem(const HvbJitKernel& k, size_t bytes, std::string* err);
 int hvb_jit_launch(const HvbJitKernel& k, unsigned grid, unsigned threads, size_t smem, void* stream, void** args, std::string* err);

@@ -45,12 +45,14 @@ class RunArgs(C.Structure):
 class KernelInfo(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("kernel_class", "group", "pmax", "threads", "smem_bytes", "regs",
                                          "ctas_per_sm", "sm_count", "rows_per_lane", "stream_words")] + [("launches", C.c_int64)] + [
-        (k, C.c_int32) for k in ("gen_rolled", "gen_cases", "local_bytes", "gen_scratch_acc")] + [("gen_flops_per_solve", C.c_int64)]
+        (k, C.c_int32) for k in ("gen_rolled", "gen_cases", "local_bytes", "gen_scratch_acc")] + [("gen_flops_per_solve", C.c_int64)] + [
+        ("gen_hub", C.c_int32), ("reserved", C.c_int32)]
 
 
 class CodegenInfo(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("supported", "rolled", "n_cases", "scratch_acc")] + [
-        (k, C.c_int64) for k in ("src_len", "n_rows", "n_itab", "n_dtab", "flops_per_solve")] + [("reason", C.c_char * 256)]
+        (k, C.c_int64) for k in ("src_len", "n_rows", "n_itab", "n_dtab", "flops_per_solve")] + [
+        ("hub", C.c_int32), ("threads", C.c_int32), ("smem_bytes", C.c_int64), ("reason", C.c_char * 256)]
 
 
 EXPORTS = ("hvb_warp_shape", "hvb_plan_create", "hvb_plan_destroy", "hvb_run_host", "hvb_run_device",
@@ -222,7 +224,8 @@ def codegen_source(plan: pl.DevicePlan, prefs: np.ndarray | None = None, mode: i
     info = CodegenInfo()
     _check(lib.hvb_codegen_source(C.byref(d), _ptr(prefs), mode, None, 0, None, None, None, C.byref(info)))
     out = {"supported": bool(info.supported), "reason": info.reason.decode(), "rolled": bool(info.rolled),
-           "n_cases": info.n_cases, "scratch_acc": bool(info.scratch_acc), "flops_per_solve": info.flops_per_solve}
+           "n_cases": info.n_cases, "scratch_acc": bool(info.scratch_acc), "flops_per_solve": info.flops_per_solve,
+           "hub": bool(info.hub), "threads": info.threads, "smem_bytes": info.smem_bytes}
     if not info.supported:
         return out
     src = C.create_string_buffer(info.src_len + 1)
@@ -231,7 +234,8 @@ def codegen_source(plan: pl.DevicePlan, prefs: np.ndarray | None = None, mode: i
     dtab = np.zeros(max(info.n_dtab, 1), dtype=np.float64)
     _check(lib.hvb_codegen_source(C.byref(d), _ptr(prefs), mode, C.cast(src, C.c_void_p), info.src_len + 1,
                                   _ptr(rows), _ptr(itab), _ptr(dtab), C.byref(info)))
-    out.update(src=src.value.decode(), rows=rows[:info.n_rows], itab=itab[:info.n_itab], dtab=dtab[:info.n_dtab])
+    out.update(src=src.value.decode(), rows=rows[:info.n_rows], itab=itab[:info.n_itab], dtab=dtab[:info.n_dtab],
+               flops_per_solve=info.flops_per_solve, hub=bool(info.hub), threads=info.threads, smem_bytes=info.smem_bytes)
     return out
 
 
@@ -421,6 +425,7 @@ class CompiledNetwork:
         """`net`: a heavi_b200 `Network` / `Model`, or a `plan.StampTable` frozen by any front-end (the
         reference's own `Network` through the binding of INTEGRATION.md)."""
         self.table = net if isinstance(net, pl.StampTable) else net.stamp_table()
+        self._hub, self._dense_fallback, self._mode_arg, self._device_arg = False, None, mode, device
         mode = mode or os.environ.get("HVB_MODE", "auto")
         self._dump = None
         # chain-like netlists (ladders, filters, cascaded lines: tridiagonal after the bandwidth-reducing
@@ -435,6 +440,16 @@ class CompiledNetwork:
                 handle = DevicePlanHandle(cplan, device, kernel_hint=2)
                 if handle.kernel_info()["kernel_class"] == 3:
                     self.plan, self.handle, self.rows_per_lane, self._band = cplan, handle, 1, False
+                    return
+            # hubs -- one N-port S block (a Touchstone device) with a matching chain on each of its nodes: the
+            # generated kernel E solves two Pn x Pn systems per point instead of one dense (chains + Pn)^2 one
+            hplan = pl.compile_plan(self.table, mode)
+            if len(hplan.coops) == 1 and hplan.epi_simple and hplan.P <= 8 and int(hplan.coops[0][2]) <= 8 and hplan.n == hplan.n_real:
+                handle = DevicePlanHandle(hplan, device, kernel_hint=2)
+                ki = handle.kernel_info()
+                if ki["kernel_class"] == 3 and ki["gen_hub"] == 1:
+                    self.plan, self.handle, self.rows_per_lane, self._band = hplan, handle, 1, False
+                    self._hub = True
                     return
         plan = pl.compile_plan(self.table, mode)
         shape = warp_shape(plan.n_real, plan.P, plan.max_nport)
@@ -464,6 +479,20 @@ class CompiledNetwork:
             if band:
                 return band
         return self.plan, self.handle
+
+    def dense_fallback(self):
+        """The same netlist on the precompiled dense kernels (built on first use)."""
+        if self._dense_fallback is None:
+            old = os.environ.get("HVB_NO_GEN")
+            os.environ["HVB_NO_GEN"] = "1"
+            try:
+                self._dense_fallback = CompiledNetwork(self.table, self._mode_arg, self._device_arg)
+            finally:
+                if old is None:
+                    os.environ.pop("HVB_NO_GEN", None)
+                else:
+                    os.environ["HVB_NO_GEN"] = old
+        return self._dense_fallback
 
     def replicas(self, handle, points: int):
         """Handles of `handle`'s plan on the other visible devices this call should use (created on first use)."""
@@ -530,6 +559,11 @@ class CompiledNetwork:
             consts, prefs, tables, samples = self.resolve(f, drivers, values, plan)
         reps = self.replicas(handle, points) if (out_ptr is None and batch_points is None) else []
         S, status = handle.run_host(f, consts, prefs, tables, samples, out, f32_out, out_ptr=out_ptr, out_ld=out_ld, replicas=reps)
+        if self._hub and (status & HVB_STATUS_ZERO_PIVOT):
+            # kernel E does not exchange a chain's last row with its core row; it flags the (rare) point where that
+            # pivot is unsafe and the whole call is repeated on the dense register kernel (full partial pivoting)
+            return self.dense_fallback().run(f, drivers, values, out=out, f32_out=f32_out, batch_points=batch_points,
+                                             out_ptr=out_ptr, out_ld=out_ld)
         if status & HVB_STATUS_NONFINITE:
             # the reference's numba lstsq raises for NaN/Inf input
             raise np.linalg.LinAlgError("MNA matrix or S-parameters contain NaN/Inf (e.g. f = 0 with an inductor)")

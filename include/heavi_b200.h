@@ -194,11 +194,16 @@ typedef struct hvb_kernel_info {
     int32_t gen_scratch_acc;/* generated kernel: port-pair sums kept in the output array (P > 4)  */
     int64_t gen_flops_per_solve; /* generated kernel: executed real flops of elimination + port
                                recurrences per point (stamp values excluded)                      */
+    int32_t gen_hub;        /* generated kernel: 0 chain kernel (tridiagonal netlist), 1 hub kernel
+                               (one N-port S block + chains hanging off its nodes)                */
+    int32_t reserved;
 } hvb_kernel_info;
 int hvb_plan_kernel_info(hvb_plan* plan, hvb_kernel_info* out);
 
 /* Kernel class 3, "generated": when the netlist is a chain -- the MNA matrix is tridiagonal in the plan's
- * row order, every port is ground-referenced with a constant real Z0 -- the library writes CUDA source for
+ * row order -- or a hub -- one N-port S block (up to 8 ports, reference node = ground) with chains of parts
+ * hanging off its nodes (a Touchstone device in per-port matching networks, BASELINE configs[2]) -- and
+ * every port is ground-referenced with a constant real Z0, the library writes CUDA source for
  * exactly this netlist (stamp formulas, matrix cells and port positions as straight-line code or a loop over
  * row shapes), compiles it with NVRTC for sm_100a at the first run and launches one thread per point.  It
  * replaces the same reference lines as hvb_run_host (network.py:385-416, solvers/spfn.py:106-179).
@@ -212,6 +217,9 @@ typedef struct hvb_codegen_info {
     int64_t src_len;        /* strlen of the source                                               */
     int64_t n_rows, n_itab, n_dtab;   /* elements of the row-loop tables (0 for straight-line code) */
     int64_t flops_per_solve;
+    int32_t hub;            /* 1: hub kernel (N-port block + chains), 0: chain kernel             */
+    int32_t threads;        /* threads per CTA the source is written for                          */
+    int64_t smem_bytes;     /* dynamic shared memory per CTA                                      */
     char reason[256];
 } hvb_codegen_info;
 int hvb_codegen_source(const hvb_plan_desc* desc, const int32_t* prefs, int32_t mode, char* src_out, int64_t src_cap,

@@ -363,3 +363,37 @@ def build_sweep(hv):
     m.capacitor(mid, m.gnd, C)
     m.resistor(mid, b, 12.0)
     return m, sweep, np.linspace(1e9, 4e9, 257)
+
+
+def build_hub(hv, n_block: int = 4, chain_rows=(2, 1, 0, 3), port_on=(0, 0, None, 1), seed: int = 0, nF: int = 33):
+    """An N-port S block (analytic passive S(f) given as Python callables) whose node k carries a chain of
+    `chain_rows[k]` extra nodes; `port_on[k]` = position on that chain (0 = far end) of a port, None = no port,
+    and for a chain of 0 rows a port value of 0 puts the port on the block node itself."""
+    rng = np.random.default_rng(500 + seed)
+    m = _model(hv)
+    Q, _ = np.linalg.qr(rng.normal(size=(n_block, n_block)) + 1j * rng.normal(size=(n_block, n_block)))
+    tau = rng.uniform(0.05e-9, 0.4e-9, n_block)
+    gain = rng.uniform(0.2, 0.7, n_block)
+
+    def S_of(i, j):
+        return lambda f: np.einsum("k,kf,k->f", Q[i, :], gain[:, None] * np.exp(-2j * np.pi * np.asarray(f)[None, :] * tau[:, None]), Q[j, :])
+
+    inner = [m.node() for _ in range(n_block)]
+    for k in range(n_block):
+        rows = chain_rows[k]
+        nodes = [m.node() for _ in range(rows)] + [inner[k]]          # far end ... block node
+        if port_on[k] is not None:
+            m.new_port(float(rng.choice([25.0, 50.0, 75.0])), nodes[port_on[k]])
+        for t in range(rows):
+            kind = (k + t) % 3
+            if kind == 0:
+                m.inductor(nodes[t], nodes[t + 1], float(10 ** rng.uniform(-9.3, -8.5)))
+            elif kind == 1:
+                m.capacitor(nodes[t], nodes[t + 1], float(10 ** rng.uniform(-12.3, -11.5)))
+            else:
+                m.transmissionline(nodes[t], nodes[t + 1], float(rng.uniform(30, 90)), float(rng.uniform(2, 4)), float(rng.uniform(1e-3, 9e-3)))
+            m.capacitor(nodes[t], m.gnd, float(10 ** rng.uniform(-12.8, -12)))
+        if k % 2:
+            m.resistor(inner[k], m.gnd, float(rng.uniform(200, 2000)))
+    m.n_port_S(m.gnd, inner, [[S_of(i, j) for j in range(n_block)] for i in range(n_block)], 50.0)
+    return m, np.linspace(0.8e9, 6e9, nF)

@@ -157,3 +157,62 @@ def test_generated_source_compiles_for_sm100a(name, mode):
         else:
             os.environ["HVB_NVRTC_FLAGS"] = old
     assert "hvb_gen_kernel" in log and "registers" in log
+
+
+# ---------------------------------------------------------------------------------------------------
+# kernel E: hub netlists (one N-port S block + chains), heavi_b200/csrc/hvb_gen_hub.cpp
+# ---------------------------------------------------------------------------------------------------
+def hub_sim(m, f):
+    p = pl.compile_plan(m.stamp_table(), "auto")
+    consts, prefs, tables, samples = pl.resolve_run(p, np.asarray(f, dtype=np.float64))
+    gen = engine.codegen_source(p, prefs, 0)
+    assert gen["supported"] and gen["hub"], gen["reason"]
+    S, f32, status = host_sim.run(gen, p.P, f, consts, prefs, tables, samples, p)
+    return S, f32, status, gen
+
+
+def test_hub_kernel_config3_matches_reference_golden():
+    g = golden("c3_touchstone")
+    m = REG["c3_touchstone"]()
+    S, f32, status, gen = hub_sim(m, g["f"])
+    assert status == 0 and gen["smem_bytes"] == 8 * 16 * 32 * 16 and gen["threads"] == 32
+    assert np.array_equal(f32, g["f32"])
+    frac, adjudicated, ext = parity_report(S[0], g["S"], g["S_ext"])
+    assert frac == 1.0 and adjudicated and ext < 5e-14
+
+
+@pytest.mark.parametrize("n_block,chain_rows,port_on", [
+    (4, (2, 1, 0, 3), (0, 0, None, 1)),            # chains of every length, a port in the middle of a chain, a bare node
+    (2, (1, 1), (0, 0)),
+    (3, (0, 2, 0), (0, 1, 0)),                     # ports directly on block nodes
+    (8, (1,) * 8, (0,) * 8),
+    (5, (4, 0, 2, 0, 1), (2, None, 0, 0, None)),   # stubs without ports
+])
+def test_hub_kernel_structures_against_oracle(n_block, chain_rows, port_on):
+    m, f = circuits.build_hub(hv, n_block, chain_rows, port_on, seed=n_block)
+    S, _, status, gen = hub_sim(m, f)
+    assert status == 0
+    assert np.max(np.abs(S[0] - oracle_S(m, f))) < 2e-13
+
+
+def test_hub_kernel_flags_an_unsafe_boundary_pivot_and_refuses_other_structures():
+    # a chain whose last row is an (almost) ideal series resonator next to the block node: the restricted pivot is
+    # unsafe there, which must raise the zero-pivot bit (the host then re-runs on the dense kernel)
+    m = hv.Model(suppress_loadbar=True)
+    b, c, mid = m.node(), m.node(), m.node()
+    m.new_port(50.0, b)
+    m.new_port(50.0, c)
+    C2, f0 = 2e-12, 1e9
+    m.capacitor(mid, b, C2)                           # stub on block node b: series C into a node ...
+    m.inductor(mid, m.gnd, 1.0 / ((2 * np.pi * f0) ** 2 * C2))   # ... whose only other part resonates with it at f0
+    m.n_port_S(m.gnd, [b, c], [[lambda f: 0.1 + 0 * f, lambda f: 0.7 + 0 * f], [lambda f: 0.7 + 0 * f, lambda f: 0.2 + 0 * f]], 50.0)
+    S, _, status, _ = hub_sim(m, np.array([f0, 1.7e9]))
+    assert status & engine.HVB_STATUS_ZERO_PIVOT
+    S2, _, status2, _ = hub_sim(m, np.array([1.3e9, 1.7e9]))
+    assert status2 == 0 and np.max(np.abs(S2[0] - oracle_S(m, np.array([1.3e9, 1.7e9])))) < 1e-13
+    # two blocks, or a mesh around the block: not a hub
+    m2, _ = circuits.build_hub(hv, 3, (1, 1, 1), (0, 0, 0))
+    nodes = [n for n in m2._nodes][-2:]
+    m2.resistor(m2._nodes[4], m2._nodes[6], 30.0)     # ties two chains together
+    gen = engine.codegen_source(pl.compile_plan(m2.stamp_table(), "auto"))
+    assert not gen["supported"] and "hub kernel" in gen["reason"]

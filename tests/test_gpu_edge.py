@@ -324,3 +324,26 @@ def test_resident_results_match_the_host_path():
     m0.inductor(a, b, 1e-9)
     with pytest.raises(np.linalg.LinAlgError):
         m0.run_sp_resident(np.array([0.0, 1e9]))
+
+
+def test_line_length_follows_its_parameter():
+    """The reference reads `self.length.value` inside every run_sp (base/tl.py:52): a swept / drawn /
+    optimised line length must change S from run to run and from sample to sample."""
+    m = hv.Model(suppress_loadbar=True)
+    sweep = hv.ParameterSweep()
+    Ln = sweep.lin(0.004, 0.031).add(5)
+    Ln.initialize()
+    a, b = m.quick_port(50), m.quick_port(50)
+    mid = m.node()
+    m.transmissionline(a, mid, 63.0, 2.9, Ln)
+    m.capacitor(mid, m.gnd, 0.7e-12)
+    m.inductor(mid, b, 1.5e-9)
+    f = np.linspace(0.8e9, 5e9, 64)
+    nd = m.run_sweep(f, sweep)
+    assert nd._sdata.shape == (5, 2, 2, 64)
+    for k, v in enumerate(Ln._values):
+        Ln._value = v
+        ref = oracle_S(m, f)
+        assert np.max(np.abs(nd._sdata[k] - ref)) < TOL
+        assert np.max(np.abs(m.run_sp(f)._S - ref)) < TOL          # the serial loop sees the new length too
+    assert np.max(np.abs(nd._sdata[0] - nd._sdata[4])) > 1e-3
