@@ -511,32 +511,49 @@ int hvb_gen_hub_source(const GenPlan& g, const int32_t* prefs, const char* prelu
            "template <int NR, int NB, int LD>\n"
            "__device__ __forceinline__ void gen_dense_lu(cplx* __restrict__ t, double& pmin, double& pmax) {\n"
            "#define TE(i, c) t[((i) * LD + (c)) * GEN_THREADS]\n"
+           "    // every loop has compile-time bounds and is unrolled: tile addresses are immediates except for the pivot row p\n"
+           "#pragma unroll\n"
            "    for (int k = 0; k < NR; ++k) {\n"
            "        int p = k;\n"
            "        double best = fabs(TE(k, k).x) + fabs(TE(k, k).y);\n"
            "        if (!(best >= 0.0)) best = -1.0;\n"
+           "#pragma unroll\n"
            "        for (int i = k + 1; i < NR; ++i) {\n"
            "            const cplx v = TE(i, k);\n"
            "            const double m = fabs(v.x) + fabs(v.y);\n"
            "            if (m > best) { best = m; p = i; }\n"
            "        }\n"
            "        pmin = fmin(pmin, best); pmax = fmax(pmax, best);\n"
-           "        if (p != k)\n"
+           "        if (p != k) {\n"
+           "#pragma unroll\n"
            "            for (int c = k; c < NR + NB; ++c) { const cplx a = TE(k, c); TE(k, c) = TE(p, c); TE(p, c) = a; }\n"
+           "        }\n"
            "        const cplx inv = crecip_fast(TE(k, k));\n"
            "        TE(k, k) = inv;\n"
-           "        for (int i = k + 1; i < NR; ++i) {\n"
-           "            const cplx m = cmul(TE(i, k), inv);\n"
-           "#pragma unroll 4\n"
-           "            for (int c = k + 1; c < NR + NB; ++c) { cplx v = TE(i, c); cfnma(v, m, TE(k, c)); TE(i, c) = v; }\n"
+           "        cplx pr[NR + NB];                                  // the pivot row stays in registers for this step\n"
+           "#pragma unroll\n"
+           "        for (int c = k + 1; c < NR + NB; ++c) pr[c] = TE(k, c);\n"
+           "#pragma unroll 1\n"
+           "        for (int i = k + 1; i < NR; ++i) {                 // rows stay a loop: bounded register use\n"
+           "            cplx* __restrict__ rowp = t + i * (LD * GEN_THREADS);\n"
+           "            const cplx m = cmul(rowp[k * GEN_THREADS], inv);\n"
+           "#pragma unroll\n"
+           "            for (int c = k + 1; c < NR + NB; ++c) { cplx v = rowp[c * GEN_THREADS]; cfnma(v, m, pr[c]); rowp[c * GEN_THREADS] = v; }\n"
            "        }\n"
            "    }\n"
+           "#pragma unroll\n"
            "    for (int k = NR - 1; k >= 0; --k) {\n"
            "        const cplx inv = TE(k, k);\n"
+           "        cplx ur[NR];\n"
+           "#pragma unroll\n"
+           "        for (int j = k + 1; j < NR; ++j) ur[j] = TE(k, j);\n"
+           "#pragma unroll 1\n"
            "        for (int c = NR; c < NR + NB; ++c) {\n"
-           "            cplx v = TE(k, c);\n"
-           "            for (int j = k + 1; j < NR; ++j) cfnma(v, TE(k, j), TE(j, c));\n"
-           "            TE(k, c) = cmul(v, inv);\n"
+           "            cplx* __restrict__ colp = t + c * GEN_THREADS;\n"
+           "            cplx v = colp[k * (LD * GEN_THREADS)];\n"
+           "#pragma unroll\n"
+           "            for (int j = k + 1; j < NR; ++j) cfnma(v, ur[j], colp[j * (LD * GEN_THREADS)]);\n"
+           "            colp[k * (LD * GEN_THREADS)] = cmul(v, inv);\n"
            "        }\n"
            "    }\n"
            "#undef TE\n}\n\n";

@@ -306,7 +306,7 @@ def test_population_objective_with_a_callable_that_reads_an_optimiser_variable()
         m.inductor(a, x, L1)
         m.impedance(x, b, lambda fr: 2.0 + 1j * 2 * np.pi * fr * L1._value * 0.1)      # reads the variable
         m.capacitor(x, m.gnd, 1e-12)
-        opt.add_splimit(1e9, 2e9, 21, (2, 1), lower_limit=optim.dBabove(-1))
+        opt.add_splimit(1e9, 2e9, 21, (2, 1), upper_limit=optim.dBbelow(-30))       # always violated: a cost per candidate
         return m, opt
 
     X = np.array([[-9.2, -8.8, -8.5, -8.1]])
