@@ -307,6 +307,9 @@ class Measurement:
     def e2e_once(self):
         """One pass of the whole job through the public API; returns the results rank 0 holds."""
         from heavi_b200 import sharding
+        if self.world == 1 and len(self.jobs_whole) > 1 and all(j[3] is None for j in self.jobs_whole):
+            # several independent sweeps (configs[1]'s filter set): queued together, collected together
+            return [S._S[None] for S in self.hv.run_sp_many([(j[0], j[1]) for j in self.jobs_whole])]
         out = []
         for (m, f, drivers, values) in self.jobs_whole:
             if self.world > 1:
@@ -338,7 +341,8 @@ class Measurement:
         h2d = sum(j[1].nbytes + (0 if j[3] is None else j[3].nbytes) for j in self.jobs_whole)
         d2h = sum(job_points(j) * st["plan"].P ** 2 * 16 for j, st in zip(self.jobs_whole, self.state))
         api = ("sharding.run_sp_distributed(model, f) -> S on rank 0 (one page-locked shared array, each GPU copies its block)"
-               if self.world > 1 else "Model.run_sp(f) / run_sp_batch -> Sparameters (pinned host result)")
+               if self.world > 1 else ("heavi_b200.run_sp_many([(model, f), ...]) -> [Sparameters] (sweeps queued together, pinned host results)"
+                                       if len(self.jobs_whole) > 1 else "Model.run_sp(f) / run_sp_batch -> Sparameters (pinned host result)"))
         return dict(value=self.points_whole * steps / dt, unit=UNIT, h2d_bytes_per_step=int(h2d), d2h_bytes_per_step=int(d2h),
                     steps=steps, ms_per_step=dt / steps * 1e3, api=api), res
 

@@ -10,11 +10,11 @@ from . import lib  # noqa: F401
 from .filters import BandType, CauerType, Filtering, FilterType
 from .lib.touchstone import FileBasedNPort
 from .model import Model
-from .netlist import Network, Node
+from .netlist import Network, Node, run_sp_many
 from .params import Function, MonteCarlo, Param, ParameterSweep, set_print_frequency
 from .results import DeviceStatSparameters, NDSparameters, Sparameters, StatSparam, StatSparameters, frange
 
 PI = 3.141592653589793
 __all__ = ["Model", "Network", "Node", "frange", "Sparameters", "NDSparameters", "StatSparam", "StatSparameters",
            "FilterType", "BandType", "CauerType", "Filtering", "MonteCarlo", "Param", "Function", "ParameterSweep",
-           "set_print_frequency", "FileBasedNPort", "lib", "PI"]
+           "set_print_frequency", "FileBasedNPort", "lib", "PI", "run_sp_many"]

@@ -101,6 +101,7 @@ struct hvb_plan {
     int max_grid = 0;
     int64_t launches = 0;
     // kernel D (generated): host copy of the plan the generator reads, compiled variants, the active one
+    bool pending = false;                              // hvb_run_host_async queued, not yet waited for
     std::vector<char> pushed;                          // consts + prefs as last uploaded by push_params
     bool pushed_valid = false;
     cudaStream_t pushed_stream = nullptr;
@@ -737,7 +738,50 @@ extern "C" int hvb_run_device(hvb_plan* pl, const hvb_run_args* a, double* d_S, 
     return launch(pl, D, st);
 }
 
+static int run_host_impl(hvb_plan* pl, const hvb_run_args* a, double* S_out, int32_t* status_out, bool wait);
+
+static void drain_after_error(hvb_plan* pl) {
+    // an error path may leave kernels and copies of earlier tiles in flight: they read the pinned staging
+    // block and write the caller's S_out, so wait for both pipeline streams before handing control back
+    const std::string keep = g_err;
+    cudaSetDevice(pl->device);
+    cudaStreamSynchronize(pl->streams[0]);
+    cudaStreamSynchronize(pl->streams[1]);
+    cudaGetLastError();
+    g_err = keep;
+}
+
+// Non-blocking form: everything is queued on the plan's streams and the call returns; hvb_run_host_wait blocks
+// until S_out (and f32_out) are complete.  Several plans -- e.g. the three filters of BASELINE configs[1] -- can
+// have a run in flight each, so their copies share the PCIe link back to back instead of each call's fixed
+// costs (host marshalling, first kernel, last copy) adding up.  Inputs are staged during the call; S_out,
+// f32_out and a page-locked `tables` array must stay alive until the wait.
+extern "C" int hvb_run_host_async(hvb_plan* pl, const hvb_run_args* a, double* S_out) {
+    if (pl && pl->pending) return fail(HVB_ERR_ARG, "a run is already in flight on this plan (hvb_run_host_wait first)");
+    const int rc = run_host_impl(pl, a, S_out, nullptr, false);
+    if (rc != HVB_OK && pl && pl->streams[0]) drain_after_error(pl);
+    if (rc == HVB_OK && pl) pl->pending = true;
+    return rc;
+}
+
+extern "C" int hvb_run_host_wait(hvb_plan* pl, int32_t* status_out) {
+    if (!pl) return fail(HVB_ERR_ARG, "null argument");
+    if (!pl->pending) { if (status_out) *status_out = 0; return HVB_OK; }
+    pl->pending = false;
+    CU(cudaSetDevice(pl->device));
+    CU(cudaStreamSynchronize(pl->streams[0]));
+    if (status_out) *status_out = *pl->h_status;
+    return HVB_OK;
+}
+
 extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, int32_t* status_out) {
+    if (pl && pl->pending) return fail(HVB_ERR_ARG, "a run is already in flight on this plan (hvb_run_host_wait first)");
+    const int rc = run_host_impl(pl, a, S_out, status_out, true);
+    if (rc != HVB_OK && pl && pl->streams[0]) drain_after_error(pl);
+    return rc;
+}
+
+static int run_host_impl(hvb_plan* pl, const hvb_run_args* a, double* S_out, int32_t* status_out, bool wait) {
     int rc = check_args(pl, a);
     if (rc) return rc;
     if (!S_out) return fail(HVB_ERR_ARG, "S_out is NULL");
@@ -847,7 +891,7 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
             // the points of sample 0 also round their frequency to float32 (`Sparameters.f`, network.py:407,421)
             D.f32 = (a->f32_out && sb == 0) ? (float*)pl->f32.p + fb : nullptr;
             rc = launch(pl, D, st, tile & 1);
-            if (rc) { cudaStreamSynchronize(s0); cudaStreamSynchronize(s1); return rc; }   // nothing in flight touches the caller's buffers after an error
+            if (rc) return rc;
             // rows of nf elements, one per (sample, j, i); destination pitch is the caller's (default: the full nF)
             char* dst = (char*)S_out + ((size_t)sb * PP * ldo + (size_t)fb) * 16;
             // contiguous destination -> one plain copy; otherwise one strided 2-D copy
@@ -871,6 +915,7 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     if (a->f32_out) CU(cudaMemcpyAsync(a->f32_out, pl->f32.p, (size_t)nF * 4, cudaMemcpyDeviceToHost, s0));   // one copy for the whole axis
     mark();
     mark();
+    if (!wait) return HVB_OK;                              // hvb_run_host_async: the caller collects with hvb_run_host_wait
     CU(cudaStreamSynchronize(s0));
     mark();
     if (trace) {

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(HVB_BAND_THREADS) hvb_band_kernel(const HvbDev
                 int col = bc < LDA ? r - B + bc : n + bc - LDA;
                 if (bc < LDA && col >= n) col = -2;            // band slot beyond the last column, not an RHS column
                 cplx acc = cmk(0.0, 0.0);
-                while (ecol == col) {
+                while (e < hi && ecol == col) {                // e < hi: `col` can itself be -1 left of the band's first column
                     const int word = __ldg(D.row_ent + e);
                     const int vid = (word >> 1) & 0x7FFFF;
                     const cplx v = vid < D.nvc ? D.const_vals[vid] : Vt[(long long)(vid - D.nvc) * T];

@@ -58,7 +58,8 @@ class CodegenInfo(C.Structure):
 EXPORTS = ("hvb_warp_shape", "hvb_plan_create", "hvb_plan_destroy", "hvb_run_host", "hvb_run_device",
            "hvb_run_stats_host", "hvb_assemble_host",
            "hvb_plan_kernel_info", "hvb_measure_dfma_peak", "hvb_last_error", "hvb_version",
-           "hvb_codegen_source", "hvb_codegen_compile", "hvb_plan_set_tunable", "hvb_run_host_multi")
+           "hvb_codegen_source", "hvb_codegen_compile", "hvb_plan_set_tunable", "hvb_run_host_multi",
+           "hvb_run_host_async", "hvb_run_host_wait")
 
 _lib = None
 
@@ -81,6 +82,10 @@ def load_library():
     lib.hvb_plan_destroy.restype = None
     lib.hvb_run_host.argtypes = [C.c_void_p, C.POINTER(RunArgs), C.c_void_p, _i32p]
     lib.hvb_run_host.restype = C.c_int
+    lib.hvb_run_host_async.argtypes = [C.c_void_p, C.POINTER(RunArgs), C.c_void_p]
+    lib.hvb_run_host_async.restype = C.c_int
+    lib.hvb_run_host_wait.argtypes = [C.c_void_p, _i32p]
+    lib.hvb_run_host_wait.restype = C.c_int
     lib.hvb_run_host_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(RunArgs), C.c_void_p, _i32p]
     lib.hvb_run_host_multi.restype = C.c_int
     lib.hvb_run_stats_host.argtypes = [C.c_void_p, C.POINTER(RunArgs), C.c_void_p, _i32p]
@@ -319,6 +324,29 @@ class DevicePlanHandle:
             _check(self.lib.hvb_run_host(self.handle, C.byref(a), dst, C.byref(status)))
         return out, status.value
 
+    def run_host_async(self, f, consts, prefs, tables, samples, out: np.ndarray | None = None, f32_out: np.ndarray | None = None):
+        """Queue one run on this plan's streams and return at once (`hvb_run_host_async`); `wait()` completes it.
+        Returns the output array (valid after `wait`)."""
+        p = self.plan
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        nF, nS = f.shape[0], samples.shape[0]
+        if out is None:
+            out = pinned_empty((nS, p.P, p.P, nF))
+        tables = np.ascontiguousarray(tables, dtype=np.complex128)
+        samples = np.ascontiguousarray(samples, dtype=np.float64)
+        a = self._args(consts, prefs, _ptr(f), nF, _ptr(samples), nS, _ptr(tables), tables.shape[0])
+        if f32_out is not None:
+            a.f32_out = _ptr(f32_out)
+        self._pending_keep = (f, tables, samples, out, f32_out, a)       # alive until wait()
+        _check(self.lib.hvb_run_host_async(self.handle, C.byref(a), C.c_void_p(out.__array_interface__["data"][0])))
+        return out
+
+    def wait(self) -> int:
+        status = C.c_int32(0)
+        _check(self.lib.hvb_run_host_wait(self.handle, C.byref(status)))
+        self._pending_keep = None
+        return status.value
+
     def run_stats_host(self, f, consts, prefs, tables, samples):
         """Monte-Carlo moments reduced on the device: float64 [6, P, P, nF]."""
         p = self.plan
@@ -400,6 +428,24 @@ class _DriversSet:
             else:
                 d._value = v
         return False
+
+
+class PendingRun:
+    """A queued `CompiledNetwork.run_async`; `result()` waits and returns S[nS,P,P,nF] (same checks as `run`)."""
+
+    def __init__(self, cn, handle, S, done, call):
+        self._cn, self._handle, self._S, self._done, self._call = cn, handle, S, done, call
+
+    def result(self) -> np.ndarray:
+        if self._done is None:
+            status = self._handle.wait()
+            if self._cn._hub and (status & HVB_STATUS_ZERO_PIVOT):
+                f, drivers, values, f32_out = self._call
+                self._done = self._cn.dense_fallback().run(f, drivers, values, f32_out=f32_out)
+            else:
+                self._cn._raise_for_status(status)
+                self._done = self._S
+        return self._done
 
 
 class CompiledNetwork:
@@ -571,6 +617,17 @@ class CompiledNetwork:
             warnings.warn("singular MNA system at one or more points: the reference returns the SVD "
                           "minimum-norm solution there, the LU solver cannot", RuntimeWarning)
         return S
+
+    def run_async(self, f: np.ndarray, drivers=None, values=None, f32_out=None):
+        """`run` without the wait: returns a `PendingRun`; several compiled networks can have one in flight each
+        (their kernels and copies share the GPU and the PCIe link back to back)."""
+        if drivers is not None and self._tables_follow_drivers(f, drivers, values):
+            return PendingRun(self, None, None, self.run(f, drivers, values, f32_out=f32_out), (f, drivers, values, f32_out))
+        points = len(f) * (1 if values is None else len(values))
+        plan, handle = self.variant(points)
+        consts, prefs, tables, samples = self.resolve(f, drivers, values, plan)
+        S = handle.run_host_async(f, consts, prefs, tables, samples, f32_out=f32_out)
+        return PendingRun(self, handle, S, None, (f, drivers, values, f32_out))
 
     def run_resident(self, f, drivers=None, values=None, out=None, check: bool = True):
         """Like `run`, but the result stays in HBM: returns a torch CUDA tensor S[nS,P,P,nF] (complex128).

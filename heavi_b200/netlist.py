@@ -228,6 +228,20 @@ class Network:
             self._initialized = False
         return Sparameters(S[0], f32)
 
+    def run_sp_async(self, frequencies: np.ndarray):
+        """`run_sp` that returns at once: the sweep is queued on the GPU and `.result()` of the returned object
+        gives the `Sparameters`.  Independent models overlap -- `run_sp_many` is the convenience form."""
+        compiled = self._compiled()
+        f64 = np.ascontiguousarray(frequencies, dtype=np.float64)
+        from .engine import pinned_empty
+        f32 = pinned_empty(f64.shape, np.float32)
+        pending = compiled.run_async(f64, f32_out=f32)
+
+        class _Pending:
+            def result(_self) -> Sparameters:
+                return Sparameters(pending.result()[0], f32)
+        return _Pending()
+
     def run_sp_batch(self, frequencies: np.ndarray, drivers, values: np.ndarray) -> np.ndarray:
         """Batched Monte-Carlo / sweep evaluation: `values[s, k]` is the value of `drivers[k]`
         (Random / Param objects) in sample s.  Returns S[nS,P,P,nF]; every (sample, frequency)
@@ -346,3 +360,11 @@ class Network:
         raise NotImplementedError("diodes belong to the DC/transient analyses, outside this package's scope")
 
     DC_source = TRANSIENT_source = diode
+
+
+def run_sp_many(jobs) -> list:
+    """[(network, frequencies), ...] -> [Sparameters, ...]: every sweep is queued before the first result is
+    awaited, so independent models (a filter set, the candidates of a design study) share the GPU and the PCIe
+    link back to back instead of paying each call's fixed costs one after the other."""
+    pending = [net.run_sp_async(f) for net, f in jobs]
+    return [p.result() for p in pending]

@@ -137,6 +137,14 @@ int hvb_plan_set_tunable(hvb_plan* plan, const char* name, double value);
  * Replaces: the whole body of Network.run_sp after index allocation (network.py:380-416). */
 int hvb_run_host(hvb_plan* plan, const hvb_run_args* args, double* S_out, int32_t* status_out);
 
+/* Non-blocking pair: hvb_run_host_async queues uploads, kernels and copies on the plan's streams and returns;
+ * hvb_run_host_wait blocks until S_out / f32_out are complete and returns the status word.  One run in flight
+ * per plan; distinct plans (the three filters of BASELINE configs[1], the models of an optimiser's inner loop)
+ * overlap.  f / samples / consts / prefs are staged during the call; S_out, f32_out and `tables` must stay
+ * alive until the wait.  Replaces several serial Network.run_sp calls (network.py:354-421). */
+int hvb_run_host_async(hvb_plan* plan, const hvb_run_args* args, double* S_out);
+int hvb_run_host_wait(hvb_plan* plan, int32_t* status_out);
+
 /* The same call spread over several devices of one process: `plans[k]` are replicas of one netlist's plan
  * created on different devices (hvb_plan_create with the same descriptor).  Points are independent, so the
  * job is cut into contiguous blocks -- whole samples when nS >= nplans, else frequency slabs -- one block
@@ -146,6 +154,9 @@ int hvb_run_host(hvb_plan* plan, const hvb_run_args* args, double* S_out, int32_
 int hvb_run_host_multi(hvb_plan* const* plans, int32_t nplans, const hvb_run_args* args, double* S_out, int32_t* status_out);
 
 /* Same computation with DEVICE buffers owned by the caller (e.g. torch tensors' data_ptr()):
+ * ONE caller and ONE stream at a time per plan: the plan owns the device copy of consts / prefs and the
+ * workspaces of the banded / block kernels, so a second call on another stream or thread must wait for the
+ * first one's kernel (use distinct plans for concurrent work -- they are independent).
  * `args->f`, `args->samples`, `args->tables` and `d_S_out` are device pointers; consts/prefs stay
  * host pointers.  Work is enqueued on `stream` (a cudaStream_t, NULL = legacy default stream) and
  * the call returns without synchronising.  `d_status` (optional) is a device int32.

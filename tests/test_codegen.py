@@ -130,10 +130,13 @@ def test_singular_and_nonfinite_points_set_status_bits():
 
 
 def test_unsupported_structures_are_refused_with_a_reason():
-    m, f = circuits.build_c3(hv, nF=8)                          # 8-port block: not a chain
+    m, f = circuits.build_c3(hv, nF=8)                          # 8-port block: not a chain, but a hub (kernel E)
     p = pl.compile_plan(m.stamp_table(), "auto")
-    gen = engine.codegen_source(p)
-    assert not gen["supported"] and gen["reason"]
+    gen = engine.codegen_source(p, pl.resolve_run(p, f)[1])
+    assert gen["supported"] and gen["hub"]
+    mb, _ = circuits.build_c2(hv, "bandstop", 8)                # shunt series-LC branches: a tree, neither chain nor hub
+    genb = engine.codegen_source(pl.compile_plan(mb.stamp_table(), "auto", order="natural"))
+    assert not genb["supported"] and genb["reason"]
     m2, _ = circuits.build_band_ladder(hv, K=40, reach=2, nports=2)  # pentadiagonal
     gen2 = engine.codegen_source(pl.compile_plan(m2.stamp_table(), "auto", order="rcm"))
     assert not gen2["supported"] and "tridiagonal" in gen2["reason"]

@@ -347,3 +347,20 @@ def test_line_length_follows_its_parameter():
         assert np.max(np.abs(nd._sdata[k] - ref)) < TOL
         assert np.max(np.abs(m.run_sp(f)._S - ref)) < TOL          # the serial loop sees the new length too
     assert np.max(np.abs(nd._sdata[0] - nd._sdata[4])) > 1e-3
+
+
+def test_run_sp_many_overlaps_independent_models_and_equals_serial_calls():
+    import circuits
+    jobs = [(circuits.build_c2(hv, band, nF=8)[0], np.linspace(2e9, 3e9, 30_001)) for band in ("bandpass", "lowpass", "highpass")]
+    jobs.append((circuits.build_c1(hv, nF=8)[0], np.linspace(1.8e9, 2.2e9, 2001)))
+    many = hv.run_sp_many(jobs)
+    for (m, f), S in zip(jobs, many):
+        serial = m.run_sp(f)
+        assert np.array_equal(S._S, serial._S) and np.array_equal(S.f, serial.f) and S.f.dtype == np.float32
+    # one run in flight per plan
+    m, f = jobs[0]
+    p = m.run_sp_async(f)
+    with pytest.raises(ValueError):
+        m.run_sp(f)
+    assert np.array_equal(p.result()._S, many[0]._S)
+    assert np.array_equal(m.run_sp(f)._S, many[0]._S)
