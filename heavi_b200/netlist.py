@@ -235,12 +235,7 @@ class Network:
         f64 = np.ascontiguousarray(frequencies, dtype=np.float64)
         from .engine import pinned_empty
         f32 = pinned_empty(f64.shape, np.float32)
-        pending = compiled.run_async(f64, f32_out=f32)
-
-        class _Pending:
-            def result(_self) -> Sparameters:
-                return Sparameters(pending.result()[0], f32)
-        return _Pending()
+        return PendingSparameters(compiled.run_async(f64, f32_out=f32), f32)
 
     def run_sp_batch(self, frequencies: np.ndarray, drivers, values: np.ndarray) -> np.ndarray:
         """Batched Monte-Carlo / sweep evaluation: `values[s, k]` is the value of `drivers[k]`
@@ -360,6 +355,18 @@ class Network:
         raise NotImplementedError("diodes belong to the DC/transient analyses, outside this package's scope")
 
     DC_source = TRANSIENT_source = diode
+
+
+class PendingSparameters:
+    """What `Network.run_sp_async` returns: `.result()` waits for the sweep and wraps it like `run_sp` does."""
+
+    __slots__ = ("_pending", "_f32")
+
+    def __init__(self, pending, f32):
+        self._pending, self._f32 = pending, f32
+
+    def result(self) -> Sparameters:
+        return Sparameters(self._pending.result()[0], self._f32)
 
 
 def run_sp_many(jobs) -> list:
