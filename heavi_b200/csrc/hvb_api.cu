@@ -17,6 +17,7 @@
 #include "hvb_device.cuh"
 #include "hvb_gen.h"
 #include "hvb_jit.h"
+#include "hvb_stamps.h"
 #include "hvb_kernels.h"
 #include "hvb_warp_shapes.h"
 
@@ -101,6 +102,8 @@ struct hvb_plan {
     int max_grid = 0;
     int64_t launches = 0;
     // kernel D (generated): host copy of the plan the generator reads, compiled variants, the active one
+    std::vector<double> def_consts;                    // plans created from a stamp table: the run parameters it implies
+    std::vector<int32_t> def_prefs;
     bool pending = false;                              // hvb_run_host_async queued, not yet waited for
     bool staged_valid = false;                         // h_in / inbuf hold the inputs of the last hvb_run_host call
     size_t staged_bytes = 0;
@@ -717,6 +720,14 @@ static int launch(hvb_plan* pl, HvbDev& D, cudaStream_t st, int slot = 0) {
     return HVB_OK;
 }
 
+// plans created from a stamp table carry their own consts / prefs: NULL in the run arguments means "those"
+static hvb_run_args effective_args(const hvb_plan* pl, const hvb_run_args* a) {
+    hvb_run_args b = *a;
+    if (!b.consts && !pl->def_consts.empty()) b.consts = pl->def_consts.data();
+    if (!b.prefs && !pl->def_prefs.empty()) b.prefs = pl->def_prefs.data();
+    return b;
+}
+
 static int check_args(const hvb_plan* pl, const hvb_run_args* a) {
     if (!pl || !a) return fail(HVB_ERR_ARG, "null argument");
     if (a->nF < 0 || a->nS < 1) return fail(HVB_ERR_ARG, "bad nF=%lld nS=%lld", (long long)a->nF, (long long)a->nS);
@@ -725,7 +736,10 @@ static int check_args(const hvb_plan* pl, const hvb_run_args* a) {
     return HVB_OK;
 }
 
-extern "C" int hvb_run_device(hvb_plan* pl, const hvb_run_args* a, double* d_S, int64_t ldS, int32_t* d_status, void* stream) {
+extern "C" int hvb_run_device(hvb_plan* pl, const hvb_run_args* a_in, double* d_S, int64_t ldS, int32_t* d_status, void* stream) {
+    if (!pl || !a_in) return fail(HVB_ERR_ARG, "null argument");
+    const hvb_run_args a_eff = effective_args(pl, a_in);
+    const hvb_run_args* a = &a_eff;
     int rc = check_args(pl, a);
     if (rc) return rc;
     if (pl->d.ncols <= pl->d.n || (!pl->kernel && pl->kclass != 3)) return fail(HVB_ERR_ARG, "plan has no right-hand sides (dump plan)");
@@ -784,7 +798,10 @@ extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, 
     return rc;
 }
 
-static int run_host_impl(hvb_plan* pl, const hvb_run_args* a, double* S_out, int32_t* status_out, bool wait) {
+static int run_host_impl(hvb_plan* pl, const hvb_run_args* a_in, double* S_out, int32_t* status_out, bool wait) {
+    if (!pl || !a_in) return fail(HVB_ERR_ARG, "null argument");
+    const hvb_run_args a_eff = effective_args(pl, a_in);
+    const hvb_run_args* a = &a_eff;
     int rc = check_args(pl, a);
     if (rc) return rc;
     if (!S_out) return fail(HVB_ERR_ARG, "S_out is NULL");
@@ -1007,7 +1024,10 @@ extern "C" int hvb_run_host_multi(hvb_plan* const* plans, int32_t nplans, const 
     return HVB_OK;
 }
 
-extern "C" int hvb_run_stats_host(hvb_plan* pl, const hvb_run_args* a, double* stats_out, int32_t* status_out) {
+extern "C" int hvb_run_stats_host(hvb_plan* pl, const hvb_run_args* a_in, double* stats_out, int32_t* status_out) {
+    if (!pl || !a_in) return fail(HVB_ERR_ARG, "null argument");
+    const hvb_run_args a_eff = effective_args(pl, a_in);
+    const hvb_run_args* a = &a_eff;
     int rc = check_args(pl, a);
     if (rc) return rc;
     if (!stats_out) return fail(HVB_ERR_ARG, "stats_out is NULL");
@@ -1067,7 +1087,10 @@ extern "C" int hvb_run_stats_host(hvb_plan* pl, const hvb_run_args* a, double* s
     return HVB_OK;
 }
 
-extern "C" int hvb_assemble_host(hvb_plan* pl, const hvb_run_args* a, double* W_out) {
+extern "C" int hvb_assemble_host(hvb_plan* pl, const hvb_run_args* a_in, double* W_out) {
+    if (!pl || !a_in) return fail(HVB_ERR_ARG, "null argument");
+    const hvb_run_args a_eff = effective_args(pl, a_in);
+    const hvb_run_args* a = &a_eff;
     int rc = check_args(pl, a);
     if (rc) return rc;
     if (!W_out) return fail(HVB_ERR_ARG, "W_out is NULL");
@@ -1108,6 +1131,75 @@ extern "C" int hvb_assemble_host(hvb_plan* pl, const hvb_run_args* a, double* W_
     CU(cudaMemcpyAsync(W_out, pl->dump.p, bytes, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return HVB_OK;
+}
+
+// ---- stamp table -> plan, below the ABI (hvb_stamps.cpp) ---------------------------------------------------------------
+struct hvb_compiled { StampPlan sp; };
+
+extern "C" int hvb_stamps_compile_host(const hvb_stamp_table* t, int32_t mode, int32_t pad_rows, int32_t pad_rhs, int32_t order,
+                                       hvb_compiled** out, hvb_plan_desc* desc_out, const double** consts_out, const int32_t** prefs_out,
+                                       int32_t info_out[8], const int32_t** table_prefs_out, const int32_t** table_slots_out) {
+    if (!t || !out) return fail(HVB_ERR_ARG, "null argument");
+    std::unique_ptr<hvb_compiled> c(new hvb_compiled());
+    std::string err;
+    if (hvb_stamps_compile(t, mode, pad_rows, pad_rhs, order, &c->sp, &err) != 0) return fail(HVB_ERR_ARG, "stamp table: %s", err.c_str());
+    if (desc_out) c->sp.fill_desc(*t, desc_out, 0);
+    if (consts_out) *consts_out = c->sp.consts.data();
+    if (prefs_out) *prefs_out = c->sp.prefs.data();
+    if (info_out) {
+        const int32_t info[8] = {c->sp.mode, c->sp.n_real, c->sp.band, c->sp.max_nport, c->sp.n_tables, c->sp.n_sample_cols,
+                                 (int32_t)c->sp.table_pref.size(), 0};
+        memcpy(info_out, info, sizeof(info));
+    }
+    if (table_prefs_out) *table_prefs_out = c->sp.table_pref.data();
+    if (table_slots_out) *table_slots_out = c->sp.table_slot.data();
+    *out = c.release();
+    return HVB_OK;
+}
+
+extern "C" void hvb_compiled_free(hvb_compiled* c) { delete c; }
+
+extern "C" int hvb_plan_create_from_stamps(const hvb_stamp_table* t, int32_t mode, int device, hvb_plan** out) {
+    if (!t || !out) return fail(HVB_ERR_ARG, "null argument");
+    std::string err;
+    auto create = [&](const StampPlan& sp, int hint, hvb_plan** pl) {
+        hvb_plan_desc d;
+        sp.fill_desc(*t, &d, hint);
+        const int rc = hvb_plan_create(&d, device, pl);
+        if (rc == HVB_OK) { (*pl)->def_consts = sp.consts; (*pl)->def_prefs = sp.prefs; }
+        return rc;
+    };
+    const char* nogen = getenv("HVB_NO_GEN");
+    const bool gen_on = !(nogen && nogen[0] == '1');
+    StampPlan sp;
+    // 1. a chain (tridiagonal after the bandwidth-reducing order) -> generated kernel D
+    if (gen_on && hvb_stamps_compile(t, mode, 0, 0, HVB_ORDER_RCM, &sp, &err) == 0 && sp.band == 1 && sp.epi_simple && sp.coops.empty()) {
+        hvb_plan* pl = nullptr;
+        if (create(sp, 2, &pl) == HVB_OK) {
+            if (pl->kclass == 3) { *out = pl; return HVB_OK; }
+            hvb_plan_destroy(pl);
+        }
+    }
+    // 2. the netlist's own row order: a hub -> generated kernel E; small -> register kernels in an instantiated shape
+    if (hvb_stamps_compile(t, mode, 0, 0, HVB_ORDER_NATURAL, &sp, &err) != 0) return fail(HVB_ERR_ARG, "stamp table: %s", err.c_str());
+    if (gen_on && sp.coops.size() == HVB_COOP_WORDS && sp.epi_simple && sp.P <= 8) {
+        hvb_plan* pl = nullptr;
+        if (create(sp, 2, &pl) == HVB_OK) {
+            if (pl->kclass == 3 && pl->gen_hub) { *out = pl; return HVB_OK; }
+            hvb_plan_destroy(pl);
+        }
+    }
+    int32_t n_pad = 0, p_pad = 0;
+    hvb_warp_shape(sp.n_real, sp.P, sp.max_nport, &n_pad, &p_pad);
+    if (n_pad > 0) {
+        StampPlan padded;
+        if (hvb_stamps_compile(t, sp.mode, n_pad, p_pad, HVB_ORDER_NATURAL, &padded, &err) != 0) return fail(HVB_ERR_ARG, "stamp table: %s", err.c_str());
+        return create(padded, 1, out);
+    }
+    // 3. large systems: banded kernel when the ordered matrix is narrow, dense block kernel otherwise
+    StampPlan big;
+    if (hvb_stamps_compile(t, sp.mode, 0, 0, HVB_ORDER_AUTO, &big, &err) != 0) return fail(HVB_ERR_ARG, "stamp table: %s", err.c_str());
+    return create(big, 0, out);
 }
 
 extern "C" int hvb_plan_kernel_info(hvb_plan* pl, hvb_kernel_info* out) {

@@ -59,7 +59,8 @@ EXPORTS = ("hvb_warp_shape", "hvb_plan_create", "hvb_plan_destroy", "hvb_run_hos
            "hvb_run_stats_host", "hvb_assemble_host",
            "hvb_plan_kernel_info", "hvb_measure_dfma_peak", "hvb_last_error", "hvb_version",
            "hvb_codegen_source", "hvb_codegen_compile", "hvb_plan_set_tunable", "hvb_run_host_multi",
-           "hvb_run_host_async", "hvb_run_host_wait")
+           "hvb_run_host_async", "hvb_run_host_wait", "hvb_plan_create_from_stamps", "hvb_stamps_compile_host",
+           "hvb_compiled_free")
 
 _lib = None
 
@@ -82,6 +83,13 @@ def load_library():
     lib.hvb_plan_destroy.restype = None
     lib.hvb_run_host.argtypes = [C.c_void_p, C.POINTER(RunArgs), C.c_void_p, _i32p]
     lib.hvb_run_host.restype = C.c_int
+    lib.hvb_plan_create_from_stamps.argtypes = [C.c_void_p, C.c_int32, C.c_int, C.POINTER(C.c_void_p)]
+    lib.hvb_plan_create_from_stamps.restype = C.c_int
+    lib.hvb_stamps_compile_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hvb_stamps_compile_host.restype = C.c_int
+    lib.hvb_compiled_free.argtypes = [C.c_void_p]
+    lib.hvb_compiled_free.restype = None
     lib.hvb_run_host_async.argtypes = [C.c_void_p, C.POINTER(RunArgs), C.c_void_p]
     lib.hvb_run_host_async.restype = C.c_int
     lib.hvb_run_host_wait.argtypes = [C.c_void_p, _i32p]
@@ -242,6 +250,152 @@ def codegen_source(plan: pl.DevicePlan, prefs: np.ndarray | None = None, mode: i
     out.update(src=src.value.decode(), rows=rows[:info.n_rows], itab=itab[:info.n_itab], dtab=dtab[:info.n_dtab],
                flops_per_solve=info.flops_per_solve, hub=bool(info.hub), threads=info.threads, smem_bytes=info.smem_bytes)
     return out
+
+
+class ParamC(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("index", C.c_int32), ("v", C.c_double * 4)]
+
+
+class StampTableC(C.Structure):
+    _fields_ = [("n_components", C.c_int32), ("comp_kind", _i32p), ("comp_port", _i32p), ("ids_off", _i32p), ("ids", _i32p),
+                ("par_off", _i32p), ("par", C.POINTER(ParamC)), ("P", C.c_int32), ("port_table", _i32p), ("port_src", _i32p),
+                ("N", C.c_int32), ("M", C.c_int32), ("n_traces", C.c_int32), ("n_knots", C.c_int32), ("n_coefs", C.c_int32),
+                ("spl_t", _f64p), ("spl_c", _f64p), ("spl_trace", _i32p), ("spl_fill", _f64p), ("spl_range", _f64p)]
+
+
+MODES = {"auto": 0, "full": 1, "norton": 2, "dump": 3}
+ORDERS = {"auto": 0, "natural": 1, "rcm": 2}
+
+
+def stamp_table_c(tagged: "pl.TaggedTable"):
+    """(StampTableC, keep-alive) for a `plan.TaggedTable`."""
+    keep = {}
+
+    def arr(name, a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        if a.size == 0:
+            a = np.zeros(1, dtype=dt)
+        keep[name] = a
+        return a
+
+    t = StampTableC()
+    t.n_components = len(tagged.comp_kind)
+    t.comp_kind = arr("ck", tagged.comp_kind, np.int32).ctypes.data_as(_i32p)
+    t.comp_port = arr("cp", tagged.comp_port, np.int32).ctypes.data_as(_i32p)
+    t.ids_off = arr("io", tagged.ids_off, np.int32).ctypes.data_as(_i32p)
+    t.ids = arr("ids", tagged.ids, np.int32).ctypes.data_as(_i32p)
+    t.par_off = arr("po", tagged.par_off, np.int32).ctypes.data_as(_i32p)
+    par = np.ascontiguousarray(tagged.par)
+    assert par.dtype.itemsize == C.sizeof(ParamC)
+    keep["par"] = par
+    t.par = C.cast(par.ctypes.data, C.POINTER(ParamC))
+    t.P = tagged.port_table.shape[0]
+    t.port_table = arr("pt", tagged.port_table, np.int32).ctypes.data_as(_i32p)
+    t.port_src = arr("ps", tagged.port_src, np.int32).ctypes.data_as(_i32p)
+    t.N, t.M = tagged.N, tagged.M
+    t.n_traces, t.n_knots, t.n_coefs = len(tagged.spl_trace), len(tagged.spl_t), len(tagged.spl_c)
+    t.spl_t = arr("st", tagged.spl_t, np.float64).ctypes.data_as(_f64p)
+    t.spl_c = arr("sc", tagged.spl_c, np.complex128).ctypes.data_as(_f64p)
+    t.spl_trace = arr("str", tagged.spl_trace, np.int32).ctypes.data_as(_i32p)
+    t.spl_fill = arr("sf", tagged.spl_fill, np.complex128).ctypes.data_as(_f64p)
+    t.spl_range = arr("sr", tagged.spl_range, np.float64).ctypes.data_as(_f64p)
+    return t, keep
+
+
+def stamps_compile_host(tagged: "pl.TaggedTable", mode: str = "auto", pad_to=None, order: str = "auto") -> dict:
+    """The plan the library's own compiler (csrc/hvb_stamps.cpp) produces for a tagged stamp table, as numpy arrays
+    named like `plan.DevicePlan`'s fields (no CUDA call)."""
+    lib = load_library()
+    t, keep = stamp_table_c(tagged)
+    d = PlanDesc()
+    handle, consts, prefs = C.c_void_p(), _f64p(), _i32p()
+    tp, ts = _i32p(), _i32p()
+    info = (C.c_int32 * 8)()
+    _check(lib.hvb_stamps_compile_host(C.byref(t), MODES[mode], pad_to[0] if pad_to else 0, pad_to[1] if pad_to else 0, ORDERS[order],
+                                       C.byref(handle), C.byref(d), C.byref(consts), C.byref(prefs), info, C.byref(tp), C.byref(ts)))
+    try:
+        def take(ptr, n, dt):
+            return np.ctypeslib.as_array(ptr, shape=(max(n, 1),)).copy()[:n].astype(dt) if n else np.zeros(0, dtype=dt)
+        n, ncols = d.n, d.ncols
+        nnz = int(np.ctypeslib.as_array(d.cell_ptr, shape=(n * ncols + 1,))[-1])
+        out = dict(
+            mode={1: "full", 2: "norton", 3: "dump"}[info[0]], n=n, ncols=ncols, P=d.P, n_real=info[1], band=info[2], max_nport=info[3],
+            n_tables=info[4], n_samples_cols=info[5], n_dyn=d.n_dyn, coop_scratch=d.coop_scratch, epi_simple=d.epi_simple,
+            consts=take(consts, d.n_consts * 2, np.float64).view(np.complex128) if d.n_consts else np.zeros(0, dtype=np.complex128),
+            prefs=take(prefs, d.n_prefs * 2, np.int32).reshape(-1, 2),
+            const_vals=take(d.const_vals, d.n_const_vals * 2, np.float64).view(np.complex128),
+            ops=take(d.ops, d.n_ops * 8, np.int32).reshape(-1, 8), coops=take(d.coops, d.n_coops * 8, np.int32).reshape(-1, 8),
+            cell_ptr=take(d.cell_ptr, n * ncols + 1, np.int32), cell_ent=take(d.cell_ent, nnz, np.int32),
+            row_ptr=take(d.row_ptr, n + 1, np.int32), row_ent=take(d.row_ent, d.n_row_ent, np.int32),
+            fop_code=take(d.fop_code, d.n_fast_ops, np.int32), fop_out=take(d.fop_out, d.n_fast_ops, np.int32),
+            fop_arg=take(d.fop_arg, d.n_fast_ops, np.float64),
+            epi_port_of_row=take(d.epi_port_of_row, max(n, 1), np.int32), epi_scale=take(d.epi_scale, max(d.P, 1) ** 2, np.float64),
+            port_rows=take(d.port_rows, d.P * 3, np.int32).reshape(-1, 3), port_zpref=take(d.port_zpref, d.P, np.int32),
+            table_pref=take(tp, info[6], np.int32), table_slot=take(ts, info[6], np.int32))
+    finally:
+        lib.hvb_compiled_free(handle)
+    return out
+
+
+class StampPlanHandle:
+    """A plan created by the library's own compiler from a tagged stamp table (`hvb_plan_create_from_stamps`): the
+    path a host without Python takes.  Per-run work left to this wrapper: tabulating callables and drawing the
+    sample matrix (`plan.resolve_run` on a light stand-in for `plan.DevicePlan`)."""
+
+    def __init__(self, table: "pl.StampTable", mode: str = "auto", device: int | None = None):
+        self.lib = load_library()
+        self.device = current_device() if device is None else device
+        self.tagged = pl.tag_table(table)
+        t, self._keep = stamp_table_c(self.tagged)
+        handle = C.c_void_p()
+        _check(self.lib.hvb_plan_create_from_stamps(C.byref(t), MODES[mode], self.device, C.byref(handle)))
+        self.handle = handle
+        self.P = t.P
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.hvb_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def kernel_info(self) -> dict:
+        ki = KernelInfo()
+        _check(self.lib.hvb_plan_kernel_info(self.handle, C.byref(ki)))
+        return {k: getattr(ki, k) for k, _ in KernelInfo._fields_}
+
+    def run(self, f, drivers=None, values=None):
+        """`run_host` with the per-run host work done: every table callable evaluated on f (a scalar result is
+        broadcast), the sample matrix filled from `values[s, k]` = value of `drivers[k]` (or the owners' current
+        values)."""
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        tabs = [np.broadcast_to(np.asarray(fn(f), dtype=np.complex128), f.shape) for fn in self.tagged.table_fns]
+        tables = np.ascontiguousarray(np.stack(tabs)) if tabs else None
+        owners = self.tagged.sample_owners
+        nS = 1 if values is None else len(values)
+        samples = np.empty((nS, len(owners)))
+        col_of = {} if drivers is None else {id(d): k for k, d in enumerate(drivers)}
+        for c, o in enumerate(owners):
+            samples[:, c] = np.asarray(values)[:, col_of[id(o)]] if id(o) in col_of else float(o._value)
+        return self.run_host(f, tables, samples)
+
+    def run_host(self, f, tables=None, samples=None):
+        """S[nS,P,P,nF]; consts / prefs are the plan's own (NULL in the run arguments)."""
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        nF = f.shape[0]
+        samples = np.zeros((1, 0)) if samples is None else np.ascontiguousarray(samples, dtype=np.float64)
+        tables = np.zeros((0, nF), dtype=np.complex128) if tables is None else np.ascontiguousarray(tables, dtype=np.complex128)
+        nS = samples.shape[0]
+        out = pinned_empty((nS, self.P, self.P, nF))
+        a = RunArgs()
+        a.consts, a.prefs = None, None
+        a.f, a.nF = _ptr(f), nF
+        a.samples, a.nS = _ptr(samples), nS
+        a.tables, a.n_tables = _ptr(tables), tables.shape[0]
+        status = C.c_int32(0)
+        _check(self.lib.hvb_run_host(self.handle, C.byref(a), C.c_void_p(out.__array_interface__["data"][0]), C.byref(status)))
+        return out, status.value
 
 
 def codegen_compile(src: str) -> str:

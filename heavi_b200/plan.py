@@ -738,3 +738,115 @@ def resolve_run(plan: DevicePlan, f: np.ndarray, drivers=None, values=None):
                 raise ValueError("Uninitialized value")
             samples[:, c] = float(v)
     return consts, prefs, tables, samples
+
+
+# ==================================================================================================
+# stamp table with tagged parameters: what the C-ABI's own compiler takes (hvb_plan_create_from_stamps)
+# ==================================================================================================
+COMP_KINDS = {"port": 0, "resistor": 1, "admittance": 2, "impedance": 3, "capacitor": 4, "inductor": 5, "tline": 6,
+              "nport_s": 7, "nport_y": 8}
+PAR_DTYPE = np.dtype([("kind", np.int32), ("index", np.int32), ("v", np.float64, (4,))])
+
+
+@dataclass
+class TaggedTable:
+    comp_kind: np.ndarray
+    comp_port: np.ndarray
+    ids_off: np.ndarray
+    ids: np.ndarray
+    par_off: np.ndarray
+    par: np.ndarray               # PAR_DTYPE
+    port_table: np.ndarray
+    port_src: np.ndarray
+    N: int
+    M: int
+    spl_t: np.ndarray
+    spl_c: np.ndarray
+    spl_trace: np.ndarray
+    spl_fill: np.ndarray
+    spl_range: np.ndarray
+    sample_owners: list
+    table_fns: list
+
+
+def tag_table(table: StampTable) -> TaggedTable:
+    """Turn every parameter object of a stamp table into a tagged slot (CONST / SAMPLE / TABLE / SPLINE / BETA / SMD),
+    in the order the compiler consumes them.  Host-side bookkeeping stays here: which object owns which sample
+    column, which callable fills which table row, the B-spline data of the traces."""
+    b = _Builder()                          # only its describe() / add_spline() are used
+    f1 = np.array([1.0])
+    pars, par_off, kinds, comp_port = [], [0], [], []
+    sample_owners, table_fns = [], []
+
+    def tag(p):
+        d = b.describe(p)
+        t = d[0]
+        if t == "const":
+            v = complex(d[1])
+            return (PK_CONST, 0, (v.real, v.imag, 0.0, 0.0))
+        if t == "sample":
+            owner, op = d[1], d[2]
+            for col, o in enumerate(sample_owners):
+                if o is owner:
+                    break
+            else:
+                sample_owners.append(owner)
+                col = len(sample_owners) - 1
+            return ({"id": PK_SAMPLE, "neg": PK_SAMPLE_NEG, "inv": PK_SAMPLE_INV}[op], col, (0.0, 0.0, 0.0, 0.0))
+        if t == "beta":
+            er = complex(d[1])
+            with np.errstate(invalid="ignore"):
+                root = complex(np.sqrt(np.float64(er.real)) if er.imag == 0 else np.sqrt(np.complex128(er)))
+            return (PK_BETA, 0, (root.real, root.imag, 0.0, 0.0))
+        if t == "spline":
+            return (PK_SPLINE, b.add_spline(d[1]), (0.0, 0.0, 0.0, 0.0))
+        if t == "beta_mul":
+            return (PK_BETA_MUL, 0, (float(d[1]), 0.0, 0.0, 0.0))
+        if t == "smd":
+            a, bb, c = (float(x) for x in d[2])
+            return (PK_SMD, int(d[1]), (a, bb, c, 0.0))
+        table_fns.append(d[1])
+        return (PK_TABLE, len(table_fns) - 1, (0.0, 0.0, 0.0, 0.0))
+
+    for kind, par in zip(table.kinds, table.params):
+        kinds.append(COMP_KINDS[kind])
+        comp_port.append(int(par.get("port", 0)) if kind == "port" else 0)
+        if kind == "port":
+            pars.append(tag(par["Z0"]))
+        elif kind == "resistor":
+            g = complex(np.asarray(par["G"](f1)).reshape(-1)[0])
+            pars.append((PK_CONST, 0, (g.real, g.imag, 0.0, 0.0)))
+        elif kind in ("admittance", "impedance", "capacitor", "inductor"):
+            pars.append(tag(par[{"admittance": "Y", "impedance": "Z", "capacitor": "C", "inductor": "L"}[kind]]))
+        elif kind == "tline":
+            length = par["length"]
+            if callable(length) and b.describe(length)[0] not in ("const", "sample"):
+                length = _ValueAtZero(length)
+            pars.extend([tag(par["Z0"]), tag(par["beta"]), tag(length)])
+        elif kind in ("nport_s", "nport_y"):
+            funcs = par["S"] if kind == "nport_s" else par["Y"]
+            for row in funcs:
+                for fn in row:
+                    pars.append(tag(fn))
+            if kind == "nport_s":
+                z0 = complex(par["Z0"])
+                pars.append((PK_CONST, 0, (z0.real, z0.imag, 0.0, 0.0)))
+        else:
+            raise NotImplementedError(f"component kind {kind!r} has no S-parameter stamp")
+        par_off.append(len(pars))
+    par_arr = np.zeros(max(len(pars), 1), dtype=PAR_DTYPE)
+    for i, (k, idx, v) in enumerate(pars):
+        par_arr[i] = (k, idx, v)
+    off = np.cumsum([0] + [len(i) for i in table.ids]).astype(np.int32)
+    nT = len(b.spl_trace)
+    return TaggedTable(
+        comp_kind=np.array(kinds, dtype=np.int32), comp_port=np.array(comp_port, dtype=np.int32), ids_off=off,
+        ids=np.array([i for lst in table.ids for i in lst], dtype=np.int32), par_off=np.array(par_off, dtype=np.int32), par=par_arr,
+        port_table=np.ascontiguousarray(table.port_table, dtype=np.int32), port_src=np.ascontiguousarray(table.port_src, dtype=np.int32),
+        N=int(table.N), M=int(table.M),
+        spl_t=np.concatenate(b.spl_t) if b.spl_t else np.zeros(0),
+        spl_c=np.concatenate(b.spl_c) if b.spl_c else np.zeros(0, dtype=np.complex128),
+        spl_trace=np.array(b.spl_trace, dtype=np.int32).reshape(nT, 4),
+        spl_fill=np.array(b.spl_fill, dtype=np.complex128).reshape(nT, 2),
+        spl_range=np.array(b.spl_range, dtype=np.float64).reshape(nT, 2),
+        sample_owners=sample_owners, table_fns=table_fns)

@@ -91,6 +91,65 @@ typedef struct hvb_plan_desc {
     const double*  spl_range;  /* [n_traces*2] first / last data abscissa                       */
 } hvb_plan_desc;
 
+/* ------------------------------------------------------------------------------------------------------
+ * Stamp table: the netlist as the reference's run_sp sees it (network.py:385-404), and the entry that compiles
+ * it below the ABI.  One record per component in creation order: its kind, its MNA indices in the reference's
+ * per-class `ids` order (ground = 0, repeated indices kept: base/port.py:23-26, base/tl.py:21-23,
+ * base/nport.py:19-22, two-terminal parts [n1, n2]) and its parameters as tagged slots; plus `port_table[P][4]`
+ * = exactly `indices` of network.py:400-404, the source row of every port, N and M.  No Python is needed to
+ * go from this to S: hvb_plan_create_from_stamps -> hvb_run_host (consts / prefs of hvb_run_args may then be
+ * NULL: the plan keeps the ones the table implies).
+ * ------------------------------------------------------------------------------------------------------ */
+enum hvb_comp_kind { HVB_COMP_PORT = 0, HVB_COMP_RESISTOR = 1, HVB_COMP_ADMITTANCE = 2, HVB_COMP_IMPEDANCE = 3,
+                     HVB_COMP_CAPACITOR = 4, HVB_COMP_INDUCTOR = 5, HVB_COMP_TLINE = 6, HVB_COMP_NPORT_S = 7, HVB_COMP_NPORT_Y = 8 };
+enum hvb_par_kind {
+    HVB_PAR_CONST = 0,      /* v[0] + j v[1], fixed for the whole run (numeric.py Scalar)                            */
+    HVB_PAR_SAMPLE = 1,     /* column `index` of the per-sample matrix (Random / Param / optimiser variable)         */
+    HVB_PAR_SAMPLE_NEG = 2, /* minus that column (numeric.py Negative)                                               */
+    HVB_PAR_SAMPLE_INV = 3, /* reciprocal of that column (numeric.py Inverse)                                        */
+    HVB_PAR_TABLE = 4,      /* row `index` of hvb_run_args.tables: an arbitrary callable tabulated by the host       */
+    HVB_PAR_SPLINE = 5,     /* B-spline trace `index` (Touchstone data, lib/touchstone.py:253-260)                   */
+    HVB_PAR_BETA = 6,       /* (2 pi f / c0) * (v[0] + j v[1]), v = sqrt(er): Network.transmissionline, :627-631     */
+    HVB_PAR_SMD = 7,        /* surface-mount part, `index` = 0 R / 1 L / 2 C, v[0..2] = its three constants          */
+    HVB_PAR_BETA_MUL = 8    /* ((2 pi f) * v[0]) / c0, v[0] = sqrt(er): the operation order of lib/tl.py             */
+};
+typedef struct hvb_param { int32_t kind; int32_t index; double v[4]; } hvb_param;
+/* parameters per component, in this order: port [Z0]; resistor [G = 1/R, const]; admittance [Y]; impedance [Z];
+ * capacitor [C]; inductor [L]; line [Z0, beta, length]; N-port S [S_00 .. row-major .. S_(P-1)(P-1), Z0 const];
+ * N-port Y [Y_00 ..] */
+typedef struct hvb_stamp_table {
+    int32_t n_components;
+    const int32_t* comp_kind;   /* [n_components] hvb_comp_kind                                                */
+    const int32_t* comp_port;   /* [n_components] port index (1-based, network.py:466) of a port, else 0       */
+    const int32_t* ids_off;     /* [n_components+1]                                                            */
+    const int32_t* ids;         /* MNA indices                                                                 */
+    const int32_t* par_off;     /* [n_components+1]                                                            */
+    const hvb_param* par;
+    int32_t P;
+    const int32_t* port_table;  /* [P*4] (iport-1, sig, int, gnd)                                              */
+    const int32_t* port_src;    /* [P] source row of each port                                                 */
+    int32_t N, M;
+    int32_t n_traces, n_knots, n_coefs;   /* splines, laid out like hvb_plan_desc                              */
+    const double* spl_t; const double* spl_c; const int32_t* spl_trace; const double* spl_fill; const double* spl_range;
+} hvb_stamp_table;
+enum hvb_solver_mode { HVB_MODE_AUTO = 0, HVB_MODE_FULL = 1, HVB_MODE_NORTON = 2, HVB_MODE_DUMP = 3 };
+enum hvb_row_order { HVB_ORDER_AUTO = 0, HVB_ORDER_NATURAL = 1, HVB_ORDER_RCM = 2 };
+
+/* Compile + create: picks the solver mode (Norton folding of the ports when legal), the row order and the kernel
+ * like the Python front-end does -- generated chain kernel, generated hub kernel, register-resident dense kernel
+ * in the shape hvb_warp_shape returns, banded kernel, dense block kernel, in that order of preference. */
+int hvb_plan_create_from_stamps(const hvb_stamp_table* table, int32_t mode, int device, hvb_plan** out);
+
+/* Host-only (no CUDA call): the compiled arrays, for inspection and for the tests that compare this compiler with
+ * heavi_b200/plan.py entry by entry.  `desc_out` points into memory owned by the returned object. */
+typedef struct hvb_compiled hvb_compiled;
+int hvb_stamps_compile_host(const hvb_stamp_table* table, int32_t mode, int32_t pad_rows, int32_t pad_rhs, int32_t order,
+                            hvb_compiled** out, hvb_plan_desc* desc_out, const double** consts_out, const int32_t** prefs_out,
+                            int32_t info_out[8] /* mode, n_real, band, max_nport, n_tables, n_sample_cols, n_table_params, 0 */,
+                            const int32_t** table_prefs_out, const int32_t** table_slots_out /* per table parameter: its
+                            parameter reference and the constant slot a scalar-valued callable is written to */);
+void hvb_compiled_free(hvb_compiled* c);
+
 /* Per-run parameters: what only the host can evaluate (callable parameters tabulated with the
  * reference's own numpy arithmetic, Monte-Carlo draws made in the reference's RNG order).
  * Replaces: SimParam.__call__(f) inside every closure (numeric.py:127-129) and
