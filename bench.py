@@ -212,8 +212,10 @@ def kernel_name(ki, cn) -> str:
         return "hvb_block_kernel<%d>" % ki["group"]
     if kc == 2:
         return "hvb_bandf_kernel<%d>" % ki["group"]
-    return "hvb_gen_kernel (NVRTC, %s, n=%d, P=%d)" % ("row loop, %d shapes" % ki["gen_cases"] if ki["gen_rolled"] == 1 else "straight-line",
-                                                        cn.plan.n_real, cn.plan.P)
+    form = "row loop, %d shapes" % ki["gen_cases"] if ki["gen_rolled"] == 1 else "straight-line"
+    if ki.get("gen_hub"):
+        return "hvb_gen_kernel (NVRTC, kernel E: N-port block + chains, n=%d, P=%d)" % (cn.plan.n_real, cn.plan.P)
+    return "hvb_gen_kernel (NVRTC, kernel D: chain, %s, n=%d, P=%d)" % (form, cn.plan.n_real, cn.plan.P)
 
 
 def executed_flops_per_solve(ki, plan) -> tuple[float, str]:
@@ -221,6 +223,8 @@ def executed_flops_per_solve(ki, plan) -> tuple[float, str]:
     values excluded)."""
     n, P = plan.n_real, plan.P
     if ki["kernel_class"] == 3:
+        if ki.get("gen_hub"):
+            return float(ki["gen_flops_per_solve"]), "counted by the generator: S->Y solve + chain eliminations + core solve + back substitution"
         return float(ki["gen_flops_per_solve"]), "counted by the generator: tridiagonal LU with partial pivoting + forward port recurrences"
     if ki["kernel_class"] == 2:
         B = ki["group"]
