@@ -70,6 +70,7 @@ struct GenKernel {
     size_t smem = 0;
     long long flops = 0;
     std::vector<int32_t> prefs;                        // the layout the value formulas were specialised on
+    std::vector<double> consts;                        // ... and the constants baked into the code
 };
 
 struct hvb_plan {
@@ -292,17 +293,25 @@ static bool gen_kernel_ok(const hvb_plan* pl) {
 static std::mutex g_cubin_mu;
 static std::map<std::string, std::shared_ptr<std::vector<char>>> g_cubins;
 
-static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs) {
-    const size_t np = (size_t)pl->d.n_prefs * 2;
-    if (pl->gk && pl->gk->prefs.size() == np && (np == 0 || memcmp(pl->gk->prefs.data(), prefs, np * 4) == 0)) return HVB_OK;
+// The generated code is specialised on the run's parameter layout (prefs) AND on the values of its constants (baked in
+// as literals / constant-bank entries): a plan keeps one compiled variant per distinct (prefs, consts) it has seen.
+static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs, const double* consts) {
+    const size_t np = (size_t)pl->d.n_prefs * 2, nc = (size_t)pl->d.n_consts * 2;
+    auto same = [&](const GenKernel* v) {
+        return v->prefs.size() == np && (np == 0 || memcmp(v->prefs.data(), prefs, np * 4) == 0) &&
+               v->consts.size() == nc && (nc == 0 || memcmp(v->consts.data(), consts, nc * 8) == 0);
+    };
+    if (pl->gk && same(pl->gk)) return HVB_OK;
     for (GenKernel* v : pl->gen_variants)
-        if (v->prefs.size() == np && (np == 0 || memcmp(v->prefs.data(), prefs, np * 4) == 0)) {
+        if (same(v)) {
             pl->gk = v; pl->threads = v->threads; pl->smem = v->smem; pl->regs = v->k.regs; pl->ctas_per_sm = v->ctas_per_sm;
             pl->max_grid = v->ctas_per_sm * pl->sm_count;
             return HVB_OK;
         }
+    if (pl->gen_variants.size() >= 64) return fail(HVB_ERR_UNSUPPORTED, "more than 64 distinct constant sets on one plan: build a new plan (or use sample columns) for values that change per run");
     GenResult res;
     std::string err;
+    pl->gen.run_consts.assign(consts, consts + nc);
     const char* md = getenv("HVB_GEN_MODE");
     const int grc = pl->gen_hub ? hvb_gen_hub_source(pl->gen, prefs, hvb_gen_prelude(), &res, &err)
                                 : hvb_gen_source(pl->gen, prefs, md ? atoi(md) : 0, hvb_gen_prelude(), &res, &err);
@@ -324,6 +333,7 @@ static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs) {
     if (hvb_jit_load(*cubin, res.kernel_name.c_str(), &gk->k, &err) != 0) return fail(HVB_ERR_CUDA, "%s", err.c_str());
     gk->rolled = res.rolled; gk->scratch_acc = res.scratch_acc; gk->n_cases = res.n_cases; gk->flops = res.flops_per_solve;
     gk->prefs.assign(prefs, prefs + np);
+    gk->consts.assign(consts, consts + nc);
     pl->threads = res.threads;
     gk->threads = res.threads; gk->smem = res.smem_bytes;
     if (res.smem_bytes > 48 * 1024) {
@@ -745,7 +755,7 @@ extern "C" int hvb_run_device(hvb_plan* pl, const hvb_run_args* a_in, double* d_
     if (pl->d.ncols <= pl->d.n || (!pl->kernel && pl->kclass != 3)) return fail(HVB_ERR_ARG, "plan has no right-hand sides (dump plan)");
     CU(cudaSetDevice(pl->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (pl->kclass == 3 && (rc = ensure_gen_kernel(pl, a->prefs)) != HVB_OK) return rc;
+    if (pl->kclass == 3 && (rc = ensure_gen_kernel(pl, a->prefs, a->consts)) != HVB_OK) return rc;
     rc = push_params(pl, a, st);
     if (rc) return rc;
     HvbDev D = make_dev(pl);
@@ -812,7 +822,7 @@ static int run_host_impl(hvb_plan* pl, const hvb_run_args* a_in, double* S_out, 
     const int64_t PP = (int64_t)d.P * d.P;
     if (nF == 0 || PP == 0) { if (status_out) *status_out = 0; return HVB_OK; }
     if ((d.n_consts && !a->consts) || (d.n_prefs && !a->prefs)) return fail(HVB_ERR_ARG, "consts/prefs missing");
-    if (pl->kclass == 3 && (rc = ensure_gen_kernel(pl, a->prefs)) != HVB_OK) return rc;
+    if (pl->kclass == 3 && (rc = ensure_gen_kernel(pl, a->prefs, a->consts)) != HVB_OK) return rc;
     cudaStream_t s0 = pl->streams[0], s1 = pl->streams[1];
     if (a->out_ld != 0 && a->out_ld < nF) return fail(HVB_ERR_ARG, "out_ld=%lld is smaller than nF=%lld", (long long)a->out_ld, (long long)nF);
     const int64_t ldo = a->out_ld ? a->out_ld : nF;       // frequency pitch of the caller's array
@@ -1038,7 +1048,7 @@ extern "C" int hvb_run_stats_host(hvb_plan* pl, const hvb_run_args* a_in, double
     const int64_t PP = (int64_t)d.P * d.P;
     if (nF == 0 || PP == 0) { if (status_out) *status_out = 0; return HVB_OK; }
     if ((d.n_consts && !a->consts) || (d.n_prefs && !a->prefs)) return fail(HVB_ERR_ARG, "consts/prefs missing");
-    if (pl->kclass == 3 && (rc = ensure_gen_kernel(pl, a->prefs)) != HVB_OK) return rc;
+    if (pl->kclass == 3 && (rc = ensure_gen_kernel(pl, a->prefs, a->consts)) != HVB_OK) return rc;
     cudaStream_t st = pl->streams[0];
     CU(pl->f.ensure((size_t)nF * 8));
     CU(cudaMemcpyAsync(pl->f.p, a->f, (size_t)nF * 8, cudaMemcpyHostToDevice, st));
@@ -1226,12 +1236,13 @@ extern "C" int hvb_plan_kernel_info(hvb_plan* pl, hvb_kernel_info* out) {
 }
 
 // ---- kernel D, host-only introspection (no CUDA call): generated source and an NVRTC compile check ----
-extern "C" int hvb_codegen_source(const hvb_plan_desc* desc, const int32_t* prefs, int32_t mode, char* src_out, int64_t src_cap,
+extern "C" int hvb_codegen_source(const hvb_plan_desc* desc, const int32_t* prefs, const double* consts, int32_t mode, char* src_out, int64_t src_cap,
                                   int32_t* rows_out, int32_t* itab_out, double* dtab_out, hvb_codegen_info* info) {
     if (!desc || !info) return fail(HVB_ERR_ARG, "null argument");
     memset(info, 0, sizeof(*info));
     GenPlan g;
     g.from_desc(*desc);
+    if (consts) g.run_consts.assign(consts, consts + 2 * (size_t)desc->n_consts);
     std::string why, why_hub;
     if (desc->n_prefs && !prefs) return fail(HVB_ERR_ARG, "prefs missing");
     const bool chain = hvb_gen_supported(g, &why);

@@ -192,10 +192,21 @@ struct Gen {
 
     Gen(const GenPlan& g_, const Analysis& a_, const int32_t* p, bool r, bool s) : g(g_), a(a_), prefs(p), rolled(r), scratch(s) {}
 
+    // a constant of the run: baked in when the generator was given the values, a load from HBM otherwise
+    std::string cst(int idx, Sink& s) {
+        static const char* bake_env = getenv("HVB_GEN_BAKE");             // experiments: 0 = never, 1 = straight-line code only, 2 = always
+        const int bake = bake_env ? atoi(bake_env) : 1;                   // measured on c5: baking into the row tables thrashes the constant cache
+        if ((size_t)idx * 2 + 1 < g.run_consts.size() && (bake == 2 || (bake == 1 && !s.rolled))) {
+            const double re = g.run_consts[2 * (size_t)idx], im = g.run_consts[2 * (size_t)idx + 1];
+            return "cmk(" + s.d(re) + ", " + (im == 0.0 ? std::string("0.0") : s.d(im)) + ")";
+        }
+        return "D.pv.consts[" + s.i(idx) + "]";
+    }
+
     std::string param(int pi, Sink& s) {
         const int kind = prefs[2 * pi], idx = prefs[2 * pi + 1];
         switch (kind) {
-            case PK_CONST: return "D.pv.consts[" + s.i(idx) + "]";
+            case PK_CONST: return cst(idx, s);
             case PK_SAMPLE: return "cmk(srow[" + s.i(idx) + "], 0.0)";
             case PK_SAMPLE_NEG: return "cmk(-srow[" + s.i(idx) + "], 0.0)";
             case PK_SAMPLE_INV: return "cmk(1.0 / srow[" + s.i(idx) + "], 0.0)";
@@ -203,7 +214,7 @@ struct Gen {
             case PK_SPLINE: return "spline_eval(D.pv.spl_t, D.pv.spl_c, D.pv.spl_trace, D.pv.spl_fill, D.pv.spl_range, " + s.i(idx) + ", f)";
             case PK_SMD: return "eval_smd(D.pv.consts + " + s.i(idx) + ", f)";
             case PK_BETA_MUL: return "cmk(__dmul_rn(w, D.pv.consts[" + s.i(idx) + "].x) / HVB_C0, 0.0)";
-            case PK_BETA: return "gen_beta(w, D.pv.consts[" + s.i(idx) + "])";
+            case PK_BETA: return "gen_beta(wc0, " + cst(idx, s) + ")";
         }
         return "cmk(0.0, 0.0)";
     }
@@ -480,10 +491,16 @@ int hvb_gen_source(const GenPlan& g, const int32_t* prefs, int mode, const char*
         // the row tables are constants of the plan: when they fit, they go into the module's constant bank
         // (uniform, cached reads) as static initialisers; otherwise the library uploads them (D.gen_*)
         const size_t table_bytes = out->rows.size() * 4 + out->itab.size() * 4 + out->dtab.size() * 8;
-        tables_in_source = table_bytes <= 56 * 1024;
+        static const char* ct_env = getenv("HVB_GEN_CONST_TABLES");        // experiments: 0 = row tables in global memory
+        tables_in_source = table_bytes <= 56 * 1024 && !(ct_env && atoi(ct_env) == 0);
+        static const char* pf_env = getenv("HVB_GEN_PREFETCH");
+        const bool prefetch = pf_env ? atoi(pf_env) != 0 : true;
+        if (tables_in_source && prefetch) body += "    int4 rwn = gen_rw[0];\n";
         body += "    for (int k = 0; k < " + std::to_string(n - 1) + "; ++k) {\n";
+        if (tables_in_source && !prefetch) body += "      const int4 rw = gen_rw[k];\n";
+        if (tables_in_source && prefetch)
+            body += fmt("      const int4 rw = rwn; rwn = gen_rw[k + 1 < %d ? k + 1 : k];          // next row's entry is fetched one row ahead\n", n - 1);
         if (tables_in_source) {
-            body += "      const int4 rw = gen_rw[k];\n";
             body += "      const int* __restrict__ it = gen_it + rw.z; const double* __restrict__ dt = gen_dt + rw.w; (void)it; (void)dt;\n";
         } else {
             body += "      const int4 rw = __ldg(reinterpret_cast<const int4*>(D.gen_rows) + k);\n";
@@ -531,8 +548,7 @@ int hvb_gen_source(const GenPlan& g, const int32_t* prefs, int mode, const char*
     src += "__device__ __forceinline__ void cfma(cplx& acc, cplx a, cplx b) {\n"
            "    acc.x = fma(a.x, b.x, acc.x); acc.x = fma(-a.y, b.y, acc.x);\n"
            "    acc.y = fma(a.x, b.y, acc.y); acc.y = fma(a.y, b.x, acc.y);\n}\n"
-           "__device__ __forceinline__ cplx gen_beta(double w, cplx s) {\n"
-           "    const double b0 = w / HVB_C0;\n"
+           "__device__ __forceinline__ cplx gen_beta(double b0, cplx s) {          // b0 = (2 pi f) / c0, once per point\n"
            "    return cmk(__dmul_rn(b0, s.x), s.y == 0.0 ? 0.0 : __dmul_rn(b0, s.y));\n}\n"
            "__device__ __forceinline__ cplx gen_cap(double w, cplx p0) {\n"
            "    return (p0.y == 0.0) ? cmk(0.0, __dmul_rn(w, p0.x)) : cmk(-__dmul_rn(w, p0.y), __dmul_rn(w, p0.x));\n}\n"
@@ -589,6 +605,7 @@ int hvb_gen_source(const GenPlan& g, const int32_t* prefs, int mode, const char*
     src += "    if (D.f32 && s == 0) D.f32[fi] = (float)f;\n";
     src += "    const double* __restrict__ srow = D.samples + s * D.nR; (void)srow;\n";
     src += "    const double w = __dmul_rn(HVB_TWOPI, f); (void)w;\n";
+    src += "    const double wc0 = w / HVB_C0; (void)wc0;\n";
     src += fmt("    cplx* __restrict__ Sp = D.S + s * %dLL * D.ldS + fi;\n", P * P);
     src += "    double pmin = 1e300, pmax = 0.0;\n";
     src += decl;

@@ -21,6 +21,8 @@ struct GenPlan {                       // host copy of what the generator reads 
     std::vector<double> fop_arg;
     std::vector<int32_t> port_rows, epi_port_of_row;
     std::vector<double> epi_scale;
+    std::vector<double> run_consts;    // optional [2*n_consts]: the run's constants; when present, constant parameters are
+                                       // baked into the code (literals / constant bank) instead of being loaded from HBM
     std::vector<int32_t> coops;        // [ncoops*8]
     std::vector<int32_t> spl_trace;    // [n_traces*4]
     void from_desc(const hvb_plan_desc& d);

@@ -229,10 +229,18 @@ struct HubGen {
 
     std::string sm(int i, int c) const { return fmt("gsm[%d * GEN_THREADS + threadIdx.x]", i * LD + c); }
 
+    std::string cst(int idx) const {                   // baked in when the run's constants are known
+        if ((size_t)idx * 2 + 1 < g.run_consts.size()) {
+            const double re = g.run_consts[2 * (size_t)idx], im = g.run_consts[2 * (size_t)idx + 1];
+            return "cmk(" + dlit(re) + ", " + (im == 0.0 ? std::string("0.0") : dlit(im)) + ")";
+        }
+        return fmt("D.pv.consts[%d]", idx);
+    }
+
     std::string param(int pi) const {
         const int kind = prefs[2 * pi], idx = prefs[2 * pi + 1];
         switch (kind) {
-            case PK_CONST: return fmt("D.pv.consts[%d]", idx);
+            case PK_CONST: return cst(idx);
             case PK_SAMPLE: return fmt("cmk(srow[%d], 0.0)", idx);
             case PK_SAMPLE_NEG: return fmt("cmk(-srow[%d], 0.0)", idx);
             case PK_SAMPLE_INV: return fmt("cmk(1.0 / srow[%d], 0.0)", idx);
@@ -240,7 +248,7 @@ struct HubGen {
             case PK_SPLINE: return fmt("spline_eval(D.pv.spl_t, D.pv.spl_c, D.pv.spl_trace, D.pv.spl_fill, D.pv.spl_range, %d, f)", idx);
             case PK_SMD: return fmt("eval_smd(D.pv.consts + %d, f)", idx);
             case PK_BETA_MUL: return fmt("cmk(__dmul_rn(w, D.pv.consts[%d].x) / HVB_C0, 0.0)", idx);
-            case PK_BETA: return fmt("gen_beta(w, D.pv.consts[%d])", idx);
+            case PK_BETA: return "gen_beta(wc0, " + cst(idx) + ")";
         }
         return "cmk(0.0, 0.0)";
     }
@@ -369,7 +377,7 @@ int hvb_gen_hub_source(const GenPlan& g, const int32_t* prefs, const char* prelu
     G.flops += 8LL * (Pn * Pn * Pn / 3 + Pn * Pn * Pn + Pn * Pn * Pn / 2);
     // core matrix A[i][j] = Y[i][j] = X[i][j] / Z0 = X^T[j][i] / Z0 (+ whatever else is stamped on core cells): read from
     // the tile's right half, written to its left half; the right half then takes the core's right-hand sides
-    b += fmt("    { const cplx iz = crecip_np(D.pv.consts[%d]);\n", h.coop_z0);
+    b += "    { const cplx iz = crecip_np(" + G.cst(h.coop_z0) + ");\n";
     for (int i = 0; i < Pn; ++i)
         for (int j = 0; j < Pn; ++j) {
             b += fmt("      { const cplx x = %s; cplx y = (iz.y == 0.0) ? cscale(x, iz.x) : cmul(iz, x);", G.sm(j, Pn + i).c_str());
@@ -496,8 +504,7 @@ int hvb_gen_hub_source(const GenPlan& g, const int32_t* prefs, const char* prelu
     src += "// generated by heavi_b200 (csrc/hvb_gen_hub.cpp): kernel E for one netlist (N-port block + matching chains)\n";
     src += prelude;
     src += fmt("\n#define GEN_THREADS %d\n", threads);
-    src += "__device__ __forceinline__ cplx gen_beta(double w, cplx s) {\n"
-           "    const double b0 = w / HVB_C0;\n"
+    src += "__device__ __forceinline__ cplx gen_beta(double b0, cplx s) {          // b0 = (2 pi f) / c0, once per point\n"
            "    return cmk(__dmul_rn(b0, s.x), s.y == 0.0 ? 0.0 : __dmul_rn(b0, s.y));\n}\n"
            "__device__ __forceinline__ cplx gen_cap(double w, cplx p0) {\n"
            "    return (p0.y == 0.0) ? cmk(0.0, __dmul_rn(w, p0.x)) : cmk(-__dmul_rn(w, p0.y), __dmul_rn(w, p0.x));\n}\n"
@@ -572,6 +579,7 @@ int hvb_gen_hub_source(const GenPlan& g, const int32_t* prefs, const char* prelu
     src += "    if (D.f32 && s == 0) D.f32[fi] = (float)f;\n";
     src += "    const double* __restrict__ srow = D.samples + s * D.nR; (void)srow;\n";
     src += "    const double w = __dmul_rn(HVB_TWOPI, f); (void)w;\n";
+    src += "    const double wc0 = w / HVB_C0; (void)wc0;\n";
     src += fmt("    cplx* __restrict__ Sp = D.S + s * %dLL * D.ldS + fi;\n", P * P);
     src += "    double pmin = 1e300, pmax = 0.0;\n";
     src += G.values();

@@ -106,7 +106,7 @@ def load_library():
     lib.hvb_plan_kernel_info.restype = C.c_int
     lib.hvb_measure_dfma_peak.argtypes = [C.c_int, _f64p]
     lib.hvb_measure_dfma_peak.restype = C.c_int
-    lib.hvb_codegen_source.argtypes = [C.POINTER(PlanDesc), C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+    lib.hvb_codegen_source.argtypes = [C.POINTER(PlanDesc), C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.POINTER(CodegenInfo)]
     lib.hvb_codegen_source.restype = C.c_int
     lib.hvb_codegen_compile.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
@@ -228,14 +228,17 @@ def make_desc(plan: pl.DevicePlan, kernel_hint: int = 0):
     return d, keep
 
 
-def codegen_source(plan: pl.DevicePlan, prefs: np.ndarray | None = None, mode: int = 0) -> dict:
+def codegen_source(plan: pl.DevicePlan, prefs: np.ndarray | None = None, mode: int = 0, consts: np.ndarray | None = None,
+                   bake_consts: bool = True) -> dict:
     """Source of the kernel the library would generate for `plan` (kernel class 3), without touching a
     GPU: {"supported", "reason", "src", "rolled", "rows", "itab", "dtab", "n_cases", "flops_per_solve"}."""
     lib = load_library()
     d, keep = make_desc(plan, 2)
     prefs = np.ascontiguousarray(plan.prefs if prefs is None else prefs, dtype=np.int32)
+    consts = np.ascontiguousarray(plan.consts if consts is None else consts, dtype=np.complex128)
+    cptr = _ptr(consts) if bake_consts else None      # what the library does at run time: constants baked into the code
     info = CodegenInfo()
-    _check(lib.hvb_codegen_source(C.byref(d), _ptr(prefs), mode, None, 0, None, None, None, C.byref(info)))
+    _check(lib.hvb_codegen_source(C.byref(d), _ptr(prefs), cptr, mode, None, 0, None, None, None, C.byref(info)))
     out = {"supported": bool(info.supported), "reason": info.reason.decode(), "rolled": bool(info.rolled),
            "n_cases": info.n_cases, "scratch_acc": bool(info.scratch_acc), "flops_per_solve": info.flops_per_solve,
            "hub": bool(info.hub), "threads": info.threads, "smem_bytes": info.smem_bytes}
@@ -245,7 +248,7 @@ def codegen_source(plan: pl.DevicePlan, prefs: np.ndarray | None = None, mode: i
     rows = np.zeros(max(info.n_rows, 1), dtype=np.int32)
     itab = np.zeros(max(info.n_itab, 1), dtype=np.int32)
     dtab = np.zeros(max(info.n_dtab, 1), dtype=np.float64)
-    _check(lib.hvb_codegen_source(C.byref(d), _ptr(prefs), mode, C.cast(src, C.c_void_p), info.src_len + 1,
+    _check(lib.hvb_codegen_source(C.byref(d), _ptr(prefs), cptr, mode, C.cast(src, C.c_void_p), info.src_len + 1,
                                   _ptr(rows), _ptr(itab), _ptr(dtab), C.byref(info)))
     out.update(src=src.value.decode(), rows=rows[:info.n_rows], itab=itab[:info.n_itab], dtab=dtab[:info.n_dtab],
                flops_per_solve=info.flops_per_solve, hub=bool(info.hub), threads=info.threads, smem_bytes=info.smem_bytes)

@@ -292,7 +292,8 @@ typedef struct hvb_codegen_info {
     int64_t smem_bytes;     /* dynamic shared memory per CTA                                      */
     char reason[256];
 } hvb_codegen_info;
-int hvb_codegen_source(const hvb_plan_desc* desc, const int32_t* prefs, int32_t mode, char* src_out, int64_t src_cap,
+int hvb_codegen_source(const hvb_plan_desc* desc, const int32_t* prefs, const double* consts /* [n_consts] complex or NULL:
+                       with the run's constants the code carries them as literals, without it loads them */, int32_t mode, char* src_out, int64_t src_cap,
                        int32_t* rows_out, int32_t* itab_out, double* dtab_out, hvb_codegen_info* info);
 int hvb_codegen_compile(const char* src, char* log_out, int64_t log_cap, int64_t* cubin_bytes);
 

@@ -28,7 +28,7 @@ def chain_plan(m):
 def sim(m, f, mode=0, drivers=None, values=None):
     p = chain_plan(m)
     consts, prefs, tables, samples = pl.resolve_run(p, np.asarray(f, dtype=np.float64), drivers, values)
-    gen = engine.codegen_source(p, prefs, mode)
+    gen = engine.codegen_source(p, prefs, mode, consts=consts)
     assert gen["supported"], gen["reason"]
     S, f32, status = host_sim.run(gen, p.P, f, consts, prefs, tables, samples, p)
     return S, f32, status, gen
@@ -168,7 +168,7 @@ def test_generated_source_compiles_for_sm100a(name, mode):
 def hub_sim(m, f):
     p = pl.compile_plan(m.stamp_table(), "auto")
     consts, prefs, tables, samples = pl.resolve_run(p, np.asarray(f, dtype=np.float64))
-    gen = engine.codegen_source(p, prefs, 0)
+    gen = engine.codegen_source(p, prefs, 0, consts=consts)
     assert gen["supported"] and gen["hub"], gen["reason"]
     S, f32, status = host_sim.run(gen, p.P, f, consts, prefs, tables, samples, p)
     return S, f32, status, gen
