@@ -513,7 +513,12 @@ def main():
         for wl in ("c1", "c2", "c3", "c4", "c5"):
             if wl == args.workload:
                 continue
-            r = run_workload(wl, min(steps, 10), 3, False)
+            try:
+                r = run_workload(wl, min(steps, 10), 3, False)
+            except Exception as exc:                              # a side workload must not take the headline line down
+                if world > 1:
+                    raise                                          # ranks would diverge: fail loudly under torchrun
+                r = {"error": "%s: %s" % (type(exc).__name__, exc)}
             if rank == 0:
                 r.pop("clocks", None)
                 per[wl] = r

@@ -36,13 +36,14 @@ Nvrtc* nvrtc() {
     static std::once_flag once;
     std::call_once(once, [] {
         std::vector<std::string> cands;
-        if (const char* e = getenv("HVB_NVRTC_LIB")) cands.push_back(e);
-        cands.push_back("libnvrtc.so.12");
-        cands.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
-        cands.push_back("libnvrtc.so");
+        const char* only = getenv("HVB_NVRTC_LIB");           // an explicit library is used exclusively
+        if (only) cands.push_back(only);
+        if (!only) cands.push_back("libnvrtc.so.12");
+        if (!only) cands.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
+        if (!only) cands.push_back("libnvrtc.so");
         // next to the CUDA runtime this process uses (pip layouts: .../nvidia/cuda_runtime/lib -> ../../cuda_nvrtc/lib)
         Dl_info di;
-        if (dladdr((void*)&cudaGetDeviceCount, &di) && di.dli_fname) {
+        if (!only && dladdr((void*)&cudaGetDeviceCount, &di) && di.dli_fname) {
             std::string p = di.dli_fname;
             const size_t s = p.rfind('/');
             if (s != std::string::npos) {

@@ -761,7 +761,17 @@ class CompiledNetwork:
         else:
             consts, prefs, tables, samples = self.resolve(f, drivers, values, plan)
         reps = self.replicas(handle, points) if (out_ptr is None and batch_points is None) else []
-        S, status = handle.run_host(f, consts, prefs, tables, samples, out, f32_out, out_ptr=out_ptr, out_ld=out_ld, replicas=reps)
+        try:
+            S, status = handle.run_host(f, consts, prefs, tables, samples, out, f32_out, out_ptr=out_ptr, out_ld=out_ld, replicas=reps)
+        except (RuntimeError, NotImplementedError) as exc:
+            # the generated kernels need NVRTC at the first run; if it cannot be loaded or refuses the source, the
+            # netlist is served by the library's precompiled kernels instead (still on the GPU) -- said once, loudly
+            if handle.kernel_info()["kernel_class"] != 3 or not any(k in str(exc) for k in ("NVRTC", "nvrtc", "kernel generator", "driver entry point", "cuModule")):
+                raise
+            warnings.warn("heavi_b200: run-time kernel generation unavailable (%s); using the precompiled kernels" % exc, RuntimeWarning)
+            fb = self.dense_fallback()
+            self.plan, self.handle, self.rows_per_lane, self._band, self._hub = fb.plan, fb.handle, fb.rows_per_lane, fb._band, False
+            return self.run(f, drivers, values, out=out, f32_out=f32_out, batch_points=batch_points, out_ptr=out_ptr, out_ld=out_ld)
         if self._hub and (status & HVB_STATUS_ZERO_PIVOT):
             # kernel E does not exchange a chain's last row with its core row; it flags the (rare) point where that
             # pivot is unsafe and the whole call is repeated on the dense register kernel (full partial pivoting)

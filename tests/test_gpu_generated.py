@@ -214,3 +214,28 @@ def test_hub_kernel_unsafe_pivot_falls_back_to_the_dense_kernel():
     cn = m._compiled()
     assert cn._hub and cn._dense_fallback is not None              # the flagged call was repeated on the dense kernel
     assert np.max(np.abs(S - oracle_S(m, f))) < 1e-12
+
+
+def test_missing_nvrtc_falls_back_to_the_precompiled_kernels():
+    """No NVRTC (a stripped-down deployment): the netlist still runs on the GPU, on the library's own kernels."""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys, warnings; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "os.environ['HVB_NVRTC_LIB'] = '/nonexistent/libnvrtc.so'\n"
+        "import ctypes, ctypes.util\n"
+        "import numpy as np, heavi_b200 as hv, circuits\n"
+        "from oracle import mna_oracle as orc\n"
+        "m, f = circuits.build_c2(hv, 'bandpass', nF=501)\n"
+        "with warnings.catch_warnings(record=True) as w:\n"
+        "    warnings.simplefilter('always')\n"
+        "    S = m.run_sp(f)._S\n"
+        "ref = orc.run_sp(m.records(), m.n_nodes, len(m.sources), f, method='lu_batched')\n"
+        "print('FALLBACK' if any('precompiled' in str(x.message) for x in w) else 'GENERATED', m._compiled().handle.kernel_info()['kernel_class'], float(np.max(np.abs(S - ref))))\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    env.pop("HVB_NO_GEN", None)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    kind, kclass, err = out.stdout.strip().split()[-3:]
+    assert kind == "FALLBACK" and float(err) < 1e-12 and int(kclass) in (0, 2)
