@@ -1,6 +1,7 @@
 """CPU: the numpy oracle against the golden vectors generated from the REAL reference
 (oracle/make_golden.py), driven through the product front-end's records -- so this also pins the
 front-end's node/source numbering, component order and element values."""
+import os
 import numpy as np
 import pytest
 
@@ -94,3 +95,16 @@ def test_known_answers():
     g = golden("ka_line")
     assert np.allclose(np.abs(g["S"][1, 0]), 1.0, atol=1e-12)  # matched lossless line
     assert np.allclose(np.abs(g["S"][0, 0]), 0.0, atol=1e-12)
+
+
+def test_live_reference_check_script_runs_when_the_reference_is_here():
+    """`oracle/check_oracle_vs_ref.py` (the open-ended version of the golden pinning) on a few fresh seeds; on a
+    machine without the reference tree it reports that and exits 0."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NUMBA_CACHE_DIR=os.environ.get("NUMBA_CACHE_DIR", "/tmp/numba_cache_heavi_ref"))
+    out = subprocess.run([sys.executable, os.path.join(root, "oracle", "check_oracle_vs_ref.py"), "--seeds", "200:203"],
+                         capture_output=True, text=True, env=env, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "all within the gate" in out.stdout or "nothing to check" in out.stdout
