@@ -212,7 +212,7 @@ def kernel_name(ki, cn) -> str:
         return "hvb_block_kernel<%d>" % ki["group"]
     if kc == 2:
         return "hvb_bandf_kernel<%d>" % ki["group"]
-    form = "row loop, %d shapes" % ki["gen_cases"] if ki["gen_rolled"] == 1 else "straight-line"
+    form = ("row loop%s, %d shapes" % (" walked from both ends" if ki.get("gen_two_sided") else "", ki["gen_cases"])) if ki["gen_rolled"] == 1 else "straight-line"
     if ki.get("gen_hub"):
         return "hvb_gen_kernel (NVRTC, kernel E: N-port block + chains, n=%d, P=%d)" % (cn.plan.n_real, cn.plan.P)
     return "hvb_gen_kernel (NVRTC, kernel D: chain, %s, n=%d, P=%d)" % (form, cn.plan.n_real, cn.plan.P)
@@ -255,6 +255,15 @@ class Measurement:
                                    d_smp=torch.from_numpy(samples).to(dev),
                                    d_S=torch.empty((samples.shape[0], P, P, len(f)), dtype=torch.complex128, device=dev),
                                    d_status=torch.zeros(1, dtype=torch.int32, device=dev)))
+
+        # a two-sided chain kernel may refuse a point (status bit 4, include/heavi_b200.h): such a plan is put back on the
+        # one-sided kernel BEFORE anything is timed, exactly what the host entries of the library do on their own
+        self.launch_all()
+        torch.cuda.synchronize()
+        for st in self.state:
+            if int(st["d_status"].item()) & 4:
+                st["handle"].set_tunable("gen_two_sided", 0)
+            st["d_status"].zero_()
 
     def launch_all(self):
         for st in self.state:

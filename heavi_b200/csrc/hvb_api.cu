@@ -65,7 +65,7 @@ struct DevBuf {
 struct GenKernel {
     HvbJitKernel k;
     DevBuf rows, itab, dtab;
-    bool rolled = false, scratch_acc = false;
+    bool rolled = false, scratch_acc = false, two_sided = false;
     int ctas_per_sm = 0, n_cases = 0, threads = 128;
     size_t smem = 0;
     long long flops = 0;
@@ -106,6 +106,8 @@ struct hvb_plan {
     std::vector<double> def_consts;                    // plans created from a stamp table: the run parameters it implies
     std::vector<int32_t> def_prefs;
     bool pending = false;                              // hvb_run_host_async queued, not yet waited for
+    bool allow_two_sided = true;                       // chain kernels: cleared for good once a two-sided run flagged a point
+    hvb_run_args pend_args{}; double* pend_out = nullptr;   // the queued call, should hvb_run_host_wait have to repeat it
     bool staged_valid = false;                         // h_in / inbuf hold the inputs of the last hvb_run_host call
     size_t staged_bytes = 0;
     int64_t staged_nF = 0, staged_nS = 0;
@@ -301,9 +303,9 @@ static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs, const double* c
         return v->prefs.size() == np && (np == 0 || memcmp(v->prefs.data(), prefs, np * 4) == 0) &&
                v->consts.size() == nc && (nc == 0 || memcmp(v->consts.data(), consts, nc * 8) == 0);
     };
-    if (pl->gk && same(pl->gk)) return HVB_OK;
+    if (pl->gk && same(pl->gk) && (pl->allow_two_sided || !pl->gk->two_sided)) return HVB_OK;
     for (GenKernel* v : pl->gen_variants)
-        if (same(v)) {
+        if (same(v) && (pl->allow_two_sided || !v->two_sided)) {
             pl->gk = v; pl->threads = v->threads; pl->smem = v->smem; pl->regs = v->k.regs; pl->ctas_per_sm = v->ctas_per_sm;
             pl->max_grid = v->ctas_per_sm * pl->sm_count;
             return HVB_OK;
@@ -312,6 +314,7 @@ static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs, const double* c
     GenResult res;
     std::string err;
     pl->gen.run_consts.assign(consts, consts + nc);
+    pl->gen.allow_two_sided = pl->allow_two_sided;
     const char* md = getenv("HVB_GEN_MODE");
     const int grc = pl->gen_hub ? hvb_gen_hub_source(pl->gen, prefs, hvb_gen_prelude(), &res, &err)
                                 : hvb_gen_source(pl->gen, prefs, md ? atoi(md) : 0, hvb_gen_prelude(), &res, &err);
@@ -332,6 +335,7 @@ static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs, const double* c
     std::unique_ptr<GenKernel> gk(new GenKernel());
     if (hvb_jit_load(*cubin, res.kernel_name.c_str(), &gk->k, &err) != 0) return fail(HVB_ERR_CUDA, "%s", err.c_str());
     gk->rolled = res.rolled; gk->scratch_acc = res.scratch_acc; gk->n_cases = res.n_cases; gk->flops = res.flops_per_solve;
+    gk->two_sided = res.two_sided;
     gk->prefs.assign(prefs, prefs + np);
     gk->consts.assign(consts, consts + nc);
     pl->threads = res.threads;
@@ -587,6 +591,7 @@ extern "C" int hvb_plan_set_tunable(hvb_plan* pl, const char* name, double value
     else if (n == "band_tile_waves") pl->env_tile_waves = value;
     else if (n == "copy2d") pl->env_copy2d = value != 0.0;
     else if (n == "band_pfb") pl->env_band_pfb = (int)value;
+    else if (n == "gen_two_sided") { pl->allow_two_sided = value != 0.0; pl->gk = nullptr; }
     else return fail(HVB_ERR_ARG, "unknown tunable '%s'", name);
     return HVB_OK;
 }
@@ -783,11 +788,20 @@ static void drain_after_error(hvb_plan* pl) {
 // have a run in flight each, so their copies share the PCIe link back to back instead of each call's fixed
 // costs (host marshalling, first kernel, last copy) adding up.  Inputs are staged during the call; S_out,
 // f32_out and a page-locked `tables` array must stay alive until the wait.
+// The two-sided chain kernel flags a point it cannot serve safely (HVB_STATUS_RERUN_BIT, hvb_gen.cpp).  The plan then
+// goes back to the one-sided kernel for good and the call is repeated: the bit never reaches a caller of the host entries.
+static bool wants_rerun(hvb_plan* pl, int32_t st) {
+    if (!(st & (int32_t)HVB_STATUS_RERUN_BIT)) return false;
+    pl->allow_two_sided = false;
+    pl->gk = nullptr;
+    return true;
+}
+
 extern "C" int hvb_run_host_async(hvb_plan* pl, const hvb_run_args* a, double* S_out) {
     if (pl && pl->pending) return fail(HVB_ERR_ARG, "a run is already in flight on this plan (hvb_run_host_wait first)");
     const int rc = run_host_impl(pl, a, S_out, nullptr, false);
     if (rc != HVB_OK && pl && pl->streams[0]) drain_after_error(pl);
-    if (rc == HVB_OK && pl) pl->pending = true;
+    if (rc == HVB_OK && pl) { pl->pending = true; pl->pend_args = effective_args(pl, a); pl->pend_out = S_out; }
     return rc;
 }
 
@@ -797,14 +811,32 @@ extern "C" int hvb_run_host_wait(hvb_plan* pl, int32_t* status_out) {
     pl->pending = false;
     CU(cudaSetDevice(pl->device));
     CU(cudaStreamSynchronize(pl->streams[0]));
-    if (status_out) *status_out = *pl->h_status;
+    int32_t st = *pl->h_status;
+    if (wants_rerun(pl, st)) {
+        // repeat from the staged copy of the inputs (the caller's f / samples / consts need not be alive any more)
+        const hvb_plan_desc& d = pl->d;
+        auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+        hvb_run_args b = pl->pend_args;
+        char* h = (char*)pl->h_in;
+        const size_t off_consts = 16, off_prefs = off_consts + up16((size_t)d.n_consts * 16), off_smp = off_prefs + up16((size_t)d.n_prefs * 8);
+        const size_t off_f = off_smp + up16(d.n_samples_cols ? (size_t)b.nS * d.n_samples_cols * 8 : 0);
+        b.consts = (const double*)(h + off_consts); b.prefs = (const int32_t*)(h + off_prefs);
+        b.samples = d.n_samples_cols ? (const double*)(h + off_smp) : nullptr;
+        b.f = (const double*)(h + off_f);
+        const int rc = run_host_impl(pl, &b, pl->pend_out, &st, true);
+        if (rc != HVB_OK) { drain_after_error(pl); return rc; }
+    }
+    if (status_out) *status_out = st & ~(int32_t)HVB_STATUS_RERUN_BIT;
     return HVB_OK;
 }
 
 extern "C" int hvb_run_host(hvb_plan* pl, const hvb_run_args* a, double* S_out, int32_t* status_out) {
     if (pl && pl->pending) return fail(HVB_ERR_ARG, "a run is already in flight on this plan (hvb_run_host_wait first)");
-    const int rc = run_host_impl(pl, a, S_out, status_out, true);
+    int32_t st = 0;
+    int rc = run_host_impl(pl, a, S_out, &st, true);
+    if (rc == HVB_OK && wants_rerun(pl, st)) rc = run_host_impl(pl, a, S_out, &st, true);
     if (rc != HVB_OK && pl && pl->streams[0]) drain_after_error(pl);
+    if (status_out) *status_out = st & ~(int32_t)HVB_STATUS_RERUN_BIT;
     return rc;
 }
 
@@ -1034,7 +1066,17 @@ extern "C" int hvb_run_host_multi(hvb_plan* const* plans, int32_t nplans, const 
     return HVB_OK;
 }
 
-extern "C" int hvb_run_stats_host(hvb_plan* pl, const hvb_run_args* a_in, double* stats_out, int32_t* status_out) {
+static int run_stats_host_impl(hvb_plan* pl, const hvb_run_args* a_in, double* stats_out, int32_t* status_out);
+
+extern "C" int hvb_run_stats_host(hvb_plan* pl, const hvb_run_args* a, double* stats_out, int32_t* status_out) {
+    int32_t st = 0;
+    int rc = run_stats_host_impl(pl, a, stats_out, &st);
+    if (rc == HVB_OK && wants_rerun(pl, st)) rc = run_stats_host_impl(pl, a, stats_out, &st);
+    if (status_out) *status_out = st & ~(int32_t)HVB_STATUS_RERUN_BIT;
+    return rc;
+}
+
+static int run_stats_host_impl(hvb_plan* pl, const hvb_run_args* a_in, double* stats_out, int32_t* status_out) {
     if (!pl || !a_in) return fail(HVB_ERR_ARG, "null argument");
     const hvb_run_args a_eff = effective_args(pl, a_in);
     const hvb_run_args* a = &a_eff;
@@ -1231,7 +1273,7 @@ extern "C" int hvb_plan_kernel_info(hvb_plan* pl, hvb_kernel_info* out) {
     out->gen_scratch_acc = pl->gk ? (pl->gk->scratch_acc ? 1 : 0) : 0;
     out->gen_flops_per_solve = pl->gk ? pl->gk->flops : 0;
     out->gen_hub = pl->gen_hub ? 1 : 0;
-    out->reserved = 0;
+    out->gen_two_sided = (pl->gk && pl->gk->two_sided) ? 1 : 0;
     return HVB_OK;
 }
 
@@ -1262,6 +1304,7 @@ extern "C" int hvb_codegen_source(const hvb_plan_desc* desc, const int32_t* pref
     info->src_len = (int64_t)res.src.size();
     info->n_rows = (int64_t)res.rows.size(); info->n_itab = (int64_t)res.itab.size(); info->n_dtab = (int64_t)res.dtab.size();
     info->flops_per_solve = res.flops_per_solve;
+    info->two_sided = res.two_sided ? 1 : 0; info->cut_row = res.cut_row;
     if (src_out) {
         if (src_cap < (int64_t)res.src.size() + 1) return fail(HVB_ERR_ARG, "source buffer too small");
         memcpy(src_out, res.src.c_str(), res.src.size() + 1);

@@ -25,6 +25,9 @@ struct GenPlan {                       // host copy of what the generator reads 
                                        // baked into the code (literals / constant bank) instead of being loaded from HBM
     std::vector<int32_t> coops;        // [ncoops*8]
     std::vector<int32_t> spl_trace;    // [n_traces*4]
+    bool allow_two_sided = true;       // false keeps a long chain on the one-sided row loop (modes 0 and 3)
+    int cut_col = -1;                  // generator-internal (half chains of the two-sided form): column index under which the
+                                       // last row's coupling to the other half is filed; -1 in a plan that came from a desc
     void from_desc(const hvb_plan_desc& d);
 };
 
@@ -40,6 +43,8 @@ struct GenResult {
     int threads = 128;                 // threads per CTA the kernel is written for
     size_t smem_bytes = 0;             // dynamic shared memory per CTA (kernel E: the per-thread dense tiles)
     int n_cases = 0;                   // distinct row shapes emitted (rolled)
+    bool two_sided = false;            // rolled, walked from both ends towards a cut row (sets HVB_STATUS_RERUN_BIT when unsafe)
+    int cut_row = -1;                  // two-sided: last row of the front half
     long long flops_per_solve = 0;     // executed real flops of the elimination / border recurrences (excl. stamp values)
 };
 
@@ -47,7 +52,8 @@ struct GenResult {
 bool hvb_gen_supported(const GenPlan& g, std::string* why);
 
 // prefs: the run's parameter references [nprefs][2] (kind, index): value formulas are specialised on the kinds.
-// mode: 0 auto (unrolled up to HVB_GEN_UNROLL_MAX rows, rolled above), 1 unrolled, 2 rolled.
+// mode: 0 auto (unrolled up to HVB_GEN_UNROLL_MAX rows; above that rolled, two-sided when that saves work),
+//       1 unrolled, 2 rolled one-sided, 3 rolled two-sided (falls back to 2 when the chain offers no cut).
 // prelude: text of plan_format.h + hvb_device.cuh (embedded at build time, see Makefile).
 int hvb_gen_source(const GenPlan& g, const int32_t* prefs, int mode, const char* prelude, GenResult* out, std::string* err);
 

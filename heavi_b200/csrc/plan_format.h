@@ -36,6 +36,7 @@
 
 #define HVB_STATUS_NONFINITE_BIT 1u
 #define HVB_STATUS_ZERO_PIVOT_BIT 2u
+#define HVB_STATUS_RERUN_BIT 4u       // two-sided chain kernel: a point was unsafe for the cut; the library repeats the call one-sided
 
 #define HVB_TWOPI 6.283185307179586     /* np.float64(2*np.pi) */
 #define HVB_C0 299792458.0

@@ -21,6 +21,7 @@ LIB_PATH = os.path.join(_HERE, "libheavi_b200.so")
 
 HVB_STATUS_NONFINITE = 1
 HVB_STATUS_ZERO_PIVOT = 2
+HVB_STATUS_RERUN = 4
 
 _i32p = C.POINTER(C.c_int32)
 _f64p = C.POINTER(C.c_double)
@@ -46,13 +47,14 @@ class KernelInfo(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("kernel_class", "group", "pmax", "threads", "smem_bytes", "regs",
                                          "ctas_per_sm", "sm_count", "rows_per_lane", "stream_words")] + [("launches", C.c_int64)] + [
         (k, C.c_int32) for k in ("gen_rolled", "gen_cases", "local_bytes", "gen_scratch_acc")] + [("gen_flops_per_solve", C.c_int64)] + [
-        ("gen_hub", C.c_int32), ("reserved", C.c_int32)]
+        ("gen_hub", C.c_int32), ("gen_two_sided", C.c_int32)]
 
 
 class CodegenInfo(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("supported", "rolled", "n_cases", "scratch_acc")] + [
         (k, C.c_int64) for k in ("src_len", "n_rows", "n_itab", "n_dtab", "flops_per_solve")] + [
-        ("hub", C.c_int32), ("threads", C.c_int32), ("smem_bytes", C.c_int64), ("reason", C.c_char * 256)]
+        ("hub", C.c_int32), ("threads", C.c_int32), ("smem_bytes", C.c_int64), ("two_sided", C.c_int32), ("cut_row", C.c_int32),
+        ("reason", C.c_char * 256)]
 
 
 EXPORTS = ("hvb_warp_shape", "hvb_plan_create", "hvb_plan_destroy", "hvb_run_host", "hvb_run_device",
@@ -241,7 +243,8 @@ def codegen_source(plan: pl.DevicePlan, prefs: np.ndarray | None = None, mode: i
     _check(lib.hvb_codegen_source(C.byref(d), _ptr(prefs), cptr, mode, None, 0, None, None, None, C.byref(info)))
     out = {"supported": bool(info.supported), "reason": info.reason.decode(), "rolled": bool(info.rolled),
            "n_cases": info.n_cases, "scratch_acc": bool(info.scratch_acc), "flops_per_solve": info.flops_per_solve,
-           "hub": bool(info.hub), "threads": info.threads, "smem_bytes": info.smem_bytes}
+           "hub": bool(info.hub), "threads": info.threads, "smem_bytes": info.smem_bytes,
+           "two_sided": bool(info.two_sided), "cut_row": info.cut_row}
     if not info.supported:
         return out
     src = C.create_string_buffer(info.src_len + 1)
@@ -251,7 +254,8 @@ def codegen_source(plan: pl.DevicePlan, prefs: np.ndarray | None = None, mode: i
     _check(lib.hvb_codegen_source(C.byref(d), _ptr(prefs), cptr, mode, C.cast(src, C.c_void_p), info.src_len + 1,
                                   _ptr(rows), _ptr(itab), _ptr(dtab), C.byref(info)))
     out.update(src=src.value.decode(), rows=rows[:info.n_rows], itab=itab[:info.n_itab], dtab=dtab[:info.n_dtab],
-               flops_per_solve=info.flops_per_solve, hub=bool(info.hub), threads=info.threads, smem_bytes=info.smem_bytes)
+               flops_per_solve=info.flops_per_solve, hub=bool(info.hub), threads=info.threads, smem_bytes=info.smem_bytes,
+               two_sided=bool(info.two_sided), cut_row=info.cut_row, n_cases=info.n_cases)
     return out
 
 
@@ -824,7 +828,14 @@ class CompiledNetwork:
         d_status = torch.zeros(1, dtype=torch.int32, device=dev)
         handle.run_device(d_f, consts, prefs, d_tab, d_smp, out, d_status)
         if check:
-            self._raise_for_status(int(d_status.item()))
+            status = int(d_status.item())
+            if status & HVB_STATUS_RERUN:
+                # the two-sided chain kernel met a point it cannot serve safely: this plan goes back to the one-sided kernel
+                handle.set_tunable("gen_two_sided", 0)
+                d_status.zero_()
+                handle.run_device(d_f, consts, prefs, d_tab, d_smp, out, d_status)
+                status = int(d_status.item())
+            self._raise_for_status(status)
         return out
 
     def _raise_for_status(self, status: int):

@@ -44,6 +44,9 @@ enum hvb_status {
  * reference silently returns the SVD minimum-norm solution (App. B-7). */
 #define HVB_STATUS_NONFINITE 1
 #define HVB_STATUS_ZERO_PIVOT 2
+#define HVB_STATUS_RERUN 4      /* hvb_run_device only: the two-sided chain kernel met a point it cannot serve safely and the
+                                   result is invalid -- hvb_plan_set_tunable(plan, "gen_two_sided", 0) and run again.  The host
+                                   entries (hvb_run_host*, hvb_run_stats_host) do this themselves and never report the bit. */
 
 /* Frozen netlist.  Field meanings follow heavi_b200/plan.py:DevicePlan one to one.
  * Replaces: the list of SP_matrix_compiler closures (network.py:385-386) plus `indices`
@@ -266,7 +269,8 @@ typedef struct hvb_kernel_info {
                                recurrences per point (stamp values excluded)                      */
     int32_t gen_hub;        /* generated kernel: 0 chain kernel (tridiagonal netlist), 1 hub kernel
                                (one N-port S block + chains hanging off its nodes)                */
-    int32_t reserved;
+    int32_t gen_two_sided;  /* generated chain kernel, row loop: 1 when the chain is walked from both ends
+                               towards a cut (about half the port-recurrence work)                */
 } hvb_kernel_info;
 int hvb_plan_kernel_info(hvb_plan* plan, hvb_kernel_info* out);
 
@@ -290,6 +294,8 @@ typedef struct hvb_codegen_info {
     int32_t hub;            /* 1: hub kernel (N-port block + chains), 0: chain kernel             */
     int32_t threads;        /* threads per CTA the source is written for                          */
     int64_t smem_bytes;     /* dynamic shared memory per CTA                                      */
+    int32_t two_sided;      /* 1: chain walked from both ends towards a cut (may set status bit 4, see hvb_run_host) */
+    int32_t cut_row;        /* two-sided: last row of the front half, else -1                     */
     char reason[256];
 } hvb_codegen_info;
 int hvb_codegen_source(const hvb_plan_desc* desc, const int32_t* prefs, const double* consts /* [n_consts] complex or NULL:

@@ -397,3 +397,33 @@ def build_hub(hv, n_block: int = 4, chain_rows=(2, 1, 0, 3), port_on=(0, 0, None
             m.resistor(inner[k], m.gnd, float(rng.uniform(200, 2000)))
     m.n_port_S(m.gnd, inner, [[S_of(i, j) for j in range(n_block)] for i in range(n_block)], 50.0)
     return m, np.linspace(0.8e9, 6e9, nF)
+
+
+def build_lc_chain(hv, K, taps, coupling=None, lossy=False, seed=0):
+    """Ladder of series L / shunt C (alternating kinds with `seed`), ports at `taps`; `coupling`: the two end ports sit
+    behind series capacitors of that size (weakly coupled, high-Q resonator chain)."""
+    rng = np.random.default_rng(seed)
+    m = _model(hv)
+    chain = [m.node() for _ in range(K + 1)]
+    if coupling is None:
+        for t in taps:
+            m.new_port(50, chain[t])
+    else:
+        pa, pb = m.node(), m.node()
+        m.new_port(50, pa)
+        m.new_port(50, pb)
+        m.capacitor(pa, chain[0], coupling)
+        m.capacitor(chain[K], pb, coupling)
+    for k in range(K):
+        if coupling is not None or k % 2 == 0:
+            m.inductor(chain[k], chain[k + 1], float(10 ** rng.uniform(-9.3, -8.3)) if coupling is None else 2e-9)
+        else:
+            m.capacitor(chain[k], chain[k + 1], float(10 ** rng.uniform(-12.5, -11.5)))
+    for k in range(K + 1):
+        if coupling is not None or k % 2:
+            m.capacitor(chain[k], m.gnd, float(10 ** rng.uniform(-13, -11.7)) if coupling is None else 1e-12)
+        else:
+            m.inductor(chain[k], m.gnd, float(10 ** rng.uniform(-9, -8)))
+        if lossy and k % 4 == 0:
+            m.resistor(chain[k], m.gnd, float(rng.uniform(500, 5000)))
+    return m

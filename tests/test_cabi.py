@@ -34,7 +34,7 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(engine.PlanDesc) == 18 * 4 + 19 * 8
     assert ctypes.sizeof(engine.RunArgs) == 10 * 8
     assert ctypes.sizeof(engine.KernelInfo) == 10 * 4 + 8 + 4 * 4 + 8 + 8
-    assert ctypes.sizeof(engine.CodegenInfo) == 4 * 4 + 5 * 8 + 2 * 4 + 8 + 256
+    assert ctypes.sizeof(engine.CodegenInfo) == 4 * 4 + 5 * 8 + 2 * 4 + 8 + 2 * 4 + 256
 
 
 def test_plan_format_constants_in_sync():

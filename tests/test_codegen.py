@@ -90,10 +90,83 @@ def test_port_positions_and_counts(n_sections, taps):
         m.capacitor(nodes[k], m.gnd, float(10 ** rng.uniform(-12.5, -11.5)))
     f = np.linspace(0.4e9, 7e9, 23)
     ref = oracle_S(m, f)
-    for mode in (1, 2):
+    for mode in (1, 2, 3):
         S, _, status, gen = sim(m, f, mode)
         assert status == 0
-        assert np.max(np.abs(S[0] - ref)) < 2e-13, (mode, np.max(np.abs(S[0] - ref)))
+        assert np.max(np.abs(S[0] - ref)) < 2e-13, (mode, gen["two_sided"], np.max(np.abs(S[0] - ref)))
+
+
+def _lc_chain(K, taps, coupling=None, lossy=False, seed=0):
+    return circuits.build_lc_chain(hv, K, taps, coupling, lossy, seed)
+
+
+def test_two_sided_form_on_config5_matches_the_reference_golden_with_less_work():
+    """Long chains are walked from both ends towards a cut (hvb_gen.cpp header): same S as the one-sided row loop within
+    rounding, checked against the reference's own output; the border work drops by a quarter."""
+    m, _ = circuits.build_c5(hv, nF=8)
+    g = golden("c5_ladder")
+    S3, _, st3, g3 = sim(m, g["f"], 3)
+    S2, _, st2, g2 = sim(m, g["f"], 2)
+    S0, _, st0, g0 = sim(m, g["f"], 0)
+    assert st3 == 0 and st2 == 0 and st0 == 0
+    assert g3["two_sided"] and g0["two_sided"] and not g2["two_sided"] and g3["cut_row"] == 95 and g2["cut_row"] == -1
+    assert np.array_equal(S0, S3)                                  # auto picks the two-sided form for this chain
+    assert g3["flops_per_solve"] < 0.8 * g2["flops_per_solve"]
+    assert len(g3["rows"]) == 4 * 190 and g3["n_cases"] < 70
+    frac, adjudicated, ext = parity_report(S3[0], g["S"], g["S_ext"])
+    assert frac == 1.0 and ext < 5e-14
+    assert np.max(np.abs(S3 - S2)) < 5e-14
+
+
+@pytest.mark.parametrize("K,taps,lossy", [(12, [0, 12], False), (40, [0, 40], False), (60, [0, 30, 60], False), (60, [0, 20, 40, 60], True),
+                                          (45, [3, 4, 40, 41, 42], True), (50, [0, 1, 2, 3, 4, 5, 6, 50], True)])
+def test_two_sided_form_on_lossless_and_lossy_ladders(K, taps, lossy):
+    """The cut grounds each half at the other's first node; lossless LC ladders (resonant halves) are the hard case."""
+    m = _lc_chain(K, taps, lossy=lossy, seed=K)
+    f = np.linspace(0.2e9, 8e9, 257)
+    ref = oracle_S(m, f)
+    S3, _, st3, g3 = sim(m, f, 3)
+    S2, _, st2, _ = sim(m, f, 2)
+    assert g3["two_sided"] and st2 == 0
+    tol = 1e-12 + 1e-10 * np.abs(ref)
+    assert np.all(np.abs(S2[0] - ref) <= tol)
+    if st3 == 0:
+        assert np.all(np.abs(S3[0] - ref) <= tol), np.max(np.abs(S3[0] - ref))
+    else:
+        assert st3 == engine.HVB_STATUS_RERUN                      # refused, never wrong silently
+
+
+def test_two_sided_form_needs_a_cut_between_ports_and_auto_mode_needs_a_saving():
+    f = np.linspace(1e9, 3e9, 5)
+    # one port, or all ports on one side of every admissible cut: no cut -> mode 3 quietly gives the one-sided row loop
+    for taps in ([7], [0, 1], [48, 49, 50]):
+        m = _lc_chain(50, taps, lossy=True)
+        S, _, st, gen = sim(m, f, 3)
+        assert gen["rolled"] and not gen["two_sided"] and st == 0
+        assert np.max(np.abs(S[0] - oracle_S(m, f))) < 2e-13
+    # every row a port row: no cut either
+    m = _lc_chain(15, list(range(16)), lossy=True)
+    assert not sim(m, f, 3)[3]["two_sided"]
+    # a port at the far end only: cutting saves nothing (its recurrence is one row long already) -> auto stays one-sided
+    m = _lc_chain(50, [49, 50], lossy=True)
+    assert not sim(m, f, 0)[3]["two_sided"]
+    m = _lc_chain(50, [0, 50], lossy=True)                       # ports at the two ends: 52 tap-rows either way
+    assert not sim(m, f, 0)[3]["two_sided"]
+    m = _lc_chain(50, [0, 10, 50], lossy=True)                   # 93 tap-rows one-sided, 55 with the cut next to the middle port
+    gen = sim(m, f, 0)[3]
+    assert gen["two_sided"] and gen["cut_row"] in (11, 38)
+
+
+def test_two_sided_form_refuses_an_unsafe_cut():
+    """Weakly coupled resonator chain: at the halves' resonances the 2 x 2 interface solve cancels beyond 10^3 and the kernel
+    sets HVB_STATUS_RERUN (the library then repeats the call one-sided, tests/test_gpu_generated.py)."""
+    m = _lc_chain(44, None, coupling=1e-15)
+    f = np.linspace(0.2e9, 8e9, 4000)
+    S3, _, st3, g3 = sim(m, f, 3)
+    S2, _, st2, g2 = sim(m, f, 2)
+    assert g3["two_sided"] and st3 == engine.HVB_STATUS_RERUN and st2 == 0
+    ref = oracle_S(m, f)
+    assert np.all(np.abs(S2[0] - ref) <= 1e-12 + 1e-10 * np.abs(ref))
 
 
 def test_monte_carlo_samples_tables_and_lossy_lines():
@@ -145,7 +218,7 @@ def test_unsupported_structures_are_refused_with_a_reason():
     assert not gen3["supported"]
 
 
-@pytest.mark.parametrize("name,mode", [("c2_bandpass", 1), ("c5_ladder", 2)])
+@pytest.mark.parametrize("name,mode", [("c2_bandpass", 1), ("c5_ladder", 2), ("c5_ladder", 3)])
 def test_generated_source_compiles_for_sm100a(name, mode):
     m = REG[name]()
     p = chain_plan(m)

@@ -40,19 +40,19 @@ def library_variant(m):
         os.environ.pop("HVB_NO_GEN")
 
 
-@pytest.mark.parametrize("gen_mode", ["1", "2"])
+@pytest.mark.parametrize("gen_mode", ["1", "2", "3"])
 @pytest.mark.parametrize("name,build", [("c1_readme", lambda: circuits.build_c1(hv)[0]),
                                         ("c2_bandpass", lambda: circuits.build_c2(hv, "bandpass")[0]),
                                         ("c2_lowpass", lambda: circuits.build_c2(hv, "lowpass")[0]),
                                         ("c2_highpass", lambda: circuits.build_c2(hv, "highpass")[0]),
                                         ("c5_ladder", lambda: circuits.build_c5(hv, nF=16)[0])])
 def test_configs_on_the_generated_kernel_match_reference_golden(name, build, gen_mode):
-    os.environ["HVB_GEN_MODE"] = gen_mode               # 1 straight-line code, 2 loop over row shapes
+    os.environ["HVB_GEN_MODE"] = gen_mode               # 1 straight-line code, 2 loop over row shapes, 3 the loop walked from both ends
     g = golden(name)
     m = build()
     S = m.run_sp(g["f"])
     ki = m._compiled().handle.kernel_info()
-    assert ki["kernel_class"] == 3 and ki["gen_rolled"] == (gen_mode == "2") , ki
+    assert ki["kernel_class"] == 3 and ki["gen_rolled"] == (gen_mode != "1") and ki["gen_two_sided"] == (gen_mode == "3"), ki
     assert S.f.dtype == np.float32 and np.array_equal(S.f, g["f32"])
     frac, adjudicated, ext = parity_report(S._S, g["S"], g["S_ext"])
     assert frac >= 0.998 and adjudicated and ext < 5e-14, (frac, adjudicated, ext)
@@ -82,6 +82,45 @@ def test_chains_of_every_size_against_oracle_and_library_kernels(n_sections, n_p
     lib = library_variant(m)
     assert lib.handle.kernel_info()["kernel_class"] != 3
     assert np.max(np.abs(S - lib.run(f)[0])) < 1e-12
+
+
+def test_two_sided_chain_kernel_at_size_and_its_refusal_path():
+    """configs[4]'s netlist: long chains are walked from both ends (csrc/hvb_gen.cpp); against the oracle, against the
+    one-sided kernel of the same plan, and -- on a weakly coupled resonator chain whose cut is unsafe at the halves'
+    resonances -- the library's own repeat on the one-sided kernel, on every host entry."""
+    m, f = circuits.build_c5(hv, nF=300_000)
+    S = m.run_sp(f)._S
+    cn = m._compiled()
+    ki = cn.handle.kernel_info()
+    assert ki["kernel_class"] == 3 and ki["gen_rolled"] == 1 and ki["gen_two_sided"] == 1, ki
+    idx = np.arange(0, 300_000, 7499)
+    assert np.max(np.abs(S[..., idx] - oracle_S(m, f[idx]))) < 1e-12
+    assert np.max(np.abs(S - S.transpose(1, 0, 2))) < 1e-12                      # reciprocal network, equal port impedances
+    cn.handle.set_tunable("gen_two_sided", 0)
+    S1 = m.run_sp(f)._S
+    assert cn.handle.kernel_info()["gen_two_sided"] == 0
+    assert np.max(np.abs(S - S1)) < 1e-13
+    cn.handle.set_tunable("gen_two_sided", 1)
+    assert np.array_equal(m.run_sp(f)._S, S) and cn.handle.kernel_info()["gen_two_sided"] == 1
+
+    fr = np.linspace(0.2e9, 8e9, 4000)
+    ref = None
+    os.environ["HVB_GEN_MODE"] = "3"          # ports at the two ends only: auto mode would not cut this chain (no saving)
+    for entry in ("run_sp", "run_sp_async", "run_sp_resident"):
+        mr = circuits.build_lc_chain(hv, 44, None, coupling=1e-15)
+        if ref is None:
+            ref = oracle_S(mr, fr)
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")                                       # no singular-system warning: the system is fine
+            if entry == "run_sp":
+                Sr = mr.run_sp(fr)._S
+            elif entry == "run_sp_async":
+                Sr = mr.run_sp_async(fr).result()._S
+            else:
+                Sr = mr.run_sp_resident(fr).cpu().numpy()[0]
+        ki = mr._compiled().handle.kernel_info()
+        assert ki["kernel_class"] == 3 and ki["gen_rolled"] == 1 and ki["gen_two_sided"] == 0, (entry, ki)   # went back for good
+        assert np.all(np.abs(Sr - ref) <= 1e-12 + 1e-10 * np.abs(ref)), entry
 
 
 def test_full_size_monte_carlo_and_sweep_properties():
