@@ -66,6 +66,7 @@ struct GenKernel {
     HvbJitKernel k;
     DevBuf rows, itab, dtab;
     bool rolled = false, scratch_acc = false, two_sided = false;
+    int occ_class = 0;                                   // 0: fewest spills, 1: one more resident CTA per SM (see ensure_gen_kernel)
     int ctas_per_sm = 0, n_cases = 0, threads = 128;
     size_t smem = 0;
     long long flops = 0;
@@ -106,6 +107,7 @@ struct hvb_plan {
     std::vector<double> def_consts;                    // plans created from a stamp table: the run parameters it implies
     std::vector<int32_t> def_prefs;
     bool pending = false;                              // hvb_run_host_async queued, not yet waited for
+    int gen_occ_matters = -1;                          // -1 unknown yet, 0 the generated kernel has one register budget, 1 two
     bool allow_two_sided = true;                       // chain kernels: cleared for good once a two-sided run flagged a point
     hvb_run_args pend_args{}; double* pend_out = nullptr;   // the queued call, should hvb_run_host_wait have to repeat it
     bool staged_valid = false;                         // h_in / inbuf hold the inputs of the last hvb_run_host call
@@ -297,10 +299,22 @@ static std::map<std::string, std::shared_ptr<std::vector<char>>> g_cubins;
 
 // The generated code is specialised on the run's parameter layout (prefs) AND on the values of its constants (baked in
 // as literals / constant-bank entries): a plan keeps one compiled variant per distinct (prefs, consts) it has seen.
-static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs, const double* consts) {
+//
+// `points` = points of ONE launch when the caller launches the whole job at once (hvb_run_device), 0 for the host pipeline
+// (its tiles are cut to one wave of the kernel).  The two-sided row loop exists in two register budgets: 168 registers
+// (3 CTAs of 128 per SM, no spills: fastest per thread) and 128 registers (4 CTAs per SM).  A launch of only a few waves
+// is dominated by its last, partly filled wave, and there the higher occupancy wins -- measured on configs[4], 125 000
+// points (one GPU's share at N = 8): 0.467 ms -> 0.404 ms; 250 000: 0.834 -> 0.777; 1 000 000: 3.04 ms against 3.45.
+static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs, const double* consts, int64_t points = 0) {
     const size_t np = (size_t)pl->d.n_prefs * 2, nc = (size_t)pl->d.n_consts * 2;
+    int cls = 0;
+    if (pl->gen_occ_matters != 0 && pl->sm_count > 0) {
+        const int64_t wave = (int64_t)3 * 128 * pl->sm_count;
+        cls = (points > wave && points <= 6 * wave) ? 1 : 0;
+    }
     auto same = [&](const GenKernel* v) {
-        return v->prefs.size() == np && (np == 0 || memcmp(v->prefs.data(), prefs, np * 4) == 0) &&
+        return v->occ_class == cls &&
+               v->prefs.size() == np && (np == 0 || memcmp(v->prefs.data(), prefs, np * 4) == 0) &&
                v->consts.size() == nc && (nc == 0 || memcmp(v->consts.data(), consts, nc * 8) == 0);
     };
     if (pl->gk && same(pl->gk) && (pl->allow_two_sided || !pl->gk->two_sided)) return HVB_OK;
@@ -315,6 +329,7 @@ static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs, const double* c
     std::string err;
     pl->gen.run_consts.assign(consts, consts + nc);
     pl->gen.allow_two_sided = pl->allow_two_sided;
+    pl->gen.occ_class = cls;
     const char* md = getenv("HVB_GEN_MODE");
     const int grc = pl->gen_hub ? hvb_gen_hub_source(pl->gen, prefs, hvb_gen_prelude(), &res, &err)
                                 : hvb_gen_source(pl->gen, prefs, md ? atoi(md) : 0, hvb_gen_prelude(), &res, &err);
@@ -336,6 +351,9 @@ static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs, const double* c
     if (hvb_jit_load(*cubin, res.kernel_name.c_str(), &gk->k, &err) != 0) return fail(HVB_ERR_CUDA, "%s", err.c_str());
     gk->rolled = res.rolled; gk->scratch_acc = res.scratch_acc; gk->n_cases = res.n_cases; gk->flops = res.flops_per_solve;
     gk->two_sided = res.two_sided;
+    // only the two-sided row loop comes in two register budgets; for every other form the classes are one kernel
+    pl->gen_occ_matters = res.two_sided ? 1 : 0;
+    gk->occ_class = res.two_sided ? cls : 0;
     gk->prefs.assign(prefs, prefs + np);
     gk->consts.assign(consts, consts + nc);
     pl->threads = res.threads;
@@ -591,7 +609,7 @@ extern "C" int hvb_plan_set_tunable(hvb_plan* pl, const char* name, double value
     else if (n == "band_tile_waves") pl->env_tile_waves = value;
     else if (n == "copy2d") pl->env_copy2d = value != 0.0;
     else if (n == "band_pfb") pl->env_band_pfb = (int)value;
-    else if (n == "gen_two_sided") { pl->allow_two_sided = value != 0.0; pl->gk = nullptr; }
+    else if (n == "gen_two_sided") { pl->allow_two_sided = value != 0.0; pl->gk = nullptr; pl->gen_occ_matters = -1; }
     else return fail(HVB_ERR_ARG, "unknown tunable '%s'", name);
     return HVB_OK;
 }
@@ -760,7 +778,7 @@ extern "C" int hvb_run_device(hvb_plan* pl, const hvb_run_args* a_in, double* d_
     if (pl->d.ncols <= pl->d.n || (!pl->kernel && pl->kclass != 3)) return fail(HVB_ERR_ARG, "plan has no right-hand sides (dump plan)");
     CU(cudaSetDevice(pl->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (pl->kclass == 3 && (rc = ensure_gen_kernel(pl, a->prefs, a->consts)) != HVB_OK) return rc;
+    if (pl->kclass == 3 && (rc = ensure_gen_kernel(pl, a->prefs, a->consts, a->nF * a->nS)) != HVB_OK) return rc;
     rc = push_params(pl, a, st);
     if (rc) return rc;
     HvbDev D = make_dev(pl);

@@ -103,6 +103,21 @@ def test_two_sided_chain_kernel_at_size_and_its_refusal_path():
     cn.handle.set_tunable("gen_two_sided", 1)
     assert np.array_equal(m.run_sp(f)._S, S) and cn.handle.kernel_info()["gen_two_sided"] == 1
 
+    # device-resident entry, whole job in one launch: a launch of a few waves gets the 4-CTA register budget (csrc/hvb_api.cu,
+    # ensure_gen_kernel), a deep one the 3-CTA budget; same arithmetic either way
+    Sa = m.run_sp_resident(f[:125_000]).cpu().numpy()[0]
+    ka = cn.handle.kernel_info()
+    Sb = m.run_sp_resident(f).cpu().numpy()[0]
+    kb = cn.handle.kernel_info()
+    m2, f2 = circuits.build_c5(hv, nF=600_000)
+    Sc = m2.run_sp_resident(f2[:600_000]).cpu().numpy()[0]
+    kc = m2._compiled().handle.kernel_info()
+    assert ka["gen_two_sided"] == kb["gen_two_sided"] == kc["gen_two_sided"] == 1
+    assert ka["ctas_per_sm"] == kb["ctas_per_sm"] == 4 and kc["ctas_per_sm"] == 3 and ka["regs"] <= 128 < kc["regs"], (ka, kb, kc)
+    assert np.max(np.abs(Sa - S[..., :125_000])) < 1e-13 and np.max(np.abs(Sb - S)) < 1e-13
+    idx2 = np.arange(0, 600_000, 14999)
+    assert np.max(np.abs(Sc[..., idx2] - oracle_S(m2, f2[idx2]))) < 1e-12
+
     fr = np.linspace(0.2e9, 8e9, 4000)
     ref = None
     os.environ["HVB_GEN_MODE"] = "3"          # ports at the two ends only: auto mode would not cut this chain (no saving)

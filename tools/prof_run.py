@@ -12,6 +12,8 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 dev = torch.device("cuda", 0)
 jobs = bench.make_jobs(hv, wl)
 m, f, drivers, values = jobs[0]
+if os.environ.get("PROF_POINTS"):                 # a rank's share of a strong-scaled sweep
+    f = f[:int(os.environ["PROF_POINTS"])]
 if wl == "c4":
     values = values[:1250]
 cn = m._compiled()
