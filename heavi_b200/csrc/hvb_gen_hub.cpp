@@ -5,13 +5,17 @@
 // two-terminal parts and lines -- each hanging off one core node, ports anywhere on the chains or on core
 // nodes.  The dense kernels treat such a system as a full (N+M-1)^2 matrix; here the generated code
 //   1. evaluates the S_ij(f) traces (device B-splines: knot interval + basis once, a 4-term dot per trace),
-//      and turns S into Y = (1/Z0)(I-S)(I+S)^-1 by an LU solve with partial pivoting of (I+S)^T X^T = (I-S)^T
-//      in a per-thread shared-memory tile;
+//      and turns S into Y = (1/Z0)(I-S)(I+S)^-1 = (1/Z0)(2 (I+S)^-1 - I) by an IN-PLACE Gauss-Jordan inversion with
+//      partial pivoting of I+S in a per-thread Pn x Pn shared-memory tile;
 //   2. eliminates every chain front to back in registers (the tridiagonal recurrence of kernel D with partial
-//      pivoting inside the chain), folding it into its core node's diagonal and right-hand sides;
-//   3. solves the remaining Pn x Pn core system for all ports with a second pivoted LU in the same tile;
+//      pivoting inside the chain), folding it into its core node's diagonal; a port's right-hand side reaches the
+//      core at ONE node (its chain's, or its own), so the core's right-hand sides are P scalars in registers;
+//   3. inverts the remaining Pn x Pn core matrix in place in the same tile: core voltage i of excitation q is
+//      Z[i][node(q)] * b_q;
 //   4. substitutes back along the chains that carry ports and forms S (solvers/spfn.py:159-176).
-// Work per point: two Pn^3-sized solves + O(chain rows), instead of (chain rows + Pn)^3.
+// Work per point: two Pn^3-sized inversions + O(chain rows), instead of (chain rows + Pn)^3.  The tile holds the
+// matrix only -- 1 KB per thread for an 8-port block, so six 32-thread CTAs fit an SM (the first version kept the
+// right-hand sides beside the matrix: 2 KB per thread, three CTAs).
 //
 // Pivoting: partial pivoting inside each chain and inside both dense solves.  The last chain row is NOT
 // exchanged with its core row (that would need a spare dense row per chain); instead the step checks the
@@ -221,11 +225,11 @@ struct HubGen {
     const GenPlan& g;
     const Hub& h;
     const int32_t* prefs;
-    int LD;                                        // columns of the shared-memory tile: Pn + max(Pn, P)
+    int LD;                                        // columns of the shared-memory tile: Pn (the matrix alone)
     long long flops = 0;
     std::string decl;                              // value declarations + code, emitted once per point
 
-    HubGen(const GenPlan& g_, const Hub& h_, const int32_t* p) : g(g_), h(h_), prefs(p) { LD = h.Pn + std::max(h.Pn, g.P); }
+    HubGen(const GenPlan& g_, const Hub& h_, const int32_t* p) : g(g_), h(h_), prefs(p) { LD = h.Pn; }
 
     std::string sm(int i, int c) const { return fmt("gsm[%d * GEN_THREADS + threadIdx.x]", i * LD + c); }
 
@@ -360,8 +364,7 @@ int hvb_gen_hub_source(const GenPlan& g, const int32_t* prefs, const char* prelu
                 const int32_t* t = &g.spl_trace[(size_t)tr * 4];
                 b += fmt("      { const double2 rg = D.pv.spl_range[%d]; const cplx s = f < rg.x ? D.pv.spl_fill[%d] : (f > rg.y ? D.pv.spl_fill[%d] : spline_dot(D.pv.spl_c + %d, sb));\n",
                          tr, 2 * tr, 2 * tr + 1, t[2]);
-                b += fmt("        %s = cmk(%s + s.x, s.y); %s = cmk(%s - s.x, -s.y); }\n", G.sm(j, i).c_str(), i == j ? "1.0" : "0.0",
-                         G.sm(j, Pn + i).c_str(), i == j ? "1.0" : "0.0");
+                b += fmt("        %s = cmk(%s + s.x, s.y); }\n", G.sm(i, j).c_str(), i == j ? "1.0" : "0.0");
                 G.flops += 16;
             }
         b += "    }\n";
@@ -369,30 +372,35 @@ int hvb_gen_hub_source(const GenPlan& g, const int32_t* prefs, const char* prelu
         for (int i = 0; i < Pn; ++i)
             for (int j = 0; j < Pn; ++j) {
                 b += fmt("    { const cplx s = %s;\n", G.param(h.coop_first + i * Pn + j).c_str());
-                b += fmt("      %s = cmk(%s + s.x, s.y); %s = cmk(%s - s.x, -s.y); }\n", G.sm(j, i).c_str(), i == j ? "1.0" : "0.0",
-                         G.sm(j, Pn + i).c_str(), i == j ? "1.0" : "0.0");
+                b += fmt("      %s = cmk(%s + s.x, s.y); }\n", G.sm(i, j).c_str(), i == j ? "1.0" : "0.0");
             }
     }
-    b += fmt("    gen_dense_lu<%d, %d, %d>(gsm + threadIdx.x, pmin, pmax);          // tile columns %d.. now hold X^T\n", Pn, Pn, LD, Pn);
-    G.flops += 8LL * (Pn * Pn * Pn / 3 + Pn * Pn * Pn + Pn * Pn * Pn / 2);
-    // core matrix A[i][j] = Y[i][j] = X[i][j] / Z0 = X^T[j][i] / Z0 (+ whatever else is stamped on core cells): read from
-    // the tile's right half, written to its left half; the right half then takes the core's right-hand sides
+    b += fmt("    gen_dense_inv<%d, %d>(gsm + threadIdx.x, pmin, pmax);              // the tile now holds W = (I + S)^-1\n", Pn, LD);
+    G.flops += 8LL * Pn * Pn * Pn + 8LL * Pn * Pn;
+    // core matrix A[i][j] = Y[i][j] = (2 W[i][j] - delta_ij) / Z0 (+ whatever else is stamped on core cells), in place
     b += "    { const cplx iz = crecip_np(" + G.cst(h.coop_z0) + ");\n";
     for (int i = 0; i < Pn; ++i)
         for (int j = 0; j < Pn; ++j) {
-            b += fmt("      { const cplx x = %s; cplx y = (iz.y == 0.0) ? cscale(x, iz.x) : cmul(iz, x);", G.sm(j, Pn + i).c_str());
+            b += fmt("      { cplx x = %s; x.x = fma(2.0, x.x, %s); x.y = 2.0 * x.y; cplx y = (iz.y == 0.0) ? cscale(x, iz.x) : cmul(iz, x);",
+                     G.sm(i, j).c_str(), i == j ? "-1.0" : "0.0");
             const std::string extra = G.cell(h.core_row[i], h.core_row[j]);
             if (!extra.empty()) b += " const cplx e = " + extra + "; y.x += e.x; y.y += e.y;";
             b += " " + G.sm(i, j) + " = y; }\n";
         }
     b += "    }\n";
+    // right-hand sides of the core system: port q's column has ONE entry, at core node cq[q] (its own node, or its chain's)
     std::string atdecl;
-    for (int i = 0; i < Pn; ++i)
-        for (int q = 0; q < P; ++q) {
-            // a port directly on a core node: its source entry
-            const std::string src = (g.port_rows[3 * q] == h.core_row[i]) ? G.cell0(h.core_row[i], g.n + q) : std::string("cmk(0.0, 0.0)");
-            b += fmt("    %s = %s;\n", G.sm(i, Pn + q).c_str(), src.c_str());
+    std::vector<int> cq(P, -1);
+    for (int q = 0; q < P; ++q) {
+        const int r = g.port_rows[3 * q];
+        if (h.core_of_row[r] >= 0) {
+            cq[q] = h.core_of_row[r];
+            b += fmt("    const cplx rb%d = %s;\n", q, G.cell0(r, g.n + q).c_str());
+        } else {
+            cq[q] = h.chains[h.chain_of_row[r]].core;
+            atdecl += fmt("    cplx rb%d = cmk(0.0, 0.0);\n", q);
         }
+    }
 
     // ---- 2. chains: front-to-back elimination in registers, folded into the core node -------------------------------
     std::string chdecl;
@@ -448,8 +456,7 @@ int hvb_gen_hub_source(const GenPlan& g, const int32_t* prefs, const char* prelu
                 b += fmt("        { cplx d = %s; cfnma(d, m, c1); %s = d; }\n", G.sm(ci, ci).c_str(), G.sm(ci, ci).c_str());
                 for (int qi = 0; qi < nq; ++qi) {
                     const int q = c.ports[qi];
-                    b += fmt("        { cplx d = %s; cfnma(d, m, yc%d); %s = d; uy%d_%d_%d = yc%d; }\n", G.sm(ci, Pn + q).c_str(), qi,
-                             G.sm(ci, Pn + q).c_str(), (int)k, t, qi, qi);
+                    b += fmt("        cfnma(rb%d, m, yc%d); uy%d_%d_%d = yc%d;\n", q, qi, (int)k, t, qi, qi);
                     G.flops += 8;
                 }
                 b += fmt("        ui%d_%d = inv; ua%d_%d = c1; ub%d_%d = cmk(0.0, 0.0); }\n", (int)k, t, (int)k, t, (int)k, t);
@@ -460,8 +467,9 @@ int hvb_gen_hub_source(const GenPlan& g, const int32_t* prefs, const char* prelu
     }
 
     // ---- 3. core solve ----------------------------------------------------------------------------------------------------
-    b += fmt("    gen_dense_lu<%d, %d, %d>(gsm + threadIdx.x, pmin, pmax);          // tile columns %d.. now hold the core voltages\n", Pn, P, LD, Pn);
-    G.flops += 8LL * (Pn * Pn * Pn / 3 + Pn * Pn * P + Pn * Pn * P / 2);
+    b += fmt("    gen_dense_inv<%d, %d>(gsm + threadIdx.x, pmin, pmax);              // the tile now holds Z = (core matrix)^-1\n", Pn, LD);
+    G.flops += 8LL * Pn * Pn * Pn + 8LL * Pn * Pn;
+    auto xcore = [&](int i, int q) { return fmt("cmul(%s, rb%d)", G.sm(i, cq[q]).c_str(), q); };   // core voltage i of excitation q
 
     // ---- 4. back substitution along the chains, S = (2 V_sig - delta) sqrt|Zi| / sqrt|Zj| ---------------------------------
     auto emit_S = [&](int pj, int i, const std::string& x) {
@@ -476,7 +484,7 @@ int hvb_gen_hub_source(const GenPlan& g, const int32_t* prefs, const char* prelu
     for (int q = 0; q < P; ++q) {
         const int r = g.port_rows[3 * q];
         if (h.core_of_row[r] >= 0)
-            for (int i = 0; i < P; ++i) b += emit_S(q, i, G.sm(h.core_of_row[r], Pn + i));
+            for (int i = 0; i < P; ++i) { b += emit_S(q, i, xcore(h.core_of_row[r], i)); G.flops += 6; }
     }
     for (size_t k = 0; k < h.chains.size(); ++k) {
         const Chain& c = h.chains[k];
@@ -485,7 +493,8 @@ int hvb_gen_hub_source(const GenPlan& g, const int32_t* prefs, const char* prelu
         int first = M;                               // farthest row a port sits on
         for (int q : c.ports) first = std::min(first, h.pos_in_chain[g.port_rows[3 * q]]);
         for (int i = 0; i < P; ++i) {                 // excitation i
-            b += fmt("    { cplx x1 = %s, x2 = cmk(0.0, 0.0);\n", G.sm(c.core, Pn + i).c_str());
+            b += fmt("    { cplx x1 = %s, x2 = cmk(0.0, 0.0);\n", xcore(c.core, i).c_str());
+            G.flops += 6;
             for (int t = M - 1; t >= first; --t) {
                 int qi_of_i = -1;
                 for (size_t qi = 0; qi < c.ports.size(); ++qi) if (c.ports[qi] == i) qi_of_i = (int)qi;
@@ -511,14 +520,14 @@ int hvb_gen_hub_source(const GenPlan& g, const int32_t* prefs, const char* prelu
            "__device__ __forceinline__ cplx gen_ind(double w, cplx p0) {\n"
            "    if (p0.y == 0.0) return cmk(0.0, -rcp_fast(__dmul_rn(w, p0.x)));\n"
            "    return cdiv_np(cmk(1.0, 0.0), cmk(-__dmul_rn(w, p0.y), __dmul_rn(w, p0.x)));\n}\n"
-           "// Dense LU with partial pivoting of a per-thread tile in shared memory: NR rows, NR matrix columns followed by NB\n"
-           "// right-hand-side columns (row stride LD), element e of this thread at t[e * GEN_THREADS].  On return the right-hand-side\n"
-           "// columns hold the solutions.  Rows are exchanged physically (a handful of words), so every index below is a loop\n"
-           "// counter -- no per-thread index arrays, nothing in local memory.\n"
-           "template <int NR, int NB, int LD>\n"
-           "__device__ __forceinline__ void gen_dense_lu(cplx* __restrict__ t, double& pmin, double& pmax) {\n"
+           "// In-place inverse of a per-thread NR x NR tile in shared memory (row stride LD, element e of this thread at\n"
+           "// t[e * GEN_THREADS]): Gauss-Jordan with partial pivoting.  Rows are exchanged physically while eliminating; the\n"
+           "// exchanges are undone on the columns afterwards, last first (the inverse of P A is A^-1 P^-1).  Every index is a\n"
+           "// loop counter or one dynamic row / column: no per-thread index arrays in local memory.\n"
+           "template <int NR, int LD>\n"
+           "__device__ __forceinline__ void gen_dense_inv(cplx* __restrict__ t, double& pmin, double& pmax) {\n"
            "#define TE(i, c) t[((i) * LD + (c)) * GEN_THREADS]\n"
-           "    // every loop has compile-time bounds and is unrolled: tile addresses are immediates except for the pivot row p\n"
+           "    int perm[NR];                                          // only ever indexed by unrolled loop counters: registers\n"
            "#pragma unroll\n"
            "    for (int k = 0; k < NR; ++k) {\n"
            "        int p = k;\n"
@@ -531,36 +540,30 @@ int hvb_gen_hub_source(const GenPlan& g, const int32_t* prefs, const char* prelu
            "            if (m > best) { best = m; p = i; }\n"
            "        }\n"
            "        pmin = fmin(pmin, best); pmax = fmax(pmax, best);\n"
+           "        perm[k] = p;\n"
            "        if (p != k) {\n"
            "#pragma unroll\n"
-           "            for (int c = k; c < NR + NB; ++c) { const cplx a = TE(k, c); TE(k, c) = TE(p, c); TE(p, c) = a; }\n"
+           "            for (int c = 0; c < NR; ++c) { const cplx a = TE(k, c); TE(k, c) = TE(p, c); TE(p, c) = a; }\n"
            "        }\n"
            "        const cplx inv = crecip_fast(TE(k, k));\n"
-           "        TE(k, k) = inv;\n"
-           "        cplx pr[NR + NB];                                  // the pivot row stays in registers for this step\n"
+           "        cplx pr[NR];                                       // the scaled pivot row stays in registers for this step\n"
            "#pragma unroll\n"
-           "        for (int c = k + 1; c < NR + NB; ++c) pr[c] = TE(k, c);\n"
+           "        for (int c = 0; c < NR; ++c) { pr[c] = (c == k) ? inv : cmul(TE(k, c), inv); TE(k, c) = pr[c]; }\n"
            "#pragma unroll 1\n"
-           "        for (int i = k + 1; i < NR; ++i) {                 // rows stay a loop: bounded register use\n"
+           "        for (int i = 0; i < NR; ++i) {                     // rows stay a loop: bounded register use and code size\n"
+           "            if (i == k) continue;\n"
            "            cplx* __restrict__ rowp = t + i * (LD * GEN_THREADS);\n"
-           "            const cplx m = cmul(rowp[k * GEN_THREADS], inv);\n"
+           "            const cplx m = rowp[k * GEN_THREADS];\n"
            "#pragma unroll\n"
-           "            for (int c = k + 1; c < NR + NB; ++c) { cplx v = rowp[c * GEN_THREADS]; cfnma(v, m, pr[c]); rowp[c * GEN_THREADS] = v; }\n"
+           "            for (int c = 0; c < NR; ++c) { cplx v = (c == k) ? cmk(0.0, 0.0) : rowp[c * GEN_THREADS]; cfnma(v, m, pr[c]); rowp[c * GEN_THREADS] = v; }\n"
            "        }\n"
            "    }\n"
            "#pragma unroll\n"
            "    for (int k = NR - 1; k >= 0; --k) {\n"
-           "        const cplx inv = TE(k, k);\n"
-           "        cplx ur[NR];\n"
+           "        const int p = perm[k];\n"
+           "        if (p != k) {\n"
            "#pragma unroll\n"
-           "        for (int j = k + 1; j < NR; ++j) ur[j] = TE(k, j);\n"
-           "#pragma unroll 1\n"
-           "        for (int c = NR; c < NR + NB; ++c) {\n"
-           "            cplx* __restrict__ colp = t + c * GEN_THREADS;\n"
-           "            cplx v = colp[k * (LD * GEN_THREADS)];\n"
-           "#pragma unroll\n"
-           "            for (int j = k + 1; j < NR; ++j) cfnma(v, ur[j], colp[j * (LD * GEN_THREADS)]);\n"
-           "            colp[k * (LD * GEN_THREADS)] = cmul(v, inv);\n"
+           "            for (int i = 0; i < NR; ++i) { const cplx a = TE(i, k); TE(i, k) = TE(i, p); TE(i, p) = a; }\n"
            "        }\n"
            "    }\n"
            "#undef TE\n}\n\n";

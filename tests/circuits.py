@@ -365,10 +365,13 @@ def build_sweep(hv):
     return m, sweep, np.linspace(1e9, 4e9, 257)
 
 
-def build_hub(hv, n_block: int = 4, chain_rows=(2, 1, 0, 3), port_on=(0, 0, None, 1), seed: int = 0, nF: int = 33):
+def build_hub(hv, n_block: int = 4, chain_rows=(2, 1, 0, 3), port_on=(0, 0, None, 1), seed: int = 0, nF: int = 33,
+              scale: float = 1.0, diag_bias: float = 0.0):
     """An N-port S block (analytic passive S(f) given as Python callables) whose node k carries a chain of
     `chain_rows[k]` extra nodes; `port_on[k]` = position on that chain (0 = far end) of a port, None = no port,
-    and for a chain of 0 rows a port value of 0 puts the port on the block node itself."""
+    and for a chain of 0 rows a port value of 0 puts the port on the block node itself.  `scale` / `diag_bias`:
+    S -> scale * S - diag_bias * I (still passive for scale * 0.7 + diag_bias < 1); with diag_bias near 1 the diagonal of
+    I + S is as small as its off-diagonal part, so the dense inversions have to exchange rows."""
     rng = np.random.default_rng(500 + seed)
     m = _model(hv)
     Q, _ = np.linalg.qr(rng.normal(size=(n_block, n_block)) + 1j * rng.normal(size=(n_block, n_block)))
@@ -376,7 +379,7 @@ def build_hub(hv, n_block: int = 4, chain_rows=(2, 1, 0, 3), port_on=(0, 0, None
     gain = rng.uniform(0.2, 0.7, n_block)
 
     def S_of(i, j):
-        return lambda f: np.einsum("k,kf,k->f", Q[i, :], gain[:, None] * np.exp(-2j * np.pi * np.asarray(f)[None, :] * tau[:, None]), Q[j, :])
+        return lambda f: scale * np.einsum("k,kf,k->f", Q[i, :], gain[:, None] * np.exp(-2j * np.pi * np.asarray(f)[None, :] * tau[:, None]), Q[j, :]) - (diag_bias if i == j else 0.0)
 
     inner = [m.node() for _ in range(n_block)]
     for k in range(n_block):

@@ -251,7 +251,7 @@ def test_hub_kernel_config3_matches_reference_golden():
     g = golden("c3_touchstone")
     m = REG["c3_touchstone"]()
     S, f32, status, gen = hub_sim(m, g["f"])
-    assert status == 0 and gen["smem_bytes"] == 8 * 16 * 32 * 16 and gen["threads"] == 32
+    assert status == 0 and gen["smem_bytes"] == 8 * 8 * 32 * 16 and gen["threads"] == 32      # the 8 x 8 matrix alone: 1 KB per thread
     assert np.array_equal(f32, g["f32"])
     frac, adjudicated, ext = parity_report(S[0], g["S"], g["S_ext"])
     assert frac == 1.0 and adjudicated and ext < 5e-14
@@ -269,6 +269,18 @@ def test_hub_kernel_structures_against_oracle(n_block, chain_rows, port_on):
     S, _, status, gen = hub_sim(m, f)
     assert status == 0
     assert np.max(np.abs(S[0] - oracle_S(m, f))) < 2e-13
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_hub_kernel_inversions_exchange_rows_when_they_must(seed):
+    """S -> 0.3 S - 0.995 I: the diagonal of I + S is no larger than its off-diagonal part (90-140 row exchanges over the 41 points
+    for these seeds, counted with the same rule on the host), so the in-place Gauss-Jordan
+    inversions (hvb_gen_hub.cpp, gen_dense_inv) have to pivot, and the column un-scrambling afterwards matters."""
+    m, f = circuits.build_hub(hv, 6, (1, 2, 0, 1, 0, 2), (0, 1, 0, 0, None, 0), seed=seed, nF=41, scale=0.3, diag_bias=0.995)
+    S, _, status, gen = hub_sim(m, f)
+    ref = oracle_S(m, f)
+    assert status == 0
+    assert np.all(np.abs(S[0] - ref) <= 1e-12 + 1e-10 * np.abs(ref)), np.max(np.abs(S[0] - ref))
 
 
 def test_hub_kernel_flags_an_unsafe_boundary_pivot_and_refuses_other_structures():
