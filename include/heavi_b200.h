@@ -189,7 +189,9 @@ void hvb_plan_destroy(hvb_plan* plan);
  * (HVB_CHUNK_MB, HVB_MIN_SLAB, HVB_STATS_MB, HVB_BAND_TILE_WAVES, HVB_COPY2D, HVB_BAND_PFB); this call
  * changes them for one plan afterwards.  Names: "chunk_mb" (bytes of S per pipeline tile, MiB; 0 = default),
  * "min_slab" (points), "stats_mb" (HBM budget of hvb_run_stats_host, MiB), "band_tile_waves", "copy2d" (0/1),
- * "band_pfb" (records prefetched by the banded kernel; -1 = automatic).  Results never depend on them. */
+ * "band_pfb" (records prefetched by the banded kernel; -1 = automatic), "gen_two_sided" (0: keep a long chain on
+ * the one-sided generated kernel; the library sets it itself once a two-sided run refused a point).  Results never
+ * depend on them beyond rounding. */
 int hvb_plan_set_tunable(hvb_plan* plan, const char* name, double value);
 
 /* S-parameters with HOST buffers: uploads f / samples / tables, runs the kernels in pipelined
