@@ -252,6 +252,18 @@ def test_hub_structures_against_oracle_and_library_kernels(n_block, chain_rows, 
     assert np.max(np.abs(S - library_variant(m).run(f)[0])) < 1e-12
 
 
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_hub_kernel_inversions_exchange_rows_when_they_must(seed):
+    """S -> 0.3 S - 0.995 I (tests/test_codegen.py, same case on the CPU): both in-place inversions of kernel E pivot at
+    most points; the result must not care."""
+    m, f = circuits.build_hub(hv, 6, (1, 2, 0, 1, 0, 2), (0, 1, 0, 0, None, 0), seed=seed, nF=513, scale=0.3, diag_bias=0.995)
+    S = m.run_sp(f)._S
+    ki = m._compiled().handle.kernel_info()
+    assert ki["kernel_class"] == 3 and ki["gen_hub"] == 1 and ki["smem_bytes"] == 6 * 6 * 32 * 16
+    ref = oracle_S(m, f)
+    assert np.all(np.abs(S - ref) <= 1e-12 + 1e-10 * np.abs(ref)), np.max(np.abs(S - ref))
+
+
 def test_hub_kernel_unsafe_pivot_falls_back_to_the_dense_kernel():
     m = hv.Model(suppress_loadbar=True)
     b, c, mid = m.node(), m.node(), m.node()
