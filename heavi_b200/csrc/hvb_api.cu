@@ -301,10 +301,11 @@ static std::map<std::string, std::shared_ptr<std::vector<char>>> g_cubins;
 // as literals / constant-bank entries): a plan keeps one compiled variant per distinct (prefs, consts) it has seen.
 //
 // `points` = points of ONE launch when the caller launches the whole job at once (hvb_run_device), 0 for the host pipeline
-// (its tiles are cut to one wave of the kernel).  The two-sided row loop exists in two register budgets: 168 registers
-// (3 CTAs of 128 per SM, no spills: fastest per thread) and 128 registers (4 CTAs per SM).  A launch of only a few waves
-// is dominated by its last, partly filled wave, and there the higher occupancy wins -- measured on configs[4], 125 000
-// points (one GPU's share at N = 8): 0.467 ms -> 0.404 ms; 250 000: 0.834 -> 0.777; 1 000 000: 3.04 ms against 3.45.
+// (its tiles are cut to one wave of the kernel).  The two-sided row loop exists in two register budgets: the compiler's
+// own (168 registers for configs[4]: 384 threads per SM, fastest per thread; capped at 168 if the natural allocation is
+// larger) and 128 registers (512 threads per SM, spills).  A launch of only a few waves is dominated by its last, partly
+// filled wave, and there the higher occupancy wins -- measured on configs[4], 125 000 points (one GPU's share at
+// N = 8): 0.445 ms -> 0.404 ms; 250 000: 0.784 -> 0.777; 1 000 000: 2.87 ms against 3.45.
 static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs, const double* consts, int64_t points = 0) {
     const size_t np = (size_t)pl->d.n_prefs * 2, nc = (size_t)pl->d.n_consts * 2;
     int cls = 0;
@@ -331,24 +332,33 @@ static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs, const double* c
     pl->gen.allow_two_sided = pl->allow_two_sided;
     pl->gen.occ_class = cls;
     const char* md = getenv("HVB_GEN_MODE");
-    const int grc = pl->gen_hub ? hvb_gen_hub_source(pl->gen, prefs, hvb_gen_prelude(), &res, &err)
-                                : hvb_gen_source(pl->gen, prefs, md ? atoi(md) : 0, hvb_gen_prelude(), &res, &err);
-    if (grc != 0) return fail(HVB_ERR_UNSUPPORTED, "kernel generator: %s", err.c_str());
-    std::shared_ptr<std::vector<char>> cubin;
-    {
-        std::lock_guard<std::mutex> lk(g_cubin_mu);
-        auto it = g_cubins.find(res.src);
-        if (it != g_cubins.end()) cubin = it->second;
-    }
-    if (!cubin) {
-        cubin = std::make_shared<std::vector<char>>();
-        std::string log;
-        if (hvb_jit_compile(res.src, cubin.get(), &log, &err) != 0) return fail(HVB_ERR_CUDA, "NVRTC: %.900s", err.c_str());
-        std::lock_guard<std::mutex> lk(g_cubin_mu);
-        g_cubins[res.src] = cubin;
-    }
     std::unique_ptr<GenKernel> gk(new GenKernel());
-    if (hvb_jit_load(*cubin, res.kernel_name.c_str(), &gk->k, &err) != 0) return fail(HVB_ERR_CUDA, "%s", err.c_str());
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int grc = pl->gen_hub ? hvb_gen_hub_source(pl->gen, prefs, hvb_gen_prelude(), &res, &err)
+                                    : hvb_gen_source(pl->gen, prefs, md ? atoi(md) : 0, hvb_gen_prelude(), &res, &err);
+        if (grc != 0) return fail(HVB_ERR_UNSUPPORTED, "kernel generator: %s", err.c_str());
+        std::shared_ptr<std::vector<char>> cubin;
+        {
+            std::lock_guard<std::mutex> lk(g_cubin_mu);
+            auto it = g_cubins.find(res.src);
+            if (it != g_cubins.end()) cubin = it->second;
+        }
+        if (!cubin) {
+            cubin = std::make_shared<std::vector<char>>();
+            std::string log;
+            if (hvb_jit_compile(res.src, cubin.get(), &log, &err) != 0) return fail(HVB_ERR_CUDA, "NVRTC: %.900s", err.c_str());
+            std::lock_guard<std::mutex> lk(g_cubin_mu);
+            g_cubins[res.src] = cubin;
+        }
+        if (hvb_jit_load(*cubin, res.kernel_name.c_str(), &gk->k, &err) != 0) return fail(HVB_ERR_CUDA, "%s", err.c_str());
+        // the compiler's own allocation is the fastest two-sided kernel as long as 384 threads stay resident per SM
+        if (attempt == 0 && res.two_sided && cls == 0 && gk->k.regs > 168 && !getenv("HVB_GEN_MINB")) {
+            hvb_jit_unload(&gk->k);
+            pl->gen.occ_class = 2;
+            continue;
+        }
+        break;
+    }
     gk->rolled = res.rolled; gk->scratch_acc = res.scratch_acc; gk->n_cases = res.n_cases; gk->flops = res.flops_per_solve;
     gk->two_sided = res.two_sided;
     // only the two-sided row loop comes in two register budgets; for every other form the classes are one kernel

@@ -655,8 +655,8 @@ static int gen_two_sided(const GenPlan& g, const int32_t* prefs, const char* pre
     GF.x_base = 2 * PM; GK.x_base = 3 * PM + 1;
     const int vslot = GF.x_base + PF;                                      // v = A[m][m+1] waits here while the back half is walked
     const int nslots = 4 * PM + 1;
-    int threads = (nslots * 128 * 16 > 48 * 1024) ? 64 : 128;
-    if (const char* e = getenv("HVB_GEN_THREADS")) { if (atoi(e) == 64 || atoi(e) == 128) threads = atoi(e); }   // experiments
+    int threads = (nslots * 64 * 16 > 48 * 1024) ? 32 : 64;               // measured on c5: 64 x 6 CTAs 2.87 ms, 128 x 3 3.03 ms
+    if (const char* e = getenv("HVB_GEN_THREADS")) { if (atoi(e) == 32 || atoi(e) == 64 || atoi(e) == 96 || atoi(e) == 128) threads = atoi(e); }   // experiments
     if (nslots * threads * 16 > 48 * 1024) { if (err) *err = "too many ports for the shared-memory sums"; return -1; }
 
     out->rolled = true; out->scratch_acc = true; out->two_sided = true; out->cut_row = m;
@@ -792,9 +792,13 @@ static int gen_two_sided(const GenPlan& g, const int32_t* prefs, const char* pre
     src += helper_text(true);
     src += tables_text(*out, nrows);
     out->kernel_name = "hvb_gen_kernel";
-    // measured on c5: 168 registers (3.04 ms per 1 M points) beat 128 (3.45 ms, spills) when the launch is many waves
-    // deep; a launch of a few waves is better off with one more resident CTA (g.occ_class, see ensure_gen_kernel)
-    int minb = (threads == 128 ? 3 : 6) + (g.occ_class ? (threads == 128 ? 1 : 2) : 0);
+    // Register budget (g.occ_class, chosen in ensure_gen_kernel).  0: the compiler's own allocation -- c5: 168 registers,
+    // 384 threads per SM, 2.87 ms per 1 M points; the same 168 registers forced through a minimum-CTA bound cost 5 %
+    // (3.02 ms).  2: capped at 168 registers (for netlists whose natural allocation is larger: fewer than 384 resident
+    // threads lose more than the spills cost).  1: 128 registers, 512 threads per SM (3.45 ms per 1 M points, spills) --
+    // better when the launch is only a few waves deep.
+    const int per_sm = 384 / threads;                                      // CTAs of the 168-register budget
+    int minb = g.occ_class == 1 ? per_sm + per_sm / 3 : (g.occ_class == 2 ? per_sm : 0);
     if (const char* e = getenv("HVB_GEN_MINB")) minb = atoi(e);
     src += fmt("extern \"C\" __global__ void __launch_bounds__(GEN_THREADS%s) hvb_gen_kernel(const HvbDev D) {\n", minb > 0 ? fmt(", %d", minb).c_str() : "");
     src += fmt("  __shared__ cplx gsm[%d * GEN_THREADS];\n", nslots);

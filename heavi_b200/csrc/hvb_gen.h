@@ -26,7 +26,8 @@ struct GenPlan {                       // host copy of what the generator reads 
     std::vector<int32_t> coops;        // [ncoops*8]
     std::vector<int32_t> spl_trace;    // [n_traces*4]
     bool allow_two_sided = true;       // false keeps a long chain on the one-sided row loop (modes 0 and 3)
-    int occ_class = 0;                 // two-sided row loop: 0 = 168 registers (3 CTAs of 128 per SM), 1 = 128 registers (4 CTAs)
+    int occ_class = 0;                 // two-sided row loop: 0 = the compiler's own register allocation, 1 = 128 registers
+                                       // (512 threads per SM), 2 = capped at 168 registers (384 threads per SM)
     int cut_col = -1;                  // generator-internal (half chains of the two-sided form): column index under which the
                                        // last row's coupling to the other half is filed; -1 in a plan that came from a desc
     void from_desc(const hvb_plan_desc& d);
