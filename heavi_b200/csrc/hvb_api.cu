@@ -21,6 +21,7 @@
 #include "hvb_kernels.h"
 #include "hvb_warp_shapes.h"
 
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -296,6 +297,7 @@ static bool gen_kernel_ok(const hvb_plan* pl) {
 // ---- kernel D: generate + compile (cached per process by source text) + load ------------------------
 static std::mutex g_cubin_mu;
 static std::map<std::string, std::shared_ptr<std::vector<char>>> g_cubins;
+static std::deque<std::string> g_cubin_order;            // insertion order: the cache holds the 256 most recent sources
 
 // The generated code is specialised on the run's parameter layout (prefs) AND on the values of its constants (baked in
 // as literals / constant-bank entries): a plan keeps one compiled variant per distinct (prefs, consts) it has seen.
@@ -325,7 +327,21 @@ static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs, const double* c
             pl->max_grid = v->ctas_per_sm * pl->sm_count;
             return HVB_OK;
         }
-    if (pl->gen_variants.size() >= 64) return fail(HVB_ERR_UNSUPPORTED, "more than 64 distinct constant sets on one plan: build a new plan (or use sample columns) for values that change per run");
+    if (pl->gen_variants.size() >= 64) {
+        // a plan keeps at most 64 compiled variants; the oldest one that is not current goes (sample columns, not
+        // constants, are the cheap way to change a value per run).  Its kernel may still be running on a caller's stream
+        // (hvb_run_device), hence the device-wide wait before the module is unloaded.
+        for (size_t i = 0; i < pl->gen_variants.size(); ++i) {
+            GenKernel* v = pl->gen_variants[i];
+            if (v == pl->gk) continue;
+            CU(cudaDeviceSynchronize());
+            v->rows.release(); v->itab.release(); v->dtab.release();
+            hvb_jit_unload(&v->k);
+            delete v;
+            pl->gen_variants.erase(pl->gen_variants.begin() + (long)i);
+            break;
+        }
+    }
     GenResult res;
     std::string err;
     pl->gen.run_consts.assign(consts, consts + nc);
@@ -348,7 +364,8 @@ static int ensure_gen_kernel(hvb_plan* pl, const int32_t* prefs, const double* c
             std::string log;
             if (hvb_jit_compile(res.src, cubin.get(), &log, &err) != 0) return fail(HVB_ERR_CUDA, "NVRTC: %.900s", err.c_str());
             std::lock_guard<std::mutex> lk(g_cubin_mu);
-            g_cubins[res.src] = cubin;
+            if (g_cubins.emplace(res.src, cubin).second) g_cubin_order.push_back(res.src);
+            while (g_cubin_order.size() > 256) { g_cubins.erase(g_cubin_order.front()); g_cubin_order.pop_front(); }
         }
         if (hvb_jit_load(*cubin, res.kernel_name.c_str(), &gk->k, &err) != 0) return fail(HVB_ERR_CUDA, "%s", err.c_str());
         // the compiler's own allocation is the fastest two-sided kernel as long as 384 threads stay resident per SM

@@ -195,6 +195,31 @@ def test_status_bits_statistics_and_resident_entry():
     assert Sr.is_cuda and np.array_equal(Sr.cpu().numpy()[0], m3.run_sp(f3)._S)
 
 
+def test_more_than_64_constant_sets_on_one_plan_evict_instead_of_failing():
+    """The generated code carries the run's constants, one compiled variant per distinct set; a plan keeps 64 of them and
+    drops the oldest beyond that (csrc/hvb_api.cu, ensure_gen_kernel).  Every set must give the result a fresh model with
+    those values gives, and a set that was evicted comes back bit-identical."""
+    m, f = circuits.build_c1(hv, nF=257)
+    cn = m._compiled()
+    consts, prefs, tables, samples = cn.resolve(f, None, None)
+    assert cn.handle.kernel_info()["kernel_class"] == 3 and len(consts) > 4 and consts[4] == 8e-10   # the SMD part's series inductance
+    first = None
+    for k in range(70):
+        c = consts.copy()
+        c[4] = consts[4] * (1.0 + 1e-2 * k)                      # one component value, 70 distinct constant sets
+        S, status = cn.handle.run_host(f, c, prefs, tables, samples)
+        assert status == 0
+        if k == 0:
+            first = S.copy()
+        if k in (1, 33, 69):
+            S2, _ = cn.handle.run_host(f, c, prefs, tables, samples)
+            assert np.array_equal(S, S2)
+            assert np.max(np.abs(S - first)) > 1e-9                  # the changed value did reach the kernel
+    S0, status = cn.handle.run_host(f, consts, prefs, tables, samples)  # set 0 was evicted (64 newer ones since)
+    assert status == 0 and np.array_equal(S0, first)
+    assert np.max(np.abs(S0[0] - oracle_S(m, f))) < 1e-12
+
+
 def test_parameter_layout_change_regenerates_the_kernel():
     """A callable that returns an array is a table, one that returns a scalar becomes a constant for that
     run (resolve_run): the value formulas are specialised on that layout, so the library keeps one kernel
