@@ -192,6 +192,43 @@ def test_monte_carlo_samples_tables_and_lossy_lines():
     assert status == 0 and np.max(np.abs(S2[0] - oracle_S(m2, f2))) < 1e-13
 
 
+@pytest.mark.parametrize("mode", [2, 3])
+def test_long_chain_with_samples_tables_and_lossy_lines_in_the_row_loop(mode):
+    """The row loop (one- and two-sided) with every parameter kind on a 60-section chain: Monte-Carlo sample columns,
+    host-tabulated callables, lossy lines (complex permittivity: the general, non-inlined line form) next to lossless
+    ones (the closed form), ports in the middle of the chain."""
+    rng = np.random.default_rng(77)
+    m = hv.Model(suppress_loadbar=True)
+    mc = hv.MonteCarlo()
+    K = 60
+    chain = [m.node() for _ in range(K + 1)]
+    for t in (0, 17, 18, 41, 60):
+        m.new_port(50.0, chain[t])
+    for k in range(K):
+        kind = k % 4
+        if kind == 0:
+            m.inductor(chain[k], chain[k + 1], mc.gaussian(float(10 ** rng.uniform(-9.3, -8.5)), 2e-11))
+        elif kind == 1:
+            m.transmissionline(chain[k], chain[k + 1], float(rng.uniform(30, 90)), float(rng.uniform(2, 4)), float(rng.uniform(1e-3, 9e-3)))
+        elif kind == 2:
+            m.transmissionline(chain[k], chain[k + 1], float(rng.uniform(30, 90)), complex(rng.uniform(2, 4), -0.04), float(rng.uniform(1e-3, 9e-3)))
+        else:
+            m.impedance(chain[k], chain[k + 1], lambda fr, r=float(rng.uniform(2, 20)): r + 1j * 1.5e-9 * fr)
+    for k in range(K + 1):
+        m.capacitor(chain[k], m.gnd, mc.uniform(0.2e-12, 0.6e-12) if k % 7 == 0 else float(10 ** rng.uniform(-12.6, -12)))
+    f = np.linspace(0.7e9, 5.5e9, 19)
+    np.random.seed(5)
+    values = mc.draw(3)
+    S, _, status, gen = sim(m, f, mode, mc._random_numbers, values)
+    assert status == 0 and gen["rolled"] and gen["two_sided"] == (mode == 3) and S.shape == (3, 5, 5, 19)
+    assert "gen_tline_lossless" in gen["src"] and "gen_tline_chain(" in gen["src"]
+    for s_ in range(3):
+        for r, v in zip(mc._random_numbers, values[s_]):
+            r._value = float(v)
+        ref = oracle_S(m, f)
+        assert np.all(np.abs(S[s_] - ref) <= 1e-12 + 1e-10 * np.abs(ref)), (s_, np.max(np.abs(S[s_] - ref)))
+
+
 def test_singular_and_nonfinite_points_set_status_bits():
     m = hv.Model(suppress_loadbar=True)
     a, b = m.quick_port(50), m.quick_port(50)
@@ -238,9 +275,9 @@ def test_generated_source_compiles_for_sm100a(name, mode):
 # ---------------------------------------------------------------------------------------------------
 # kernel E: hub netlists (one N-port S block + chains), heavi_b200/csrc/hvb_gen_hub.cpp
 # ---------------------------------------------------------------------------------------------------
-def hub_sim(m, f):
+def hub_sim(m, f, drivers=None, values=None):
     p = pl.compile_plan(m.stamp_table(), "auto")
-    consts, prefs, tables, samples = pl.resolve_run(p, np.asarray(f, dtype=np.float64))
+    consts, prefs, tables, samples = pl.resolve_run(p, np.asarray(f, dtype=np.float64), drivers, values)
     gen = engine.codegen_source(p, prefs, 0, consts=consts)
     assert gen["supported"] and gen["hub"], gen["reason"]
     S, f32, status = host_sim.run(gen, p.P, f, consts, prefs, tables, samples, p)
@@ -281,6 +318,45 @@ def test_hub_kernel_inversions_exchange_rows_when_they_must(seed):
     ref = oracle_S(m, f)
     assert status == 0
     assert np.all(np.abs(S[0] - ref) <= 1e-12 + 1e-10 * np.abs(ref)), np.max(np.abs(S[0] - ref))
+
+
+def test_hub_kernel_with_monte_carlo_samples_and_tabulated_parts():
+    """Kernel E with sample columns and host-tabulated callables on the chains, a port on a block node, a lossy line."""
+    rng = np.random.default_rng(9)
+    m = hv.Model(suppress_loadbar=True)
+    mc = hv.MonteCarlo()
+    nb = 4
+    Q, _ = np.linalg.qr(rng.normal(size=(nb, nb)) + 1j * rng.normal(size=(nb, nb)))
+    tau = rng.uniform(0.05e-9, 0.4e-9, nb)
+    gain = rng.uniform(0.2, 0.7, nb)
+
+    def S_of(i, j):
+        return lambda fr: np.einsum("k,kf,k->f", Q[i, :], gain[:, None] * np.exp(-2j * np.pi * np.asarray(fr)[None, :] * tau[:, None]), Q[j, :])
+
+    inner = [m.node() for _ in range(nb)]
+    a, a2 = m.node(), m.node()
+    m.new_port(50.0, a)
+    m.inductor(a, a2, mc.gaussian(1.2e-9, 4e-11))
+    m.capacitor(a2, m.gnd, mc.uniform(0.3e-12, 0.7e-12))
+    m.capacitor(a2, inner[0], 2.1e-12)
+    b = m.node()
+    m.new_port(75.0, b)
+    m.transmissionline(b, inner[1], 55.0, 2.9 - 0.03j, 0.007)
+    m.new_port(50.0, inner[2])                                   # a port directly on a block node
+    c = m.node()
+    m.impedance(c, inner[3], lambda fr: 4.0 + 1j * 1e-9 * fr)    # a stub without a port
+    m.capacitor(c, m.gnd, mc.gaussian(0.8e-12, 2e-14))
+    m.n_port_S(m.gnd, inner, [[S_of(i, j) for j in range(nb)] for i in range(nb)], 50.0)
+    f = np.linspace(0.9e9, 5e9, 21)
+    np.random.seed(12)
+    values = mc.draw(4)
+    S, _, status, gen = hub_sim(m, f, mc._random_numbers, values)
+    assert status == 0 and gen["hub"] and S.shape == (4, 3, 3, 21)
+    for s_ in range(4):
+        for r, v in zip(mc._random_numbers, values[s_]):
+            r._value = float(v)
+        ref = oracle_S(m, f)
+        assert np.all(np.abs(S[s_] - ref) <= 1e-12 + 1e-10 * np.abs(ref)), (s_, np.max(np.abs(S[s_] - ref)))
 
 
 def test_hub_kernel_flags_an_unsafe_boundary_pivot_and_refuses_other_structures():
