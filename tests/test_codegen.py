@@ -136,6 +136,47 @@ def test_two_sided_form_on_lossless_and_lossy_ladders(K, taps, lossy):
         assert st3 == engine.HVB_STATUS_RERUN                      # refused, never wrong silently
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_two_sided_form_fuzz_against_oracle(seed):
+    """Random chains (41-110 rows, 2-8 ports anywhere, random mix of inductors, capacitors, resistors, lossless and lossy
+    lines, some shunt loss) on the two-sided row loop: within the parity gate of the oracle, or refused (never wrong)."""
+    rng = np.random.default_rng(9000 + seed)
+    K = int(rng.integers(41, 111))
+    m = hv.Model(suppress_loadbar=True)
+    chain = [m.node() for _ in range(K + 1)]
+    taps = sorted(set(int(t) for t in rng.integers(0, K + 1, int(rng.integers(2, 9)))))
+    for t in taps:
+        m.new_port(float(rng.choice([25.0, 50.0, 75.0])), chain[t])
+    for k in range(K):
+        kind = int(rng.integers(0, 5))
+        if kind == 0:
+            m.inductor(chain[k], chain[k + 1], float(10 ** rng.uniform(-9.5, -8.3)))
+        elif kind == 1:
+            m.capacitor(chain[k], chain[k + 1], float(10 ** rng.uniform(-12.3, -11)))
+        elif kind == 2:
+            m.resistor(chain[k], chain[k + 1], float(rng.uniform(1, 60)))
+        elif kind == 3:
+            m.transmissionline(chain[k], chain[k + 1], float(rng.uniform(30, 90)), float(rng.uniform(2, 4)), float(rng.uniform(1e-3, 9e-3)))
+        else:
+            m.transmissionline(chain[k], chain[k + 1], float(rng.uniform(30, 90)), complex(rng.uniform(2, 4), -rng.uniform(0.01, 0.1)), float(rng.uniform(1e-3, 9e-3)))
+    for k in range(K + 1):
+        m.capacitor(chain[k], m.gnd, float(10 ** rng.uniform(-12.8, -11.8)))
+        if rng.random() < 0.2:
+            m.resistor(chain[k], m.gnd, float(rng.uniform(300, 5000)))
+    f = np.sort(10 ** rng.uniform(8.5, 9.9, 24))
+    ref = oracle_S(m, f)
+    S3, _, st3, g3 = sim(m, f, 3)
+    assert g3["rolled"]
+    if not g3["two_sided"]:                                       # no admissible cut for this draw: the one-sided loop serves it
+        assert len(taps) < 2 or st3 == 0
+    if st3 == 0:
+        assert np.all(np.abs(S3[0] - ref) <= 1e-12 + 1e-10 * np.abs(ref)), np.max(np.abs(S3[0] - ref))
+    else:
+        assert g3["two_sided"] and st3 == engine.HVB_STATUS_RERUN
+        S2, _, st2, _ = sim(m, f, 2)
+        assert st2 == 0 and np.all(np.abs(S2[0] - ref) <= 1e-12 + 1e-10 * np.abs(ref))
+
+
 def test_two_sided_form_needs_a_cut_between_ports_and_auto_mode_needs_a_saving():
     f = np.linspace(1e9, 3e9, 5)
     # one port, or all ports on one side of every admissible cut: no cut -> mode 3 quietly gives the one-sided row loop
