@@ -361,6 +361,25 @@ def test_hub_kernel_inversions_exchange_rows_when_they_must(seed):
     assert np.all(np.abs(S[0] - ref) <= 1e-12 + 1e-10 * np.abs(ref)), np.max(np.abs(S[0] - ref))
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_hub_kernel_fuzz_against_oracle(seed):
+    """Random hubs: 2-8 block ports, chains of 0-4 rows, ports anywhere or nowhere on them, half of the draws with a block
+    whose I + S needs row exchanges."""
+    rng = np.random.default_rng(77000 + seed)
+    nb = int(rng.integers(2, 9))
+    rows = tuple(int(x) for x in rng.integers(0, 5, nb))
+    port_on = [None if rng.random() < 0.25 else (int(rng.integers(0, rows[k] + 1)) if rows[k] > 0 else 0) for k in range(nb)]
+    if all(p is None for p in port_on):
+        port_on[0] = 0
+    sc, db = (1.0, 0.0) if rng.random() < 0.5 else (float(rng.uniform(0.05, 0.5)), float(rng.uniform(0.8, 1.0)))
+    m, f = circuits.build_hub(hv, nb, rows, tuple(port_on), seed=seed, nF=9, scale=sc, diag_bias=db)
+    S, _, status, gen = hub_sim(m, f)
+    ref = oracle_S(m, f)
+    assert status in (0, engine.HVB_STATUS_ZERO_PIVOT)            # refused (unsafe boundary pivot) is legal, wrong is not
+    if status == 0:
+        assert np.all(np.abs(S[0] - ref) <= 1e-12 + 1e-10 * np.abs(ref)), np.max(np.abs(S[0] - ref))
+
+
 def test_hub_kernel_with_monte_carlo_samples_and_tabulated_parts():
     """Kernel E with sample columns and host-tabulated callables on the chains, a port on a block node, a lossy line."""
     rng = np.random.default_rng(9)
